@@ -1,0 +1,194 @@
+/*
+ * pqt_b200.h -- C ABI of the B200-native Product-Quantization-Tree query engine
+ * (libpqt_b200.so).
+ *
+ * The reference has no FFI layer: its boundary is the C++ class
+ * pqt::PerturbationProTree (pqt/PerturbationProTree.hh:28-235) used directly by
+ * tool_query.cpp:92-155 and tool_createdb.cpp:74-114.  Every entry point below
+ * names the reference method it replaces (file:line into /root/reference).  The
+ * C++ mirror of that class over this ABI lives in
+ * product-quantization-tree_b200/host/PerturbationProTree.hh; INTEGRATION.md
+ * shows the binding a reference maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every call returns PQT_OK (0) or a
+ * negative pqt_status (the reference exit()s instead, utils/helper.hpp:7-15);
+ * pqt_last_error() returns the message of the last failing call on that handle.
+ * The caller owns every buffer it passes; the handle owns all device memory.
+ * One handle = one device + one stream; calls on one handle must be serialised
+ * by the caller (like the reference object, which is not re-entrant).
+ * There is no CPU fallback: without a CUDA device pqt_create() fails with
+ * PQT_ERR_CUDA.
+ */
+#ifndef PQT_B200_H
+#define PQT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PQT_ABI_VERSION 1
+
+typedef enum pqt_status {
+  PQT_OK = 0,
+  PQT_ERR_INVALID = -1,     /* bad argument / unsupported shape            */
+  PQT_ERR_STATE = -2,       /* call order (e.g. query before set_db)       */
+  PQT_ERR_IO = -3,          /* file could not be read / written            */
+  PQT_ERR_CUDA = -4,        /* CUDA runtime error (message has the detail) */
+  PQT_ERR_NOMEM = -5        /* device or host allocation failed            */
+} pqt_status;
+
+/* id written to result slots beyond the number of candidates found.  The
+ * reference leaves stale shared memory there (pqt/PerturbationProTree.cu:
+ * 5331-5346); the distance of such a slot is 1e7f exactly as in the reference. */
+#define PQT_PAD_IDX 0xFFFFFFFFu
+
+typedef struct pqt_index pqt_index; /* opaque: pqt::PerturbationProTree */
+
+/* The literals the reference hard-codes inside its methods;
+ * defaults reproduce them. */
+typedef struct pqt_params {
+  uint32_t k1;              /* L1 cells expanded per part in queries; 8 (pqt/PerturbationProTree.cu:8187) */
+  uint32_t max_bins;        /* 4096 (:8218)                                              */
+  uint32_t max_trials;      /* 16 (:3569)                                                */
+  uint32_t bin_threads;     /* 1024, probes per trial (:3556)                            */
+  uint32_t max_vec_per_bin; /* 2800 (:6208)                                              */
+  uint32_t hash_size;       /* HASH_SIZE 400000000 (pqt/PerturbationProTree.hh:12); the
+                               tools' --hashsize flag (tool_query.cpp:33)                */
+  uint32_t k1_build;        /* 16, L1 cells searched when binning DB vectors (:1237)     */
+  uint32_t max_vec;         /* 0 = reference behaviour: candidates re-ranked per query =
+                               pow2ceil(k) (:6159).  Non-zero (power of two >= k): fixed
+                               candidate budget, results = first k of that ranking
+                               (extension; lets k be small without shrinking the scan)  */
+  uint32_t reserved[8];
+} pqt_params;
+
+/* cumulative device-side timings of the query kernels (CUDA events on the
+ * handle's stream), filled only while profiling is enabled */
+typedef struct pqt_stats {
+  uint64_t calls;           /* pqt_query_knn calls measured                 */
+  uint64_t queries;         /* queries processed                            */
+  uint64_t candidates;      /* line-coded candidates scanned (sum of nVec)  */
+  uint64_t kernel_launches; /* kernels launched by the library              */
+  double ms_tables;         /* Steps A+B+C (distance-table build)           */
+  double ms_bins;           /* Step D+E1 (bin enumeration, candidate list)  */
+  double ms_scan;           /* Step E2 ADC scan over line codes             */
+  double ms_sort;           /* exact bitonic ranking + top-k emit           */
+  double ms_total;          /* first kernel start .. last kernel end        */
+  uint64_t scan_launches;   /* launches of the ADC scan kernel              */
+  uint64_t reserved[7];
+} pqt_stats;
+
+/* ---- lifetime ------------------------------------------------------------- */
+
+/* PerturbationProTree(uint dim, uint p, uint p2), pqt/PerturbationProTree.hh:37
+ * (+ cudaSetDevice, tool_query.cpp:74).  p2 must equal p. */
+int pqt_create(uint32_t dim, uint32_t p, uint32_t p2, int device, pqt_index **out);
+/* ~PerturbationProTree, pqt/PerturbationProTree.cu:37-58 */
+int pqt_destroy(pqt_index *h);
+const char *pqt_last_error(const pqt_index *h);
+int pqt_abi_version(void);
+
+void pqt_default_params(pqt_params *prm);
+int pqt_set_params(pqt_index *h, const pqt_params *prm);
+int pqt_get_params(const pqt_index *h, pqt_params *prm);
+/* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the
+ * handle's own stream.  The reference uses the default stream throughout. */
+int pqt_set_stream(pqt_index *h, void *cuda_stream);
+
+/* ---- index state (load path) ----------------------------------------------- */
+
+/* readTreeFromFile(name), pqt/PerturbationProTree.cu:118-220 (.ppqt: ASCII
+ * "dim p p2 c1 c2 nDBs", one skipped byte, float cb1[c1][dim],
+ * float cb2[p][c1][c2][dim/p]); overrides dim/p from the file like the reference */
+int pqt_read_tree(pqt_index *h, const char *path);
+/* writeTreeToFile(name), :60-116 */
+int pqt_write_tree(pqt_index *h, const char *path);
+/* codebooks straight from host memory (what createTree leaves in
+ * d_multiCodeBook / d_multiCodeBook2, :274-303) */
+int pqt_set_tree(pqt_index *h, uint32_t c1, uint32_t c2, const float *cb1, const float *cb2);
+int pqt_get_tree_shape(const pqt_index *h, uint32_t *dim, uint32_t *p, uint32_t *c1, uint32_t *c2);
+int pqt_get_tree(const pqt_index *h, float *cb1, float *cb2);
+
+/* setDB(N, prefix, counts, dbIdx), :1184-1229: HOST pointers, copied;
+ * prefix/counts have params.hash_size entries, dbIdx has N. */
+int pqt_set_db(pqt_index *h, uint32_t N, const uint32_t *prefix, const uint32_t *counts,
+               const uint32_t *db_idx);
+/* The line codes the reference keeps in d_lineLambda (lineDist :7663-7737 /
+ * prepareEmptyLambda pqt/PerturbationProTree.hh:103 + upload, test/test1B.cpp:
+ * 1181-1233): HOST lineDescr[N][LP] (4 bytes each, indexed by vector id).  Sets
+ * d_lineParts = LP.  Must follow pqt_set_db (codes are re-laid in bin order). */
+int pqt_set_lines(pqt_index *h, const uint32_t *lines, uint32_t N, uint32_t line_parts);
+
+/* ---- query (hot path) -------------------------------------------------------- */
+
+/* queryKNN(resIdx, resDist, Q, QN, k), :8179-8323.  Q: float[QN][dim], device
+ * pointer if q_on_device (as in the reference) else host.  idx/dist: [QN][k],
+ * device pointers if out_on_device else host.  Ascending by distance. */
+int pqt_query_knn(pqt_index *h, const float *Q, int q_on_device, uint32_t QN, uint32_t k,
+                  uint32_t *idx, float *dist, int out_on_device);
+
+/* ---- build side (creates the query path's inputs) ----------------------------- */
+
+/* buildKBestDB(A, N), :1231-1315 -- bins every vector (k1_build L1 cells), builds
+ * counts / exclusive prefix / ids grouped by bin (ascending id inside a bin) on
+ * the device and installs them as the DB (same state as pqt_set_db).
+ * X: float[N][dim], device pointer if x_on_device. */
+int pqt_build_kbest_db(pqt_index *h, const float *X, int x_on_device, uint32_t N);
+/* lineDist(DB, N), :7663-7737 with an explicit LP (the reference hard-sets 16):
+ * encodes and installs the line codes (same state as pqt_set_lines). */
+int pqt_line_dist(pqt_index *h, const float *X, int x_on_device, uint32_t N, uint32_t line_parts);
+/* getBinPrefix/getBinCounts/getDBIdx/getLine, pqt/PerturbationProTree.hh:97-101,
+ * as host copies (any pointer may be NULL) */
+int pqt_get_db(const pqt_index *h, uint32_t *prefix, uint32_t *counts, uint32_t *db_idx);
+int pqt_get_lines(const pqt_index *h, uint32_t *lines);
+int pqt_get_db_size(const pqt_index *h, uint32_t *N, uint32_t *line_parts);
+
+/* ---- multi-GPU: bin-range shards ---------------------------------------------- */
+
+/* Keep only the line codes / ids whose position in the bin-ordered list lies in
+ * this rank's slice (equal vector counts per rank, cut at bin boundaries).  Call
+ * between pqt_create and pqt_set_db.  world = 1 restores the single-GPU layout. */
+int pqt_set_shard(pqt_index *h, uint32_t rank, uint32_t world);
+/* Per-shard half of queryKNN: Steps A-E2 over this rank's candidates only.
+ * val/idx: DEVICE [QN][max_vec]; slots owned by other ranks hold +inf / 0 so that
+ * an element-wise min / max across ranks (one reduce-scatter or all-reduce)
+ * assembles exactly the single-GPU candidate arrays. */
+int pqt_query_scan_shard(pqt_index *h, const float *Q, int q_on_device, uint32_t QN, uint32_t k,
+                         float *val, uint32_t *idx);
+/* Ranking half: bitonic network over assembled val/idx (DEVICE [QN][max_vec]) and
+ * emit the first k per query, exactly like the tail of rerankKernelFast :5331-5346 */
+int pqt_rank_candidates(pqt_index *h, float *val, uint32_t *idx, uint32_t QN, uint32_t max_vec,
+                        uint32_t k, uint32_t *out_idx, float *out_dist, int out_on_device);
+/* pow2ceil(k) or params.max_vec: row length of the candidate arrays */
+int pqt_candidate_width(const pqt_index *h, uint32_t k, uint32_t *max_vec);
+
+/* ---- measurement / introspection ------------------------------------------------ */
+
+int pqt_profile_enable(pqt_index *h, int on); /* per-kernel CUDA-event timing */
+int pqt_get_stats(const pqt_index *h, pqt_stats *st);
+int pqt_reset_stats(pqt_index *h);
+
+/* Per-query intermediates of the last pqt_query_knn call,
+ * recorded only while pqt_debug_enable(h, 1); copied to HOST buffers. */
+typedef enum pqt_stage {
+  PQT_STAGE_ASSIGN = 0,     /* uint32 [QN][k1][p]        Step A  */
+  PQT_STAGE_LUT = 1,        /* float  [QN][LP][c1]       Step B  */
+  PQT_STAGE_ASSIGN_VAL = 2, /* float  [QN][p][k1*c2]     Step C  */
+  PQT_STAGE_ASSIGN_IDX = 3, /* uint32 [QN][p][k1*c2]     Step C  */
+  PQT_STAGE_BINS = 4,       /* uint32 [QN][max_bins]     Step D  */
+  PQT_STAGE_NBINS = 5,      /* uint32 [QN]               Step D  */
+  PQT_STAGE_SELECT_IDX = 6, /* uint32 [QN][max_vec]      Step E1 */
+  PQT_STAGE_NVEC = 7,       /* uint32 [QN]               Step E1 */
+  PQT_STAGE_CB_DIST = 8,    /* float  [c1][c1][LP]       computeCBL1L1Dist :1902-1917 */
+  PQT_STAGE_DIST_SEQ = 9    /* uint32 [65536]            prepareDistSequence pqt/ProTree.cu:128-207 */
+} pqt_stage;
+int pqt_debug_enable(pqt_index *h, int on);
+int pqt_debug_stage(const pqt_index *h, int stage, void *host_out, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PQT_B200_H */

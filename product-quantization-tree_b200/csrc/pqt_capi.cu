@@ -1,0 +1,958 @@
+// pqt_capi.cu -- the C ABI of include/pqt_b200.h over the sm_100a kernels.
+//
+// Host-side orchestration only: handle state, load-time preparation, launches.
+// Reference citations are file:line into /root/reference.
+#include "../../include/pqt_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "build_kernels.cuh"
+#include "common.cuh"
+#include "index_kernels.cuh"
+#include "query_kernels.cuh"
+
+using namespace pqtb;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
+}  // namespace
+
+struct pqt_index {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  mutable std::string err;
+  pqt_params prm{};
+
+  // tree (readTreeFromFile / createTree state)
+  uint32_t dim = 0, p = 0, c1 = 0, c2 = 0, vl = 0;
+  std::vector<float> h_cb1, h_cb2;
+  DevBuf d_cb1, d_cb2;
+
+  // traversal order (prepareDistSequence), cached per (m, p)
+  DevBuf d_distseq;
+  std::vector<uint32_t> h_distseq;
+  uint32_t seq_m = 0, seq_p = 0;
+
+  // DB (setDB / buildKBestDB state)
+  bool has_db = false;
+  uint32_t N = 0;
+  uint32_t rank = 0, world = 1;
+  uint32_t pos_lo = 0, pos_hi = 0;
+  uint32_t db_hash_size = 0;
+  uint32_t n_nonempty = 0;
+  DevBuf d_bitmap, d_rank_base, d_cprefix, d_dbidx;  // d_dbidx: full [N], bin order
+
+  // line codes (lineDist / prepareEmptyLambda state)
+  bool has_lines = false;
+  uint32_t LP = 0, sl = 0;
+  DevBuf d_codes;  // [pos_hi - pos_lo][LP], bin order
+  DevBuf d_cbd, d_cbd_dup;
+
+  // per-batch scratch
+  DevBuf s_q, s_lut, s_idx16, s_cand, s_nvec, s_val, s_idx, s_outd, s_outi;
+  // debug
+  bool debug = false;
+  uint32_t dbg_QN = 0, dbg_k = 0, dbg_maxvec = 0;
+  DevBuf g_assign, g_lut, g_aval, g_aidx, g_bins, g_nbins, g_sel;
+
+  // profiling
+  bool profile = false;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  pqt_stats stats{};
+};
+
+namespace {
+
+int fail(const pqt_index* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  return code;
+}
+
+#define CU_TRY(h, call)                                                                  \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess)                                                              \
+      return fail(h, e__ == cudaErrorMemoryAllocation ? PQT_ERR_NOMEM : PQT_ERR_CUDA,    \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__,     \
+                  __LINE__);                                                             \
+  } while (0)
+
+#define PQ_TRY(call)          \
+  do {                        \
+    int rc__ = (call);        \
+    if (rc__ != PQT_OK) return rc__; \
+  } while (0)
+
+bool is_pow2(uint32_t x) { return x && !(x & (x - 1)); }
+
+int check_tree_shape(const pqt_index* h, uint32_t dim, uint32_t p, uint32_t c1, uint32_t c2) {
+  if (!dim || !p || !c1 || !c2) return fail(h, PQT_ERR_INVALID, "zero-sized tree shape");
+  if (dim % p) return fail(h, PQT_ERR_INVALID, "dim %u not divisible by p %u", dim, p);
+  uint32_t vl = dim / p;
+  if (!is_pow2(vl) || vl > 128)
+    return fail(h, PQT_ERR_INVALID,
+                "segment length dim/p = %u must be a power of two <= 128 (the reference's tree "
+                "reduction, pqt/PerturbationProTree.cu:7151-7159, needs 2^n)",
+                vl);
+  if (p > 8) return fail(h, PQT_ERR_INVALID, "p = %u > 8 (16^p traversal codes overflow uint32)", p);
+  if (c1 > 127) return fail(h, PQT_ERR_INVALID, "c1 = %u > 127 (lineDescr stores char p1, p2)", c1);
+  if (pow2ceil(c1) > 1024) return fail(h, PQT_ERR_INVALID, "c1 too large");
+  return PQT_OK;
+}
+
+// ---- prepareDistSequence (pqt/ProTree.cu:128-207) on the host, cached ---------------
+int ensure_dist_seq(pqt_index* h, uint32_t max_cluster) {
+  uint32_t m = max_cluster > 16 ? 16 : max_cluster;
+  if (h->d_distseq.p && h->seq_m == m && h->seq_p == h->p) return PQT_OK;
+  uint64_t n64 = 1;
+  for (uint32_t j = 0; j < h->p; j++) n64 *= m;
+  uint32_t nvec = (uint32_t)n64;
+  std::vector<std::pair<float, uint32_t>> d(nvec);
+  std::vector<uint32_t> den(h->p);
+  den[0] = 1;
+  for (uint32_t j = 1; j < h->p; j++) den[j] = den[j - 1] * m;
+  for (uint32_t i = 0; i < nvec; i++) {
+    float dist = 0.f;
+    for (uint32_t j = 0; j < h->p; j++) dist += std::sqrt((float)((i / den[j]) % m));
+    d[i] = std::make_pair(dist, i);
+  }
+  std::sort(d.begin(), d.end());
+  h->h_distseq.assign(kNumDistSeq, 0u);
+  uint32_t keep = std::min<uint32_t>(nvec, kNumDistSeq);
+  for (uint32_t i = 0; i < keep; i++) h->h_distseq[i] = d[i].second;
+  CU_TRY(h, h->d_distseq.ensure(kNumDistSeq * sizeof(uint32_t)));
+  CU_TRY(h, cudaMemcpyAsync(h->d_distseq.p, h->h_distseq.data(), kNumDistSeq * sizeof(uint32_t),
+                            cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  h->seq_m = m;
+  h->seq_p = h->p;
+  return PQT_OK;
+}
+
+int upload_tree(pqt_index* h) {
+  CU_TRY(h, h->d_cb1.ensure(h->h_cb1.size() * sizeof(float)));
+  CU_TRY(h, h->d_cb2.ensure(h->h_cb2.size() * sizeof(float)));
+  CU_TRY(h, cudaMemcpyAsync(h->d_cb1.p, h->h_cb1.data(), h->h_cb1.size() * sizeof(float),
+                            cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(h, cudaMemcpyAsync(h->d_cb2.p, h->h_cb2.data(), h->h_cb2.size() * sizeof(float),
+                            cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  h->has_lines = false;  // cbDist depends on cb1
+  return PQT_OK;
+}
+
+uint32_t candidate_width(const pqt_index* h, uint32_t k) {
+  return h->prm.max_vec ? h->prm.max_vec : pow2ceil(k);
+}
+
+// ---- builds bitmap / rank_base / cprefix from dense device arrays ---------------------
+int build_directory(pqt_index* h, const uint32_t* d_counts, const uint32_t* d_prefix,
+                    uint32_t hash_size, uint32_t N) {
+  const size_t nwords = ((size_t)hash_size + 31) >> 5;
+  const size_t ngroups = (nwords + 7) >> 3;
+  CU_TRY(h, h->d_bitmap.ensure((ngroups * 8) * sizeof(uint32_t)));
+  CU_TRY(h, cudaMemsetAsync(h->d_bitmap.p, 0, ngroups * 8 * sizeof(uint32_t), h->stream));
+  CU_TRY(h, h->d_rank_base.ensure((ngroups + 1) * sizeof(uint32_t)));
+  DevBuf tmp;
+  CU_TRY(h, tmp.ensure(scan_tmp_words(ngroups + 1) * sizeof(uint32_t)));
+  const int blocks = h->num_sms * 8;
+  bitmap_build_kernel<<<blocks, 256, 0, h->stream>>>(d_counts, hash_size, h->d_bitmap.as<uint32_t>());
+  CU_TRY(h, cudaMemsetAsync(h->d_rank_base.p, 0, (ngroups + 1) * sizeof(uint32_t), h->stream));
+  group_popc_kernel<<<blocks, 256, 0, h->stream>>>(h->d_bitmap.as<uint32_t>(), nwords, ngroups,
+                                                   h->d_rank_base.as<uint32_t>());
+  device_exscan_u32(h->d_rank_base.as<uint32_t>(), h->d_rank_base.as<uint32_t>(), ngroups + 1,
+                    tmp.as<uint32_t>(), h->stream);
+  uint32_t nne = 0;
+  CU_TRY(h, cudaMemcpyAsync(&nne, h->d_rank_base.as<uint32_t>() + ngroups, sizeof(uint32_t),
+                            cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  h->n_nonempty = nne;
+  CU_TRY(h, h->d_cprefix.ensure(((size_t)nne + 2) * sizeof(uint32_t)));
+  cprefix_fill_kernel<<<blocks, 256, 0, h->stream>>>(d_counts, d_prefix, hash_size,
+                                                     h->d_bitmap.as<uint32_t>(),
+                                                     h->d_rank_base.as<uint32_t>(),
+                                                     h->d_cprefix.as<uint32_t>());
+  CU_TRY(h, cudaMemcpyAsync(h->d_cprefix.as<uint32_t>() + nne, &N, sizeof(uint32_t),
+                            cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaGetLastError());
+  tmp.release();
+  h->db_hash_size = hash_size;
+  h->N = N;
+  h->pos_lo = (uint32_t)((uint64_t)N * h->rank / h->world);
+  h->pos_hi = (uint32_t)((uint64_t)N * (h->rank + 1) / h->world);
+  h->has_db = true;
+  h->has_lines = false;
+  return PQT_OK;
+}
+
+int check_lp(const pqt_index* h, uint32_t LP) {
+  if (!LP || h->dim % LP) return fail(h, PQT_ERR_INVALID, "dim %u not divisible by lineparts %u", h->dim, LP);
+  uint32_t sl = h->dim / LP;
+  if (!is_pow2(LP) || LP > 32)
+    return fail(h, PQT_ERR_INVALID,
+                "lineparts = %u must be a power of two <= 32 (warp-shuffle reduction, "
+                "pqt/PerturbationProTree.cu:5183-5187)",
+                LP);
+  if (!is_pow2(sl) || sl > 128) return fail(h, PQT_ERR_INVALID, "dim/lineparts = %u must be 2^n <= 128", sl);
+  return PQT_OK;
+}
+
+int compute_cbd(pqt_index* h, uint32_t LP) {
+  const size_t n = (size_t)h->c1 * h->c1 * LP;
+  CU_TRY(h, h->d_cbd.ensure(n * sizeof(float)));
+  CU_TRY(h, h->d_cbd_dup.ensure((size_t)h->c1 * h->c1 * 32 * sizeof(float)));
+  cb_dist_kernel<<<64, 256, 0, h->stream>>>(h->d_cb1.as<float>(), h->c1, h->dim, LP, h->dim / LP,
+                                            h->d_cbd.as<float>(), h->d_cbd_dup.as<float>());
+  CU_TRY(h, cudaGetLastError());
+  return PQT_OK;
+}
+
+struct QueryPlan {
+  uint32_t QN, k, max_vec;
+  const float* dQ;
+};
+
+// Steps A..E2 (distance part) for QN queries already on the device; fills
+// val/idx [QN][max_vec].  Records profile events ev[0..3] when enabled.
+int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float* d_val,
+                   uint32_t* d_idx) {
+  const uint32_t max_vec = candidate_width(h, k);
+  const pqt_params& P = h->prm;
+  PQ_TRY(ensure_dist_seq(h, h->c2 * P.k1));  // :8191
+  const uint32_t m = h->seq_m;
+  const uint32_t n = P.k1 * h->c2;
+  if (m > n) return fail(h, PQT_ERR_INVALID, "k1*c2 < traversal width");
+
+  CU_TRY(h, h->s_lut.ensure((size_t)QN * h->c1 * 32 * sizeof(float)));
+  CU_TRY(h, h->s_idx16.ensure((size_t)QN * h->p * 16 * sizeof(uint32_t)));
+  CU_TRY(h, h->s_cand.ensure((size_t)QN * max_vec * sizeof(uint32_t)));
+  CU_TRY(h, h->s_nvec.ensure((size_t)QN * sizeof(uint32_t)));
+  if (h->debug) {
+    CU_TRY(h, h->g_assign.ensure((size_t)QN * P.k1 * h->p * 4));
+    CU_TRY(h, h->g_lut.ensure((size_t)QN * h->LP * h->c1 * 4));
+    CU_TRY(h, h->g_aval.ensure((size_t)QN * h->p * n * 4));
+    CU_TRY(h, h->g_aidx.ensure((size_t)QN * h->p * n * 4));
+    CU_TRY(h, h->g_bins.ensure((size_t)QN * P.max_bins * 4));
+    CU_TRY(h, h->g_nbins.ensure((size_t)QN * 4));
+    CU_TRY(h, h->g_sel.ensure((size_t)QN * max_vec * 4));
+    h->dbg_QN = QN;
+    h->dbg_k = k;
+    h->dbg_maxvec = max_vec;
+  }
+
+  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[0], h->stream));
+  // ---- Steps A+B+C
+  {
+    TablesArgs a{};
+    a.Q = dQ;
+    a.cb1 = h->d_cb1.as<float>();
+    a.cb2 = h->d_cb2.as<float>();
+    a.QN = QN; a.dim = h->dim; a.p = h->p; a.c1 = h->c1; a.c2 = h->c2; a.LP = h->LP;
+    a.k1 = P.k1; a.vl = h->vl; a.sl = h->sl;
+    a.npA = pow2ceil(h->c1);
+    a.npC = pow2ceil(n);
+    a.m = m;
+    a.lut_dup = h->s_lut.as<float>();
+    a.idx16 = h->s_idx16.as<uint32_t>();
+    if (h->debug) {
+      a.dbg_assign = h->g_assign.as<uint32_t>();
+      a.dbg_lut = h->g_lut.as<float>();
+      a.dbg_aval = h->g_aval.as<float>();
+      a.dbg_aidx = h->g_aidx.as<uint32_t>();
+    }
+    const uint32_t npMax = std::max(a.npA, a.npC);
+    size_t smem = (size_t)(h->dim + 2 * h->p * npMax + P.k1 * h->p) * 4;
+    if (smem > 48 * 1024)
+      CU_TRY(h, cudaFuncSetAttribute(tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 16);
+    tables_kernel<<<grid, 128, smem, h->stream>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    h->stats.kernel_launches++;
+  }
+  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[1], h->stream));
+  // ---- Steps D+E1
+  {
+    BinsArgs a{};
+    a.idx16 = h->s_idx16.as<uint32_t>();
+    a.dist_seq = h->d_distseq.as<uint32_t>();
+    a.dir.bitmap = h->d_bitmap.as<uint32_t>();
+    a.dir.rank_base = h->d_rank_base.as<uint32_t>();
+    a.dir.cprefix = h->d_cprefix.as<uint32_t>();
+    a.hash = make_fastmod(h->db_hash_size);
+    a.QN = QN; a.p = h->p; a.m = m; a.c1c2 = h->c1 * h->c2;
+    a.max_bins = P.max_bins; a.max_trials = P.max_trials; a.bin_threads = P.bin_threads;
+    a.max_vec_per_bin = P.max_vec_per_bin; a.max_vec = max_vec;
+    a.cand_pos = h->s_cand.as<uint32_t>();
+    a.n_vec = h->s_nvec.as<uint32_t>();
+    if (h->debug) {
+      a.dbg_bins = h->g_bins.as<uint32_t>();
+      a.dbg_nbins = h->g_nbins.as<uint32_t>();
+    }
+    size_t smem = (size_t)(P.max_bins + h->p * 16 + 32) * 4;
+    if (smem > 48 * 1024)
+      CU_TRY(h, cudaFuncSetAttribute(bins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 8);
+    bins_kernel<<<grid, kBinsThreads, smem, h->stream>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    h->stats.kernel_launches++;
+  }
+  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+  // ---- Step E2: ADC scan
+  {
+    ScanArgs a{};
+    a.codes = h->d_codes.as<uint32_t>();
+    a.ids = h->d_dbidx.as<uint32_t>() + h->pos_lo;
+    a.cand_pos = h->s_cand.as<uint32_t>();
+    a.n_vec = h->s_nvec.as<uint32_t>();
+    a.lut_dup = h->s_lut.as<float>();
+    a.cbd_dup = h->d_cbd_dup.as<float>();
+    a.QN = QN; a.c1 = h->c1; a.max_vec = max_vec;
+    a.pos_lo = h->pos_lo; a.pos_hi = h->pos_hi;
+    a.owns_pad = (h->rank == 0) ? 1u : 0u;
+    a.sharded = h->world > 1 ? 1u : 0u;
+    a.out_val = d_val;
+    a.out_idx = d_idx;
+    size_t smem = ((size_t)h->c1 * h->c1 * 32 + 2 * (size_t)h->c1 * 32) * 4 + 64;
+    if (smem <= 220 * 1024) {
+      uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms);
+#define LAUNCH_SCAN(LPV)                                                                         \
+  do {                                                                                           \
+    CU_TRY(h, cudaFuncSetAttribute(adc_scan_kernel<LPV>,                                         \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    adc_scan_kernel<LPV><<<grid, kScanThreads, smem, h->stream>>>(a);                            \
+  } while (0)
+      switch (h->LP) {
+        case 1: LAUNCH_SCAN(1); break;
+        case 2: LAUNCH_SCAN(2); break;
+        case 4: LAUNCH_SCAN(4); break;
+        case 8: LAUNCH_SCAN(8); break;
+        case 16: LAUNCH_SCAN(16); break;
+        default: LAUNCH_SCAN(32); break;
+      }
+#undef LAUNCH_SCAN
+    } else {
+      // c1 > 32: tables do not fit in shared memory; canonical-layout fallback
+      if (!h->debug) CU_TRY(h, h->g_lut.ensure((size_t)QN * h->LP * h->c1 * 4));
+      return fail(h, PQT_ERR_INVALID, "c1 = %u > 32 is not supported by the ADC scan yet", h->c1);
+    }
+    CU_TRY(h, cudaGetLastError());
+    h->stats.kernel_launches++;
+    h->stats.scan_launches++;
+  }
+  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+  if (h->debug && h->world == 1) {
+    gather_select_idx_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(
+        h->s_cand.as<uint32_t>(), h->s_nvec.as<uint32_t>(), h->d_dbidx.as<uint32_t>(), QN, max_vec,
+        h->g_sel.as<uint32_t>());
+    CU_TRY(h, cudaGetLastError());
+  }
+  return PQT_OK;
+}
+
+int run_rank(pqt_index* h, const float* d_val, const uint32_t* d_idx, uint32_t QN, uint32_t max_vec,
+             uint32_t k, float* d_out_dist, uint32_t* d_out_idx) {
+  if (!is_pow2(max_vec) || max_vec > 4096)
+    return fail(h, PQT_ERR_INVALID, "candidate width %u must be a power of two <= 4096", max_vec);
+  if (k > max_vec) return fail(h, PQT_ERR_INVALID, "k %u > candidate width %u", k, max_vec);
+  RankArgs a{};
+  a.val = d_val; a.idx = d_idx; a.QN = QN; a.max_vec = max_vec; a.k = k;
+  a.out_dist = d_out_dist; a.out_idx = d_out_idx;
+  size_t smem = (size_t)max_vec * 8;
+  uint32_t threads = std::min<uint32_t>(kRankThreads, std::max<uint32_t>(32, max_vec / 2));
+  uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 4);
+  rank_kernel<<<grid, threads, smem, h->stream>>>(a);
+  CU_TRY(h, cudaGetLastError());
+  h->stats.kernel_launches++;
+  return PQT_OK;
+}
+
+int check_query_state(const pqt_index* h, uint32_t QN, uint32_t k) {
+  if (!h->c1) return fail(h, PQT_ERR_STATE, "no tree loaded (pqt_read_tree / pqt_set_tree)");
+  if (!h->has_db) return fail(h, PQT_ERR_STATE, "no DB loaded (pqt_set_db / pqt_build_kbest_db)");
+  if (!h->has_lines)
+    return fail(h, PQT_ERR_STATE,
+                "no line codes loaded (pqt_set_lines / pqt_line_dist); the reference would "
+                "divide by d_lineParts = 0 here (pqt/PerturbationProTree.cu:5281)");
+  if (!QN || !k) return fail(h, PQT_ERR_INVALID, "QN and k must be non-zero");
+  const pqt_params& P = h->prm;
+  if (P.k1 > h->c1) return fail(h, PQT_ERR_INVALID, "k1 %u > c1 %u", P.k1, h->c1);
+  if ((uint64_t)P.max_trials * P.bin_threads > kNumDistSeq)
+    return fail(h, PQT_ERR_INVALID, "max_trials * bin_threads exceeds the %u traversal codes", kNumDistSeq);
+  if (P.bin_threads > 16u * kBinsThreads) return fail(h, PQT_ERR_INVALID, "bin_threads > %u", 16 * kBinsThreads);
+  if (pow2ceil(P.k1 * h->c2) > 1024) return fail(h, PQT_ERR_INVALID, "k1*c2 > 1024");
+  if (P.max_bins < 2 || P.max_bins > 8192) return fail(h, PQT_ERR_INVALID, "max_bins out of range");
+  uint32_t mv = candidate_width(h, k);
+  if (!is_pow2(mv) || mv > 4096 || mv < k)
+    return fail(h, PQT_ERR_INVALID,
+                "candidate width %u (pow2ceil(k) or params.max_vec) must be a power of two in "
+                "[k, 4096]",
+                mv);
+  if (P.hash_size != h->db_hash_size) return fail(h, PQT_ERR_STATE, "hash_size changed after the DB was set");
+  return PQT_OK;
+}
+
+void accumulate_profile(pqt_index* h, uint32_t QN, bool with_rank) {
+  float t = 0;
+  cudaEventElapsedTime(&t, h->ev[0], h->ev[1]);
+  h->stats.ms_tables += t;
+  cudaEventElapsedTime(&t, h->ev[1], h->ev[2]);
+  h->stats.ms_bins += t;
+  cudaEventElapsedTime(&t, h->ev[2], h->ev[3]);
+  h->stats.ms_scan += t;
+  if (with_rank) {
+    cudaEventElapsedTime(&t, h->ev[4], h->ev[5]);
+    h->stats.ms_sort += t;
+    cudaEventElapsedTime(&t, h->ev[0], h->ev[5]);
+  } else {
+    cudaEventElapsedTime(&t, h->ev[0], h->ev[3]);
+  }
+  h->stats.ms_total += t;
+  h->stats.calls++;
+  h->stats.queries += QN;
+  std::vector<uint32_t> nv(QN);
+  cudaMemcpy(nv.data(), h->s_nvec.p, (size_t)QN * 4, cudaMemcpyDeviceToHost);
+  uint64_t s = 0;
+  for (uint32_t v : nv) s += v;
+  h->stats.candidates += s;
+}
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+int pqt_abi_version(void) { return PQT_ABI_VERSION; }
+
+void pqt_default_params(pqt_params* prm) {
+  std::memset(prm, 0, sizeof(*prm));
+  prm->k1 = 8;
+  prm->max_bins = 4096;
+  prm->max_trials = 16;
+  prm->bin_threads = 1024;
+  prm->max_vec_per_bin = 2800;
+  prm->hash_size = 400000000u;
+  prm->k1_build = 16;
+  prm->max_vec = 0;
+}
+
+int pqt_create(uint32_t dim, uint32_t p, uint32_t p2, int device, pqt_index** out) {
+  if (!out) return PQT_ERR_INVALID;
+  *out = nullptr;
+  if (p2 != p || !dim || !p) return PQT_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return PQT_ERR_CUDA;  // no CPU fallback
+  if (device < 0 || device >= ndev) return PQT_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return PQT_ERR_CUDA;
+  pqt_index* h = new pqt_index();
+  h->device = device;
+  h->dim = dim;
+  h->p = p;
+  pqt_default_params(&h->prm);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return PQT_ERR_CUDA;
+  }
+  h->stream = h->own_stream;
+  for (auto& e : h->ev) cudaEventCreate(&e);
+  *out = h;
+  return PQT_OK;
+}
+
+int pqt_destroy(pqt_index* h) {
+  if (!h) return PQT_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (DevBuf* b : {&h->d_cb1, &h->d_cb2, &h->d_distseq, &h->d_bitmap, &h->d_rank_base, &h->d_cprefix,
+                    &h->d_dbidx, &h->d_codes, &h->d_cbd, &h->d_cbd_dup, &h->s_q, &h->s_lut, &h->s_idx16,
+                    &h->s_cand, &h->s_nvec, &h->s_val, &h->s_idx, &h->s_outd, &h->s_outi, &h->g_assign,
+                    &h->g_lut, &h->g_aval, &h->g_aidx, &h->g_bins, &h->g_nbins, &h->g_sel})
+    b->release();
+  for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return PQT_OK;
+}
+
+const char* pqt_last_error(const pqt_index* h) { return h ? h->err.c_str() : "null handle"; }
+
+int pqt_set_params(pqt_index* h, const pqt_params* prm) {
+  if (!h || !prm) return PQT_ERR_INVALID;
+  if (!prm->k1 || !prm->max_bins || !prm->max_trials || !prm->bin_threads || !prm->hash_size ||
+      !prm->k1_build)
+    return fail(h, PQT_ERR_INVALID, "zero parameter");
+  if (prm->max_vec && !is_pow2(prm->max_vec)) return fail(h, PQT_ERR_INVALID, "max_vec must be a power of two");
+  h->prm = *prm;
+  return PQT_OK;
+}
+
+int pqt_get_params(const pqt_index* h, pqt_params* prm) {
+  if (!h || !prm) return PQT_ERR_INVALID;
+  *prm = h->prm;
+  return PQT_OK;
+}
+
+int pqt_set_stream(pqt_index* h, void* cuda_stream) {
+  if (!h) return PQT_ERR_INVALID;
+  cudaStreamSynchronize(h->stream);
+  h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  return PQT_OK;
+}
+
+// ---- tree ---------------------------------------------------------------------------
+int pqt_set_tree(pqt_index* h, uint32_t c1, uint32_t c2, const float* cb1, const float* cb2) {
+  if (!h || !cb1 || !cb2) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  PQ_TRY(check_tree_shape(h, h->dim, h->p, c1, c2));
+  h->c1 = c1;
+  h->c2 = c2;
+  h->vl = h->dim / h->p;
+  h->h_cb1.assign(cb1, cb1 + (size_t)c1 * h->dim);
+  h->h_cb2.assign(cb2, cb2 + (size_t)c1 * c2 * h->dim);
+  return upload_tree(h);
+}
+
+int pqt_read_tree(pqt_index* h, const char* path) {
+  if (!h || !path) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  std::ifstream f(path, std::ios::in | std::ios::binary);
+  if (!f.good()) return fail(h, PQT_ERR_IO, "cannot open %s", path);
+  uint32_t dim = 0, p = 0, p2 = 0, c1 = 0, c2 = 0, ndb = 0;
+  f >> dim >> p >> p2 >> c1 >> c2 >> ndb;
+  if (!f.good()) return fail(h, PQT_ERR_IO, "%s: bad .ppqt header", path);
+  f.ignore(1);
+  if (ndb != 1) return fail(h, PQT_ERR_INVALID, "%s: nDBs = %u (only 1 is supported: perturbations were removed from the reference)", path, ndb);
+  if (p2 != p) return fail(h, PQT_ERR_INVALID, "%s: p2 != p", path);
+  PQ_TRY(check_tree_shape(h, dim, p, c1, c2));
+  std::vector<float> cb1((size_t)c1 * dim), cb2((size_t)c1 * c2 * dim);
+  f.read(reinterpret_cast<char*>(cb1.data()), cb1.size() * sizeof(float));
+  f.read(reinterpret_cast<char*>(cb2.data()), cb2.size() * sizeof(float));
+  if (!f.good() && !f.eof()) return fail(h, PQT_ERR_IO, "%s: read error", path);
+  if ((size_t)f.gcount() != cb2.size() * sizeof(float))
+    return fail(h, PQT_ERR_IO, "%s: truncated codebooks (the reference would silently read garbage)", path);
+  h->dim = dim;  // the file overrides the constructor arguments (:120-125)
+  h->p = p;
+  h->c1 = c1;
+  h->c2 = c2;
+  h->vl = dim / p;
+  h->h_cb1.swap(cb1);
+  h->h_cb2.swap(cb2);
+  return upload_tree(h);
+}
+
+int pqt_write_tree(pqt_index* h, const char* path) {
+  if (!h || !path) return PQT_ERR_INVALID;
+  if (!h->c1) return fail(h, PQT_ERR_STATE, "no tree to write");
+  std::ofstream f(path, std::ios::out | std::ios::binary);
+  if (!f.good()) return fail(h, PQT_ERR_IO, "cannot open %s for writing", path);
+  f << h->dim << std::endl << h->p << std::endl << h->p << std::endl;
+  f << h->c1 << std::endl << h->c2 << std::endl << 1 << std::endl;
+  f.write(reinterpret_cast<const char*>(h->h_cb1.data()), h->h_cb1.size() * sizeof(float));
+  f.write(reinterpret_cast<const char*>(h->h_cb2.data()), h->h_cb2.size() * sizeof(float));
+  f.close();
+  if (!f.good()) return fail(h, PQT_ERR_IO, "write error on %s", path);
+  return PQT_OK;
+}
+
+int pqt_get_tree_shape(const pqt_index* h, uint32_t* dim, uint32_t* p, uint32_t* c1, uint32_t* c2) {
+  if (!h) return PQT_ERR_INVALID;
+  if (dim) *dim = h->dim;
+  if (p) *p = h->p;
+  if (c1) *c1 = h->c1;
+  if (c2) *c2 = h->c2;
+  return PQT_OK;
+}
+
+int pqt_get_tree(const pqt_index* h, float* cb1, float* cb2) {
+  if (!h) return PQT_ERR_INVALID;
+  if (!h->c1) return fail(h, PQT_ERR_STATE, "no tree loaded");
+  if (cb1) std::memcpy(cb1, h->h_cb1.data(), h->h_cb1.size() * sizeof(float));
+  if (cb2) std::memcpy(cb2, h->h_cb2.data(), h->h_cb2.size() * sizeof(float));
+  return PQT_OK;
+}
+
+// ---- DB -----------------------------------------------------------------------------
+int pqt_set_shard(pqt_index* h, uint32_t rank, uint32_t world) {
+  if (!h || !world || rank >= world) return PQT_ERR_INVALID;
+  if (h->has_db && (rank != h->rank || world != h->world))
+    return fail(h, PQT_ERR_STATE, "pqt_set_shard must precede pqt_set_db");
+  h->rank = rank;
+  h->world = world;
+  return PQT_OK;
+}
+
+int pqt_set_db(pqt_index* h, uint32_t N, const uint32_t* prefix, const uint32_t* counts,
+               const uint32_t* db_idx) {
+  if (!h || !prefix || !counts || !db_idx || !N) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  const uint32_t hs = h->prm.hash_size;
+  DevBuf d_counts, d_prefix;
+  CU_TRY(h, d_counts.ensure((size_t)hs * 4));
+  CU_TRY(h, d_prefix.ensure((size_t)hs * 4));
+  // chunked H2D like the reference (:1212-1222); host memory may be pageable
+  const size_t chunk = 100000000;
+  for (size_t off = 0; off < hs; off += chunk) {
+    size_t n = std::min(chunk, (size_t)hs - off);
+    CU_TRY(h, cudaMemcpyAsync(d_counts.as<uint32_t>() + off, counts + off, n * 4, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(d_prefix.as<uint32_t>() + off, prefix + off, n * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  CU_TRY(h, h->d_dbidx.ensure((size_t)N * 4));
+  CU_TRY(h, cudaMemcpyAsync(h->d_dbidx.p, db_idx, (size_t)N * 4, cudaMemcpyHostToDevice, h->stream));
+  int rc = build_directory(h, d_counts.as<uint32_t>(), d_prefix.as<uint32_t>(), hs, N);
+  d_counts.release();
+  d_prefix.release();
+  return rc;
+}
+
+int pqt_set_lines(pqt_index* h, const uint32_t* lines, uint32_t N, uint32_t line_parts) {
+  if (!h || !lines) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (!h->c1) return fail(h, PQT_ERR_STATE, "pqt_set_lines needs the tree (cbDist is derived from cb1)");
+  if (!h->has_db) return fail(h, PQT_ERR_STATE, "pqt_set_lines must follow pqt_set_db (codes are stored in bin order)");
+  if (N != h->N) return fail(h, PQT_ERR_INVALID, "N = %u differs from the DB's %u", N, h->N);
+  PQ_TRY(check_lp(h, line_parts));
+  const uint32_t LP = line_parts;
+  h->LP = LP;
+  h->sl = h->dim / LP;
+  PQ_TRY(compute_cbd(h, LP));
+  const uint32_t n_local = h->pos_hi - h->pos_lo;
+  CU_TRY(h, h->d_codes.ensure(std::max<size_t>((size_t)n_local * LP * 4, 16)));
+  DevBuf inv, stage;
+  CU_TRY(h, inv.ensure((size_t)N * 4));
+  invert_perm_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->d_dbidx.as<uint32_t>(), N, inv.as<uint32_t>());
+  const uint32_t chunk = 4u << 20;
+  CU_TRY(h, stage.ensure((size_t)std::min(chunk, N) * LP * 4));
+  for (uint32_t id0 = 0; id0 < N; id0 += chunk) {
+    uint32_t n = std::min(chunk, N - id0);
+    CU_TRY(h, cudaMemcpyAsync(stage.p, lines + (size_t)id0 * LP, (size_t)n * LP * 4, cudaMemcpyHostToDevice, h->stream));
+    scatter_codes_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(
+        stage.as<uint32_t>(), id0, n, LP, inv.as<uint32_t>(), h->pos_lo, h->pos_hi, h->d_codes.as<uint32_t>());
+    CU_TRY(h, cudaStreamSynchronize(h->stream));  // staging buffer reuse
+  }
+  CU_TRY(h, cudaGetLastError());
+  inv.release();
+  stage.release();
+  h->has_lines = true;
+  return PQT_OK;
+}
+
+int pqt_get_db_size(const pqt_index* h, uint32_t* N, uint32_t* line_parts) {
+  if (!h) return PQT_ERR_INVALID;
+  if (N) *N = h->has_db ? h->N : 0;
+  if (line_parts) *line_parts = h->has_lines ? h->LP : 0;
+  return PQT_OK;
+}
+
+int pqt_get_db(const pqt_index* hc, uint32_t* prefix, uint32_t* counts, uint32_t* db_idx) {
+  pqt_index* h = const_cast<pqt_index*>(hc);
+  if (!h) return PQT_ERR_INVALID;
+  if (!h->has_db) return fail(h, PQT_ERR_STATE, "no DB");
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (db_idx) CU_TRY(h, cudaMemcpy(db_idx, h->d_dbidx.p, (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+  if (prefix || counts) {
+    const uint32_t hs = h->db_hash_size;
+    DevBuf dc, dp;
+    CU_TRY(h, dc.ensure((size_t)hs * 4));
+    CU_TRY(h, dp.ensure((size_t)hs * 4));
+    BinDir d{h->d_bitmap.as<uint32_t>(), h->d_rank_base.as<uint32_t>(), h->d_cprefix.as<uint32_t>()};
+    expand_directory_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(d, hs, dc.as<uint32_t>(), dp.as<uint32_t>());
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (counts) CU_TRY(h, cudaMemcpy(counts, dc.p, (size_t)hs * 4, cudaMemcpyDeviceToHost));
+    if (prefix) CU_TRY(h, cudaMemcpy(prefix, dp.p, (size_t)hs * 4, cudaMemcpyDeviceToHost));
+    dc.release();
+    dp.release();
+  }
+  return PQT_OK;
+}
+
+int pqt_get_lines(const pqt_index* hc, uint32_t* lines) {
+  pqt_index* h = const_cast<pqt_index*>(hc);
+  if (!h || !lines) return PQT_ERR_INVALID;
+  if (!h->has_lines) return fail(h, PQT_ERR_STATE, "no line codes");
+  if (h->world != 1) return fail(h, PQT_ERR_STATE, "pqt_get_lines on a sharded handle");
+  CU_TRY(h, cudaSetDevice(h->device));
+  DevBuf out;
+  CU_TRY(h, out.ensure((size_t)h->N * h->LP * 4));
+  gather_codes_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->d_codes.as<uint32_t>(), h->d_dbidx.as<uint32_t>(),
+                                                             h->N, h->LP, out.as<uint32_t>());
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaMemcpy(lines, out.p, (size_t)h->N * h->LP * 4, cudaMemcpyDeviceToHost));
+  out.release();
+  return PQT_OK;
+}
+
+// ---- build side -----------------------------------------------------------------------
+int pqt_build_kbest_db(pqt_index* h, const float* X, int x_on_device, uint32_t N) {
+  if (!h || !X || !N) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (!h->c1) return fail(h, PQT_ERR_STATE, "no tree loaded");
+  const pqt_params& P = h->prm;
+  if (P.k1_build > h->c1) return fail(h, PQT_ERR_INVALID, "k1_build %u > c1 %u (the reference needs c1 >= 16)", P.k1_build, h->c1);
+  const uint32_t hs = P.hash_size;
+  DevBuf dX, d_bin, d_counts, d_prefix, tmp;
+  const float* x = X;
+  if (!x_on_device) {
+    CU_TRY(h, dX.ensure((size_t)N * h->dim * 4));
+    CU_TRY(h, cudaMemcpyAsync(dX.p, X, (size_t)N * h->dim * 4, cudaMemcpyHostToDevice, h->stream));
+    x = dX.as<float>();
+  }
+  CU_TRY(h, d_bin.ensure((size_t)N * 4));
+  CU_TRY(h, d_counts.ensure((size_t)hs * 4));
+  CU_TRY(h, d_prefix.ensure((size_t)hs * 4));
+  CU_TRY(h, tmp.ensure(scan_tmp_words(hs) * 4));
+  CU_TRY(h, cudaMemsetAsync(d_counts.p, 0, (size_t)hs * 4, h->stream));
+  {
+    AssignBinsArgs a{};
+    a.X = x; a.cb1 = h->d_cb1.as<float>(); a.cb2 = h->d_cb2.as<float>();
+    a.N = N; a.dim = h->dim; a.p = h->p; a.c1 = h->c1; a.c2 = h->c2; a.vl = h->vl;
+    a.k1 = P.k1_build; a.npA = pow2ceil(h->c1);
+    a.hash = make_fastmod(hs);
+    a.bin_of = d_bin.as<uint32_t>();
+    a.counts = d_counts.as<uint32_t>();
+    size_t smem = (size_t)(h->dim + 2 * h->p * a.npA + a.k1 * h->p + 2 * h->p * 4) * 4;
+    uint32_t grid = std::min<uint32_t>(N, (uint32_t)h->num_sms * 16);
+    assign_bins_kernel<<<grid, 128, smem, h->stream>>>(a);
+    CU_TRY(h, cudaGetLastError());
+  }
+  device_exscan_u32(d_counts.as<uint32_t>(), d_prefix.as<uint32_t>(), hs, tmp.as<uint32_t>(), h->stream);
+  CU_TRY(h, h->d_dbidx.ensure((size_t)N * 4));
+  // directory first: bin_slot_kernel consumes the histogram as its cursor
+  int rc = build_directory(h, d_counts.as<uint32_t>(), d_prefix.as<uint32_t>(), hs, N);
+  if (rc == PQT_OK) {
+    bin_slot_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(d_bin.as<uint32_t>(), N, d_counts.as<uint32_t>(),
+                                                           d_prefix.as<uint32_t>(), h->d_dbidx.as<uint32_t>());
+    sort_within_bins_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(
+        BinDir{h->d_bitmap.as<uint32_t>(), h->d_rank_base.as<uint32_t>(), h->d_cprefix.as<uint32_t>()},
+        h->n_nonempty, h->d_dbidx.as<uint32_t>());
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) rc = fail(h, PQT_ERR_CUDA, "build_kbest_db: %s", cudaGetErrorString(e));
+  }
+  for (DevBuf* b : {&dX, &d_bin, &d_counts, &d_prefix, &tmp}) b->release();
+  return rc;
+}
+
+int pqt_line_dist(pqt_index* h, const float* X, int x_on_device, uint32_t N, uint32_t line_parts) {
+  if (!h || !X) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (!h->c1) return fail(h, PQT_ERR_STATE, "no tree loaded");
+  if (!h->has_db) return fail(h, PQT_ERR_STATE, "pqt_line_dist must follow pqt_build_kbest_db / pqt_set_db");
+  if (N != h->N) return fail(h, PQT_ERR_INVALID, "N = %u differs from the DB's %u", N, h->N);
+  if (h->world != 1) return fail(h, PQT_ERR_STATE, "pqt_line_dist on a sharded handle");
+  PQ_TRY(check_lp(h, line_parts));
+  if (!is_pow2(h->c1)) return fail(h, PQT_ERR_INVALID, "line encoding needs c1 = 2^n (tree over centroids, pqt/PerturbationProTree.cu:7633-7641)");
+  if (h->c1 * line_parts > 1024) return fail(h, PQT_ERR_INVALID, "lineparts * c1 > 1024 (:7694-7697)");
+  const uint32_t LP = line_parts;
+  h->LP = LP;
+  h->sl = h->dim / LP;
+  PQ_TRY(compute_cbd(h, LP));
+  DevBuf dX;
+  const float* x = X;
+  if (!x_on_device) {
+    CU_TRY(h, dX.ensure((size_t)N * h->dim * 4));
+    CU_TRY(h, cudaMemcpyAsync(dX.p, X, (size_t)N * h->dim * 4, cudaMemcpyHostToDevice, h->stream));
+    x = dX.as<float>();
+  }
+  CU_TRY(h, h->d_codes.ensure((size_t)N * LP * 4));
+  LineEncodeArgs a{};
+  a.X = x; a.cb1 = h->d_cb1.as<float>(); a.cbd = h->d_cbd.as<float>();
+  a.ids = h->d_dbidx.as<uint32_t>();
+  a.N = N; a.dim = h->dim; a.c1 = h->c1; a.LP = LP; a.sl = h->sl;
+  a.codes = h->d_codes.as<uint32_t>();
+  size_t smem = (size_t)(h->dim + 3 * LP * h->c1) * 4;
+  if (smem > 48 * 1024)
+    CU_TRY(h, cudaFuncSetAttribute(line_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  uint32_t grid = std::min<uint32_t>(N, (uint32_t)h->num_sms * 8);
+  line_encode_kernel<<<grid, LP * h->c1, smem, h->stream>>>(a);
+  CU_TRY(h, cudaGetLastError());
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  dX.release();
+  h->has_lines = true;
+  return PQT_OK;
+}
+
+// ---- query ----------------------------------------------------------------------------
+int pqt_candidate_width(const pqt_index* h, uint32_t k, uint32_t* max_vec) {
+  if (!h || !max_vec || !k) return PQT_ERR_INVALID;
+  *max_vec = candidate_width(h, k);
+  return PQT_OK;
+}
+
+int pqt_query_knn(pqt_index* h, const float* Q, int q_on_device, uint32_t QN, uint32_t k,
+                  uint32_t* idx, float* dist, int out_on_device) {
+  if (!h || !Q || !idx || !dist) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  PQ_TRY(check_query_state(h, QN, k));
+  if (h->world != 1) return fail(h, PQT_ERR_STATE, "sharded handle: use pqt_query_scan_shard + pqt_rank_candidates");
+  const uint32_t max_vec = candidate_width(h, k);
+  const float* dQ = Q;
+  if (!q_on_device) {
+    CU_TRY(h, h->s_q.ensure((size_t)QN * h->dim * 4));
+    CU_TRY(h, cudaMemcpyAsync(h->s_q.p, Q, (size_t)QN * h->dim * 4, cudaMemcpyHostToDevice, h->stream));
+    dQ = h->s_q.as<float>();
+  }
+  CU_TRY(h, h->s_val.ensure((size_t)QN * max_vec * 4));
+  CU_TRY(h, h->s_idx.ensure((size_t)QN * max_vec * 4));
+  float* d_out_dist = dist;
+  uint32_t* d_out_idx = idx;
+  if (!out_on_device) {
+    CU_TRY(h, h->s_outd.ensure((size_t)QN * k * 4));
+    CU_TRY(h, h->s_outi.ensure((size_t)QN * k * 4));
+    d_out_dist = h->s_outd.as<float>();
+    d_out_idx = h->s_outi.as<uint32_t>();
+  }
+  PQ_TRY(run_scan_chain(h, dQ, QN, k, h->s_val.as<float>(), h->s_idx.as<uint32_t>()));
+  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
+  PQ_TRY(run_rank(h, h->s_val.as<float>(), h->s_idx.as<uint32_t>(), QN, max_vec, k, d_out_dist, d_out_idx));
+  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+  if (!out_on_device) {
+    CU_TRY(h, cudaMemcpyAsync(idx, d_out_idx, (size_t)QN * k * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(dist, d_out_dist, (size_t)QN * k * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  if (h->profile) accumulate_profile(h, QN, true);
+  return PQT_OK;
+}
+
+int pqt_query_scan_shard(pqt_index* h, const float* Q, int q_on_device, uint32_t QN, uint32_t k,
+                         float* val, uint32_t* idx) {
+  if (!h || !Q || !val || !idx) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  PQ_TRY(check_query_state(h, QN, k));
+  const float* dQ = Q;
+  if (!q_on_device) {
+    CU_TRY(h, h->s_q.ensure((size_t)QN * h->dim * 4));
+    CU_TRY(h, cudaMemcpyAsync(h->s_q.p, Q, (size_t)QN * h->dim * 4, cudaMemcpyHostToDevice, h->stream));
+    dQ = h->s_q.as<float>();
+  }
+  PQ_TRY(run_scan_chain(h, dQ, QN, k, val, idx));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  if (h->profile) accumulate_profile(h, QN, false);
+  return PQT_OK;
+}
+
+int pqt_rank_candidates(pqt_index* h, float* val, uint32_t* idx, uint32_t QN, uint32_t max_vec,
+                        uint32_t k, uint32_t* out_idx, float* out_dist, int out_on_device) {
+  if (!h || !val || !idx || !out_idx || !out_dist || !QN || !k) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  float* d_out_dist = out_dist;
+  uint32_t* d_out_idx = out_idx;
+  if (!out_on_device) {
+    CU_TRY(h, h->s_outd.ensure((size_t)QN * k * 4));
+    CU_TRY(h, h->s_outi.ensure((size_t)QN * k * 4));
+    d_out_dist = h->s_outd.as<float>();
+    d_out_idx = h->s_outi.as<uint32_t>();
+  }
+  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
+  PQ_TRY(run_rank(h, val, idx, QN, max_vec, k, d_out_dist, d_out_idx));
+  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+  if (!out_on_device) {
+    CU_TRY(h, cudaMemcpyAsync(out_idx, d_out_idx, (size_t)QN * k * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(out_dist, d_out_dist, (size_t)QN * k * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  if (h->profile) {
+    float t = 0;
+    cudaEventElapsedTime(&t, h->ev[4], h->ev[5]);
+    h->stats.ms_sort += t;
+    h->stats.ms_total += t;
+  }
+  return PQT_OK;
+}
+
+// ---- measurement / introspection --------------------------------------------------------
+int pqt_profile_enable(pqt_index* h, int on) {
+  if (!h) return PQT_ERR_INVALID;
+  h->profile = on != 0;
+  return PQT_OK;
+}
+int pqt_get_stats(const pqt_index* h, pqt_stats* st) {
+  if (!h || !st) return PQT_ERR_INVALID;
+  *st = h->stats;
+  return PQT_OK;
+}
+int pqt_reset_stats(pqt_index* h) {
+  if (!h) return PQT_ERR_INVALID;
+  std::memset(&h->stats, 0, sizeof(h->stats));
+  return PQT_OK;
+}
+int pqt_debug_enable(pqt_index* h, int on) {
+  if (!h) return PQT_ERR_INVALID;
+  h->debug = on != 0;
+  return PQT_OK;
+}
+
+int pqt_debug_stage(const pqt_index* hc, int stage, void* host_out, size_t bytes) {
+  pqt_index* h = const_cast<pqt_index*>(hc);
+  if (!h || !host_out) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  const void* src = nullptr;
+  size_t need = 0;
+  const uint32_t QN = h->dbg_QN, n = h->prm.k1 * h->c2;
+  switch (stage) {
+    case PQT_STAGE_ASSIGN: src = h->g_assign.p; need = (size_t)QN * h->prm.k1 * h->p * 4; break;
+    case PQT_STAGE_LUT: src = h->g_lut.p; need = (size_t)QN * h->LP * h->c1 * 4; break;
+    case PQT_STAGE_ASSIGN_VAL: src = h->g_aval.p; need = (size_t)QN * h->p * n * 4; break;
+    case PQT_STAGE_ASSIGN_IDX: src = h->g_aidx.p; need = (size_t)QN * h->p * n * 4; break;
+    case PQT_STAGE_BINS: src = h->g_bins.p; need = (size_t)QN * h->prm.max_bins * 4; break;
+    case PQT_STAGE_NBINS: src = h->g_nbins.p; need = (size_t)QN * 4; break;
+    case PQT_STAGE_SELECT_IDX: src = h->g_sel.p; need = (size_t)QN * h->dbg_maxvec * 4; break;
+    case PQT_STAGE_NVEC: src = h->s_nvec.p; need = (size_t)QN * 4; break;
+    case PQT_STAGE_CB_DIST:
+      if (!h->has_lines) return fail(h, PQT_ERR_STATE, "no line codes");
+      src = h->d_cbd.p; need = (size_t)h->c1 * h->c1 * h->LP * 4; break;
+    case PQT_STAGE_DIST_SEQ:
+      if (h->h_distseq.empty()) return fail(h, PQT_ERR_STATE, "no query has run yet");
+      if (bytes != kNumDistSeq * 4) return fail(h, PQT_ERR_INVALID, "size mismatch");
+      std::memcpy(host_out, h->h_distseq.data(), bytes);
+      return PQT_OK;
+    default: return fail(h, PQT_ERR_INVALID, "unknown stage %d", stage);
+  }
+  if (stage <= PQT_STAGE_NVEC && (!h->debug || !QN)) return fail(h, PQT_ERR_STATE, "debug recording is off or no query has run");
+  if (bytes != need) return fail(h, PQT_ERR_INVALID, "stage %d holds %zu bytes, caller passed %zu", stage, need, bytes);
+  CU_TRY(h, cudaMemcpy(host_out, src, need, cudaMemcpyDeviceToHost));
+  return PQT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,586 @@
+// query_kernels.cuh -- the queryKNN chain as sm_100a kernels.
+//
+//   tables_kernel   Steps A+B+C  (getKBestAssignment, getLineAssignment,
+//                                 getKBestAssignment2)
+//   bins_kernel     Steps D+E1   (getBins / selectBinKernelFast2,
+//                                 getKVectorIDsKernelFast)
+//   adc_scan_kernel Step E2      (rerankKernelFast, distance part)
+//   rank_kernel     Step E2 tail (bitonic3 / bitonicLarge + first-k emit)
+//
+// Citations are file:line into /root/reference/pqt/PerturbationProTree.cu unless
+// another file is named.  Semantics follow SURVEY.md App. B and are checked
+// bit-for-bit against oracle/pqt_oracle.c.
+#pragma once
+#include "common.cuh"
+
+namespace pqtb {
+
+// ============================================================================
+// in-shared-memory bitonic network, identical compare-exchange order to
+// pqt/bitonicSort.cuh:16-78 (ascending iff (i & k) == 0, swap on strict > / <).
+// Sorts `narr` independent arrays of n (power of two) elements laid out back to
+// back.  All threads of the block must call.
+// ============================================================================
+__device__ __forceinline__ void bitonic_smem(float* val, uint32_t* idx, uint32_t n, uint32_t narr) {
+  const uint32_t half = n >> 1;
+  const uint32_t total = half * narr;
+  for (uint32_t k = 2; k <= n; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t e = threadIdx.x; e < total; e += blockDim.x) {
+        uint32_t arr = e / half, t = e - arr * half;
+        uint32_t i = ((t / j) * (j << 1)) + (t % j);  // (i & j) == 0
+        uint32_t a = arr * n + i, b = a + j;
+        float va = val[a], vb = val[b];
+        bool sw = ((i & k) == 0) ? (va > vb) : (va < vb);
+        if (sw) {
+          val[a] = vb;
+          val[b] = va;
+          uint32_t ia = idx[a];
+          idx[a] = idx[b];
+          idx[b] = ia;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ============================================================================
+// Steps A + B + C: one CTA per query.
+// ============================================================================
+struct TablesArgs {
+  const float* Q;    // [QN][dim]
+  const float* cb1;  // [c1][dim]
+  const float* cb2;  // [p][c1][c2][vl]
+  uint32_t QN, dim, p, c1, c2, LP, k1, vl, sl;
+  uint32_t npA;  // pow2ceil(c1)
+  uint32_t npC;  // pow2ceil(k1*c2)
+  uint32_t m;    // min(c2*k1, 16): entries of the sorted Step-C list reachable by Step D
+  float* lut_dup;   // [QN][c1][32]: index c*32 + j*LP + lp, replicated j < 32/LP (see adc_scan)
+  uint32_t* idx16;  // [QN][p][16]
+  // optional debug outputs (canonical reference layouts), may be null
+  uint32_t* dbg_assign;  // [QN][k1][p]
+  float* dbg_lut;        // [QN][LP][c1]
+  float* dbg_aval;       // [QN][p][k1*c2]
+  uint32_t* dbg_aidx;    // [QN][p][k1*c2]
+};
+
+// dynamic smem: q[dim] | val[p*npMax] | idx[p*npMax] | assign[k1*p]
+__global__ void __launch_bounds__(128) tables_kernel(TablesArgs a) {
+  extern __shared__ float smem_f[];
+  const uint32_t npMax = a.npA > a.npC ? a.npA : a.npC;
+  float* sq = smem_f;
+  float* sval = sq + a.dim;
+  uint32_t* sidx = reinterpret_cast<uint32_t*>(sval + a.p * npMax);
+  uint32_t* sassign = sidx + a.p * npMax;
+
+  for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < a.dim; t += blockDim.x) sq[t] = a.Q[(size_t)qi * a.dim + t];
+    // Step A sort buffers: pad to 1e7 (:7185)
+    for (uint32_t e = threadIdx.x; e < a.p * a.npA; e += blockDim.x) {
+      sval[e] = kPadSortA;
+      sidx[e] = kPadIdx;
+    }
+    __syncthreads();
+
+    // ---- Step A distances (:7146-7176): val[part][c] over vl dims
+    for (uint32_t e = threadIdx.x; e < a.p * a.c1; e += blockDim.x) {
+      uint32_t part = e / a.c1, c = e - part * a.c1;
+      sval[part * a.npA + c] =
+          seg_dist_dyn(sq + part * a.vl, a.cb1 + (size_t)c * a.dim + part * a.vl, a.vl);
+      sidx[part * a.npA + c] = c;
+    }
+    // ---- Step B (:7764-7796): lut[lp][c] over dim/LP dims
+    {
+      const uint32_t R = 32 / a.LP;
+      float* lut = a.lut_dup + (size_t)qi * a.c1 * 32;
+      for (uint32_t e = threadIdx.x; e < a.LP * a.c1; e += blockDim.x) {
+        uint32_t c = e / a.LP, lp = e - c * a.LP;
+        float v = seg_dist_dyn(sq + lp * a.sl, a.cb1 + (size_t)c * a.dim + lp * a.sl, a.sl);
+        for (uint32_t j = 0; j < R; j++) lut[c * 32 + j * a.LP + lp] = v;
+        if (a.dbg_lut) a.dbg_lut[((size_t)qi * a.LP + lp) * a.c1 + c] = v;
+      }
+    }
+    __syncthreads();
+    bitonic_smem(sval, sidx, a.npA, a.p);  // :7194
+    // assign[k][part] (:7203-7209)
+    for (uint32_t e = threadIdx.x; e < a.k1 * a.p; e += blockDim.x) {
+      uint32_t k = e / a.p, part = e - k * a.p;
+      uint32_t v = sidx[part * a.npA + k];
+      sassign[e] = v;
+      if (a.dbg_assign) a.dbg_assign[(size_t)qi * a.k1 * a.p + e] = v;
+    }
+    __syncthreads();
+
+    // ---- Step C (:1592-1621): k1 cells x c2 centroids per part, pad 1e9 (:1627)
+    const uint32_t n = a.k1 * a.c2;
+    for (uint32_t e = threadIdx.x; e < a.p * a.npC; e += blockDim.x) {
+      uint32_t part = e / a.npC, i = e - part * a.npC;
+      float v = kPadSortC;
+      uint32_t id = kPadIdx;
+      if (i < n) {
+        uint32_t k = i / a.c2, l2 = i - k * a.c2;
+        uint32_t l1 = sassign[k * a.p + part];
+        const float* cb = a.cb2 + ((size_t)(part * a.c1 + l1) * a.c2 + l2) * a.vl;  // getCBIdx
+        v = seg_dist_dyn(sq + part * a.vl, cb, a.vl);
+        id = l2 + l1 * a.c2;
+      }
+      sval[e] = v;
+      sidx[e] = id;
+    }
+    __syncthreads();
+    bitonic_smem(sval, sidx, a.npC, a.p);  // :1639
+    for (uint32_t e = threadIdx.x; e < a.p * 16; e += blockDim.x) {
+      uint32_t part = e >> 4, r = e & 15;
+      a.idx16[(size_t)qi * a.p * 16 + e] = (r < a.m) ? sidx[part * a.npC + r] : 0u;
+    }
+    if (a.dbg_aval) {
+      for (uint32_t e = threadIdx.x; e < a.p * n; e += blockDim.x) {
+        uint32_t part = e / n, i = e - part * n;
+        a.dbg_aval[(size_t)qi * a.p * n + e] = sval[part * a.npC + i];
+        a.dbg_aidx[(size_t)qi * a.p * n + e] = sidx[part * a.npC + i];
+      }
+    }
+  }
+}
+
+// ============================================================================
+// Bin directory: occupancy bitmap + rank.  Replaces probing the dense
+// binCounts[hash_size] (1.6 GB) by one 32-byte sector of a hash_size/8-byte
+// bitmap (50 MB, L2 resident), and the dense binPrefix by a compact array
+// indexed by the rank of the non-empty bin.
+//   bitmap[w]     bit b = (binCounts[32w + b] != 0)
+//   rank_base[g]  number of non-empty bins before bin 256 g   (group = one sector)
+//   cprefix[r]    binPrefix of the r-th non-empty bin; cprefix[nNonEmpty] = N
+// ============================================================================
+struct BinDir {
+  const uint32_t* bitmap;
+  const uint32_t* rank_base;
+  const uint32_t* cprefix;
+};
+
+__device__ __forceinline__ bool dir_occupied(const BinDir& d, uint32_t bin) {
+  return (__ldg(d.bitmap + (bin >> 5)) >> (bin & 31)) & 1u;
+}
+
+// (start, count) of a bin in the bin-ordered arrays; count 0 if empty
+__device__ __forceinline__ void dir_lookup(const BinDir& d, uint32_t bin, uint32_t& start,
+                                           uint32_t& count) {
+  const uint32_t w = bin >> 5, g = bin >> 8;
+  uint32_t word = __ldg(d.bitmap + w);
+  if (!((word >> (bin & 31)) & 1u)) {
+    start = 0;
+    count = 0;
+    return;
+  }
+  uint32_t r = __ldg(d.rank_base + g);
+  for (uint32_t ww = g << 3; ww < w; ww++) r += __popc(__ldg(d.bitmap + ww));
+  r += __popc(word & ((1u << (bin & 31)) - 1u));
+  start = __ldg(d.cprefix + r);
+  count = __ldg(d.cprefix + r + 1) - start;
+}
+
+// block-wide exclusive scan of one uint per thread (blockDim.x <= 1024, multiple
+// of 32); returns the exclusive prefix and the block total.  `warp_sums` is 32
+// words of shared memory.
+__device__ __forceinline__ uint32_t block_exscan(uint32_t v, uint32_t* warp_sums, uint32_t& total) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  __syncthreads();  // protect warp_sums reuse
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  uint32_t ws = (lane < nw) ? warp_sums[lane] : 0;
+  uint32_t winc = ws;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, winc, d);
+    if (lane >= d) winc += t;
+  }
+  total = __shfl_sync(0xffffffffu, winc, 31);
+  uint32_t wbase = __shfl_sync(0xffffffffu, winc - ws, warp);
+  return wbase + inc - v;
+}
+
+// ============================================================================
+// Steps D + E1: one CTA (256 threads) per query.
+// ============================================================================
+struct BinsArgs {
+  const uint32_t* idx16;     // [QN][p][16]
+  const uint32_t* dist_seq;  // [65536] traversal codes (prepareDistSequence)
+  BinDir dir;
+  FastMod hash;
+  uint32_t QN, p, m, c1c2;
+  uint32_t max_bins, max_trials, bin_threads, max_vec_per_bin, max_vec;
+  uint32_t* cand_pos;  // [QN][max_vec] positions in the bin-ordered code array
+  uint32_t* n_vec;     // [QN]
+  uint32_t* dbg_bins;  // [QN][max_bins] or null
+  uint32_t* dbg_nbins; // [QN] or null
+};
+
+constexpr int kBinsThreads = 256;
+
+// dynamic smem: list[max_bins] | idx[p*16] | warp_sums[32]
+__global__ void __launch_bounds__(kBinsThreads) bins_kernel(BinsArgs a) {
+  extern __shared__ uint32_t smem_u[];
+  uint32_t* list = smem_u;
+  uint32_t* sidx = list + a.max_bins;
+  uint32_t* warp_sums = sidx + a.p * 16;
+
+  // probes per thread and trial, consecutive in traversal order
+  const uint32_t ppt = (a.bin_threads + kBinsThreads - 1) / kBinsThreads;
+  uint32_t denom[8];
+  denom[0] = 1;
+#pragma unroll
+  for (int j = 1; j < 8; j++) denom[j] = denom[j - 1] * a.m;
+
+  for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < a.p * 16; e += blockDim.x)
+      sidx[e] = a.idx16[(size_t)qi * a.p * 16 + e];
+    if (threadIdx.x == 0) list[0] = 0;  // slot 0 keeps the memset value (:3561)
+    __syncthreads();
+
+    // ---- Step D (:3462-3537)
+    uint32_t n_out = 0;
+    for (uint32_t it = 0; it < a.max_trials && n_out < a.max_bins; it++) {
+      uint32_t keep_mask = 0;
+      uint32_t my_bins[16];
+#pragma unroll 4
+      for (uint32_t r = 0; r < ppt && r < 16; r++) {
+        uint32_t t = threadIdx.x * ppt + r;
+        uint32_t bin = 0;
+        bool keep = false;
+        if (t < a.bin_threads) {
+          uint32_t s = __ldg(a.dist_seq + it * a.bin_threads + t);
+          uint32_t o = 0;
+          for (uint32_t j = 0; j < a.p; j++) {
+            uint32_t bp = (s / denom[j]) % a.m;
+            o = o * a.c1c2 + sidx[j * 16 + bp];  // uint32 wrap (:3487)
+          }
+          bin = fastmod(o, a.hash);
+          keep = dir_occupied(a.dir, bin);
+        }
+        my_bins[r] = bin;
+        keep_mask |= (keep ? 1u : 0u) << r;
+      }
+      uint32_t total;
+      uint32_t base = block_exscan(__popc(keep_mask), warp_sums, total);
+      // inclusive-scan position + nOutBins: 1-based (:3504-3510)
+      uint32_t pos = n_out + base;
+#pragma unroll 4
+      for (uint32_t r = 0; r < ppt && r < 16; r++) {
+        if ((keep_mask >> r) & 1u) {
+          pos++;
+          if (pos < a.max_bins) list[pos] = my_bins[r];
+        }
+      }
+      n_out += total;
+    }
+    __syncthreads();
+    const uint32_t nb = n_out < a.max_bins ? n_out : a.max_bins;
+    if (a.dbg_bins) {
+      for (uint32_t e = threadIdx.x; e < a.max_bins; e += blockDim.x)
+        a.dbg_bins[(size_t)qi * a.max_bins + e] =
+            (e == 0) ? 0u : ((e <= n_out && e < a.max_bins) ? list[e] : 0u);
+      if (threadIdx.x == 0) a.dbg_nbins[qi] = nb;
+    }
+
+    // ---- Step E1 (:4339-4417): concatenate min(count, max_vec_per_bin) vectors
+    // of every listed bin, truncated at max_vec
+    uint32_t offset = 0;
+    uint32_t* cand = a.cand_pos + (size_t)qi * a.max_vec;
+    for (uint32_t b0 = 0; b0 < nb && offset < a.max_vec; b0 += blockDim.x) {
+      uint32_t b = b0 + threadIdx.x;
+      uint32_t start = 0, nv = 0;
+      if (b < nb) {
+        uint32_t cnt;
+        dir_lookup(a.dir, list[b], start, cnt);
+        nv = cnt < a.max_vec_per_bin ? cnt : a.max_vec_per_bin;
+      }
+      uint32_t total;
+      uint32_t pos = offset + block_exscan(nv, warp_sums, total);
+      if (pos + nv > a.max_vec) nv = (pos >= a.max_vec) ? 0 : (a.max_vec - pos);
+      for (uint32_t v = 0; v < nv; v++) cand[pos + v] = start + v;
+      offset += total;
+    }
+    if (threadIdx.x == 0) a.n_vec[qi] = offset < a.max_vec ? offset : a.max_vec;
+  }
+}
+
+// ============================================================================
+// Step E2, distance part: the ADC scan over line codes (:5277-5329).
+//
+// Lane mapping (LP lanes per candidate, as the reference): lane = g*LP + lp.  A
+// warp step evaluates R = 32/LP candidates; segment lp of candidate g reads
+//   a2 = lut[p1][lane], b2 = lut[p2][lane], c2 = cbd[p2*c1 + p1][lane]
+// from tables whose 32-float rows hold the LP values replicated R times, so the
+// 32 lanes of a warp always hit 32 distinct banks (conflict-free by layout).
+// The LP partial distances are summed with the same pairwise tree as
+// warpReduceSum (:5183-5187), as an xor butterfly: fp32 addition is commutative,
+// so every lane ends with the bit pattern lane 0 of the group gets in the
+// reference.  Candidate `a` of a 32-chunk is evaluated by lane group a / LP at
+// step a % LP, so lane a captures its own result without a final shuffle.
+//
+// One persistent CTA per SM: cbd (c1*c1*32 floats) is staged once, the per-query
+// LUT (c1*32 floats) is double-buffered with TMA bulk copies (cp.async.bulk +
+// mbarrier).
+// ============================================================================
+struct ScanArgs {
+  const uint32_t* codes;     // [n_local][LP] line codes in bin order (this shard's slice)
+  const uint32_t* ids;       // [n_local] vector id of each position
+  const uint32_t* cand_pos;  // [QN][max_vec] global positions
+  const uint32_t* n_vec;     // [QN]
+  const float* lut_dup;      // [QN][c1][32]
+  const float* cbd_dup;      // [c1*c1][32]
+  uint32_t QN, c1, max_vec;
+  uint32_t pos_lo, pos_hi;  // this shard's slice of positions
+  uint32_t owns_pad;        // 1: write (1e7, PAD) into slots >= nVec; 0: (+inf, 0)
+  uint32_t sharded;         // 1: slots of other shards get (+inf, 0)
+  float* out_val;           // [QN][max_vec]
+  uint32_t* out_idx;        // [QN][max_vec]
+};
+
+constexpr int kScanThreads = 1024;
+
+template <int LP>
+__global__ void __launch_bounds__(kScanThreads, 1) adc_scan_kernel(ScanArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t lut_floats = a.c1 * 32;
+  const uint32_t cbd_floats = a.c1 * a.c1 * 32;
+  float* s_cbd = reinterpret_cast<float*>(smem_raw);
+  float* s_lut0 = s_cbd + cbd_floats;
+  float* s_lut1 = s_lut0 + lut_floats;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lut1 + lut_floats);  // [0],[1]: lut, [2]: cbd
+
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const uint32_t lp = lane & (LP - 1);
+  const uint32_t grp_base = lane & ~(uint32_t)(LP - 1);
+
+  if (blockIdx.x >= a.QN) return;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // stage cbd once (chunks of <= 32 KB) and the first query's LUT
+    const uint32_t cbd_bytes = cbd_floats * 4;
+    mbar_expect_tx(&bars[2], cbd_bytes);
+    for (uint32_t off = 0; off < cbd_bytes; off += 32768) {
+      uint32_t n = cbd_bytes - off < 32768 ? cbd_bytes - off : 32768;
+      tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_cbd) + off,
+                   reinterpret_cast<const unsigned char*>(a.cbd_dup) + off, n, &bars[2]);
+    }
+    mbar_expect_tx(&bars[0], lut_floats * 4);
+    tma_bulk_g2s(s_lut0, a.lut_dup + (size_t)blockIdx.x * lut_floats, lut_floats * 4, &bars[0]);
+  }
+  mbar_wait(&bars[2], 0);
+
+  uint32_t buf = 0, phase0 = 0, phase1 = 0;
+  for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
+    // prefetch the next query's LUT into the other buffer (its readers passed the
+    // __syncthreads at the end of the previous iteration)
+    const uint32_t qn = qi + gridDim.x;
+    if (threadIdx.x == 0 && qn < a.QN) {
+      uint64_t* nb = &bars[buf ^ 1];
+      mbar_expect_tx(nb, lut_floats * 4);
+      tma_bulk_g2s(buf ? s_lut0 : s_lut1, a.lut_dup + (size_t)qn * lut_floats, lut_floats * 4, nb);
+    }
+    const float* s_lut = buf ? s_lut1 : s_lut0;
+    mbar_wait(&bars[buf], buf ? phase1 : phase0);
+    if (buf)
+      phase1 ^= 1;
+    else
+      phase0 ^= 1;
+
+    const uint32_t nv = min(__ldg(a.n_vec + qi), a.max_vec);
+    const uint32_t* cand = a.cand_pos + (size_t)qi * a.max_vec;
+    float* oval = a.out_val + (size_t)qi * a.max_vec;
+    uint32_t* oidx = a.out_idx + (size_t)qi * a.max_vec;
+
+    for (uint32_t base = warp * 32; base < a.max_vec; base += nwarps * 32) {
+      const uint32_t ca = base + lane;
+      const bool valid = ca < nv;
+      uint32_t pos = 0;
+      bool mine = false;
+      if (valid) {
+        pos = __ldg(cand + ca);
+        mine = (pos >= a.pos_lo) && (pos < a.pos_hi);
+      }
+      const uint32_t lpos = pos - a.pos_lo;
+      float myval = 0.f;
+      uint32_t myid = 0;
+      const uint32_t any_mine = __ballot_sync(0xffffffffu, mine);
+      if (any_mine) {
+        if (mine) myid = __ldg(a.ids + lpos);
+        // issue all code loads of the chunk first (LP independent 128-byte requests)
+        uint32_t w[LP];
+#pragma unroll
+        for (int s = 0; s < LP; s++) {
+          const uint32_t src = grp_base + s;
+          const uint32_t cpos = __shfl_sync(0xffffffffu, lpos, src);
+          const bool cm = (any_mine >> src) & 1u;
+          w[s] = cm ? __ldg(a.codes + (size_t)cpos * LP + lp) : 0u;
+        }
+#pragma unroll
+        for (int s = 0; s < LP; s++) {
+          const uint32_t p1 = w[s] & 0xFFu;         // lineDescr.p1 (pqt/PerturbationProTree.hh:21-25)
+          const uint32_t p2 = (w[s] >> 8) & 0xFFu;  // lineDescr.p2
+          const float lam = lambda_of(w[s]);
+          const float a2 = s_lut[p1 * 32 + lane];
+          const float b2 = s_lut[p2 * 32 + lane];
+          const float c2 = s_cbd[(p2 * a.c1 + p1) * 32 + lane];
+          float d = tri_dist(a2, b2, c2, lam);
+#pragma unroll
+          for (int st = LP >> 1; st > 0; st >>= 1)
+            d = __fadd_rn(d, __shfl_xor_sync(0xffffffffu, d, st));
+          if (lp == (uint32_t)s) myval = d;
+        }
+      }
+      float v;
+      uint32_t id;
+      if (mine) {
+        v = myval;
+        id = myid;
+      } else if (valid) {  // another shard's candidate
+        v = __int_as_float(0x7f800000);
+        id = 0;
+      } else if (a.owns_pad) {
+        v = kPadDist;
+        id = kPadIdx;
+      } else {
+        v = __int_as_float(0x7f800000);
+        id = 0;
+      }
+      oval[ca] = v;
+      oidx[ca] = id;
+    }
+    __syncthreads();  // everyone is done with s_lut[buf] before it is refilled
+    buf ^= 1;
+  }
+}
+
+// Fallback for shapes whose cbd table does not fit in shared memory (c1 > 32):
+// same arithmetic, tables read through L1/L2 in their canonical layouts.
+struct ScanGenericArgs {
+  ScanArgs s;
+  const float* lut;  // [QN][LP][c1] canonical
+  const float* cbd;  // [c1][c1][LP] canonical
+  uint32_t LP;
+};
+
+__global__ void __launch_bounds__(256) adc_scan_generic_kernel(ScanGenericArgs g) {
+  const ScanArgs& a = g.s;
+  const uint32_t LP = g.LP;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const uint32_t lp = lane & (LP - 1);
+  const uint32_t grp_base = lane & ~(LP - 1);
+  for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
+    const float* lut = g.lut + (size_t)qi * LP * a.c1;
+    const uint32_t nv = min(__ldg(a.n_vec + qi), a.max_vec);
+    const uint32_t* cand = a.cand_pos + (size_t)qi * a.max_vec;
+    for (uint32_t base = warp * 32; base < a.max_vec; base += nwarps * 32) {
+      const uint32_t ca = base + lane;
+      const bool valid = ca < nv;
+      uint32_t pos = 0;
+      bool mine = false;
+      if (valid) {
+        pos = __ldg(cand + ca);
+        mine = (pos >= a.pos_lo) && (pos < a.pos_hi);
+      }
+      const uint32_t lpos = pos - a.pos_lo;
+      float myval = 0.f;
+      uint32_t myid = 0;
+      const uint32_t any_mine = __ballot_sync(0xffffffffu, mine);
+      if (any_mine) {
+        if (mine) myid = __ldg(a.ids + lpos);
+        for (uint32_t s = 0; s < LP; s++) {
+          const uint32_t src = grp_base + s;
+          const uint32_t cpos = __shfl_sync(0xffffffffu, lpos, src);
+          const bool cm = (any_mine >> src) & 1u;
+          float d = 0.f;
+          if (cm) {
+            uint32_t w = __ldg(a.codes + (size_t)cpos * LP + lp);
+            const uint32_t p1 = w & 0xFFu, p2 = (w >> 8) & 0xFFu;
+            const float lam = lambda_of(w);
+            d = tri_dist(__ldg(lut + lp * a.c1 + p1), __ldg(lut + lp * a.c1 + p2),
+                         __ldg(g.cbd + ((size_t)p2 * a.c1 + p1) * LP + lp), lam);
+          }
+          for (uint32_t st = LP >> 1; st > 0; st >>= 1)
+            d = __fadd_rn(d, __shfl_xor_sync(0xffffffffu, d, st));
+          if (lp == s) myval = d;
+        }
+      }
+      float v;
+      uint32_t id;
+      if (mine) {
+        v = myval;
+        id = myid;
+      } else if (valid || !a.owns_pad) {
+        v = __int_as_float(0x7f800000);
+        id = 0;
+      } else {
+        v = kPadDist;
+        id = kPadIdx;
+      }
+      a.out_val[(size_t)qi * a.max_vec + ca] = v;
+      a.out_idx[(size_t)qi * a.max_vec + ca] = id;
+    }
+  }
+}
+
+// ============================================================================
+// Step E2 tail: exact bitonic network over max_vec (val, idx) pairs and emit of
+// the first k (:5337-5346).  One CTA per query, network in shared memory.
+// ============================================================================
+struct RankArgs {
+  const float* val;     // [QN][max_vec]
+  const uint32_t* idx;  // [QN][max_vec]
+  uint32_t QN, max_vec, k;
+  float* out_dist;    // [QN][k]
+  uint32_t* out_idx;  // [QN][k]
+};
+
+constexpr int kRankThreads = 1024;
+
+__global__ void __launch_bounds__(kRankThreads) rank_kernel(RankArgs a) {
+  extern __shared__ float smem_f[];
+  float* sval = smem_f;
+  uint32_t* sidx = reinterpret_cast<uint32_t*>(sval + a.max_vec);
+  for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < a.max_vec; e += blockDim.x) {
+      sval[e] = a.val[(size_t)qi * a.max_vec + e];
+      sidx[e] = a.idx[(size_t)qi * a.max_vec + e];
+    }
+    __syncthreads();
+    bitonic_smem(sval, sidx, a.max_vec, 1);
+    for (uint32_t e = threadIdx.x; e < a.k; e += blockDim.x) {
+      a.out_dist[(size_t)qi * a.k + e] = sval[e];
+      a.out_idx[(size_t)qi * a.k + e] = sidx[e];
+    }
+  }
+}
+
+// debug: select_idx[a] = ids[cand_pos[a]] for a < nVec else 0 (:6183 memset)
+__global__ void gather_select_idx_kernel(const uint32_t* cand_pos, const uint32_t* n_vec,
+                                         const uint32_t* ids, uint32_t QN, uint32_t max_vec,
+                                         uint32_t* out) {
+  size_t total = (size_t)QN * max_vec;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x) {
+    uint32_t qi = (uint32_t)(e / max_vec), ca = (uint32_t)(e - (size_t)qi * max_vec);
+    out[e] = (ca < n_vec[qi]) ? ids[cand_pos[e]] : 0u;
+  }
+}
+
+}  // namespace pqtb

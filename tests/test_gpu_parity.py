@@ -1,0 +1,219 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the oracle on the same
+inputs -- bit-exact for ids, bins and every float (the kernels pin the reference's
+rounding order, so distances are compared for equality, well inside the 1e-4 relative
+tolerance north_star states)."""
+import numpy as np
+import pytest
+
+import pqt_oracle as po
+from util import golden_case, make_gpu_index, oracle_query
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-4  # north_star's tolerance for ADC distances; we assert equality below
+
+
+def _stages(t, prm, QN, k):
+    n = prm.k1 * prm.c2
+    mv = t.candidateWidth(k)
+    return dict(
+        assign=t.stage("assign", (QN, prm.k1, prm.p), np.uint32),
+        lut=t.stage("lut", (QN, prm.line_parts, prm.c1), np.float32),
+        assign_val=t.stage("assign_val", (QN, prm.p, n), np.float32),
+        assign_idx=t.stage("assign_idx", (QN, prm.p, n), np.uint32),
+        bins=t.stage("bins", (QN, prm.max_bins), np.uint32),
+        n_bins=t.stage("n_bins", (QN,), np.uint32),
+        select_idx=t.stage("select_idx", (QN, mv), np.uint32),
+        n_vec=t.stage("n_vec", (QN,), np.uint32))
+
+
+def _check_all_stages(case, k, **over):
+    d0, i0, st0 = oracle_query(case, k, stages=True, **over)
+    t = make_gpu_index(case, **over)
+    t.debug(True)
+    QN = case["Q"].shape[0]
+    i1, d1 = t.queryKNN(case["Q"], QN, k)
+    prm = po.Params.from_buffer_copy(case["prm"])
+    for kk, v in over.items():
+        setattr(prm, kk, v)
+    st1 = _stages(t, prm, QN, k)
+    seq0, m, _ = po.dist_seq(prm.c2 * prm.k1, prm.p)
+    assert np.array_equal(t.stage("dist_seq", (65536,), np.uint32), seq0)
+    assert np.array_equal(t.stage("cb_dist", (prm.c1, prm.c1, prm.line_parts), np.float32),
+                          case["cb_dist"])
+    for name in ("assign", "lut", "assign_val", "n_bins", "bins", "n_vec", "select_idx"):
+        assert np.array_equal(st1[name], st0[name]), name
+    # assign_idx: padded slots (only when k1*c2 is not a power of two) are unspecified
+    assert np.array_equal(st1["assign_idx"], st0["assign_idx"])
+    assert np.array_equal(i1, i0)
+    assert np.array_equal(d1, d0)
+    assert np.allclose(d1, d0, rtol=REL_TOL, atol=0)
+    t.close()
+    return d1, i1
+
+
+def test_small_case_every_stage(case_small):
+    _check_all_stages(case_small, 256)
+
+
+def test_lp32_case_every_stage(case_lp32):
+    _check_all_stages(case_lp32, 512)
+
+
+@pytest.mark.parametrize("name", ["c1_16_c2_8_lp16", "c1_32_c2_32_lp32"])
+def test_golden_fixtures(name):
+    case, g = golden_case(name)
+    t = make_gpu_index(case)
+    i1, d1 = t.queryKNN(case["Q"], case["Q"].shape[0], int(g["k"]))
+    assert np.array_equal(i1, g["idx"])
+    assert np.array_equal(d1, g["dist"])
+    t.close()
+
+
+@pytest.mark.parametrize("k", [1, 3, 32, 1000, 4096])
+def test_k_sweep(case_small, k):
+    d0, i0 = oracle_query(case_small, k)
+    t = make_gpu_index(case_small)
+    i1, d1 = t.queryKNN(case_small["Q"], case_small["Q"].shape[0], k)
+    assert np.array_equal(i1, i0) and np.array_equal(d1, d0)
+    t.close()
+
+
+def test_truncation_budgets(case_small):
+    _check_all_stages(case_small, 64, max_bins=8, max_vec_per_bin=3)
+    _check_all_stages(case_small, 64, max_trials=1)
+    _check_all_stages(case_small, 128, bin_threads=256, max_trials=7, k1=4)
+
+
+def test_empty_index_and_single_query(case_small):
+    c = dict(case_small)
+    c["counts"] = np.zeros_like(case_small["counts"])
+    c["prefix"] = np.zeros_like(case_small["prefix"])
+    t = make_gpu_index(c)
+    i1, d1 = t.queryKNN(c["Q"], c["Q"].shape[0], 32)
+    assert np.all(i1 == po.PAD_IDX) and np.all(d1 == np.float32(1e7))
+    t.close()
+    c = dict(case_small)
+    c["Q"] = case_small["Q"][5:6]
+    d0, i0 = oracle_query(c, 256)
+    t = make_gpu_index(c)
+    i1, d1 = t.queryKNN(c["Q"], 1, 256)
+    assert np.array_equal(i1, i0) and np.array_equal(d1, d0)
+    t.close()
+
+
+def test_device_pointers_and_max_vec_extension(case_small):
+    import torch
+    c = case_small
+    QN = c["Q"].shape[0]
+    d0, i0 = oracle_query(c, 1024)
+    t = make_gpu_index(c, max_vec=1024)
+    Qd = torch.from_numpy(c["Q"]).cuda()
+    oi = torch.zeros((QN, 10), dtype=torch.int32, device="cuda")
+    od = torch.zeros((QN, 10), dtype=torch.float32, device="cuda")
+    t.queryKNN(Qd, QN, 10, oi, od)
+    # first k of the width-1024 ranking (params.max_vec extension)
+    assert np.array_equal(oi.cpu().numpy().view(np.uint32), i0[:, :10])
+    assert np.array_equal(od.cpu().numpy(), d0[:, :10])
+    # pinned host outputs
+    pi = torch.zeros((QN, 10), dtype=torch.int32).pin_memory()
+    pd = torch.zeros((QN, 10), dtype=torch.float32).pin_memory()
+    t.queryKNN(Qd, QN, 10, pi, pd)
+    assert np.array_equal(pi.numpy().view(np.uint32), i0[:, :10])
+    t.close()
+
+
+def test_error_behaviour(case_small, tmp_path):
+    import pqt_b200
+    c = case_small
+    prm = c["prm"]
+    t = pqt_b200.PerturbationProTree(prm.dim, prm.p)
+    with pytest.raises(pqt_b200.PqtError):  # query before anything is loaded
+        t.queryKNN(c["Q"], 4, 4)
+    t.set_params(hash_size=prm.hash_size)
+    t.setTree(c["cb1"], c["cb2"].reshape(prm.p, prm.c1, prm.c2, -1))
+    t.setDB(c["db_idx"].size, c["prefix"], c["counts"], c["db_idx"])
+    with pytest.raises(pqt_b200.PqtError) as e:  # the shipped tool_query forgets the lines
+        t.queryKNN(c["Q"], 4, 4)
+    assert "line codes" in str(e.value)
+    with pytest.raises(pqt_b200.PqtError):
+        t.setLines(c["lines"], c["db_idx"].size, 24)  # not a power of two
+    t.setLines(c["lines"], c["db_idx"].size, prm.line_parts)
+    with pytest.raises(pqt_b200.PqtError):
+        t.queryKNN(c["Q"], 4, 8192)  # candidate width > 4096
+    with pytest.raises(pqt_b200.PqtError):
+        t.readTreeFromFile(str(tmp_path / "missing.ppqt"))
+    # tree file round trip through the reference's .ppqt format
+    path = str(tmp_path / "t_128_4_16_8.ppqt")
+    t.writeTreeToFile(path)
+    from pqt_b200 import formats
+    f = formats.read_ppqt(path)
+    assert np.array_equal(f["cb1"], c["cb1"]) and f["c2"] == prm.c2
+    t2 = pqt_b200.PerturbationProTree(8, 1)  # constructor args are overridden by the file
+    t2.readTreeFromFile(path)
+    assert t2.shape() == (prm.dim, prm.p, prm.c1, prm.c2)
+    t.close()
+    t2.close()
+
+
+def test_gpu_builder_matches_oracle_builder(case_small):
+    import pqt_b200
+    c = case_small
+    prm = c["prm"]
+    t = pqt_b200.PerturbationProTree(prm.dim, prm.p)
+    t.set_params(hash_size=prm.hash_size, k1_build=min(16, prm.c1))
+    t.setTree(c["cb1"], c["cb2"].reshape(prm.p, prm.c1, prm.c2, -1))
+    N = c["X"].shape[0]
+    t.buildKBestDB(c["X"], N)
+    t.lineDist(c["X"], N, prm.line_parts)
+    prefix, counts, db_idx = t.getDB()
+    assert np.array_equal(counts, c["counts"])
+    assert np.array_equal(prefix, c["prefix"])
+    assert np.array_equal(db_idx, c["db_idx"])
+    assert np.array_equal(t.getLine(), c["lines"])
+    d0, i0 = oracle_query(c, 256)
+    i1, d1 = t.queryKNN(c["Q"], c["Q"].shape[0], 256)
+    assert np.array_equal(i1, i0) and np.array_equal(d1, d0)
+    t.close()
+
+
+def test_loaded_db_round_trips(case_small):
+    t = make_gpu_index(case_small)
+    prefix, counts, db_idx = t.getDB()
+    assert np.array_equal(counts, case_small["counts"])
+    assert np.array_equal(prefix, case_small["prefix"])
+    assert np.array_equal(db_idx, case_small["db_idx"])
+    assert np.array_equal(t.getLine(), case_small["lines"])
+    t.close()
+
+
+def test_sharded_scan_assembles_the_single_gpu_result(case_small):
+    """bin-range shards on one device: element-wise min / max over the per-shard candidate
+    arrays (what the reduce-scatter does across GPUs) reproduces queryKNN exactly."""
+    import torch
+    c = case_small
+    QN, k = c["Q"].shape[0], 256
+    d0, i0 = oracle_query(c, k)
+    world = 3
+    Qd = torch.from_numpy(c["Q"]).cuda()
+    vals, idxs = [], []
+    for r in range(world):
+        t = make_gpu_index(c, shard=(r, world))
+        mv = t.candidateWidth(k)
+        v = torch.empty((QN, mv), dtype=torch.float32, device="cuda")
+        i = torch.empty((QN, mv), dtype=torch.int32, device="cuda")
+        t.queryScanShard(Qd, QN, k, v, i)
+        vals.append(v)
+        idxs.append(i.to(torch.int64) & 0xFFFFFFFF)
+        t.close()
+    val = torch.stack(vals).amin(0).contiguous()
+    idx = torch.stack(idxs).amax(0).to(torch.int32).contiguous()
+    # every slot has exactly one finite owner
+    assert int((torch.stack(vals) < float("inf")).sum(0).min()) == 1
+    t = make_gpu_index(c)
+    oi = torch.zeros((QN, k), dtype=torch.int32, device="cuda")
+    od = torch.zeros((QN, k), dtype=torch.float32, device="cuda")
+    t.rankCandidates(val, idx, QN, mv, k, oi, od)
+    assert np.array_equal(oi.cpu().numpy().view(np.uint32), i0)
+    assert np.array_equal(od.cpu().numpy(), d0)
+    t.close()
