@@ -148,14 +148,16 @@ int pqt_get_db_size(const pqt_index *h, uint32_t *N, uint32_t *line_parts);
 
 /* ---- multi-GPU: bin-range shards ---------------------------------------------- */
 
-/* Keep only the line codes / ids whose position in the bin-ordered list lies in
- * this rank's slice (equal vector counts per rank, cut at bin boundaries).  Call
- * between pqt_create and pqt_set_db.  world = 1 restores the single-GPU layout. */
+/* Keep only the line codes whose position in the bin-ordered list lies in this
+ * rank's slice [rank*N/world, (rank+1)*N/world) -- contiguous bin ranges with equal
+ * vector counts.  Either before pqt_set_db (the slice is all that is uploaded) or
+ * after the index is complete (the resident codes are trimmed in place). */
 int pqt_set_shard(pqt_index *h, uint32_t rank, uint32_t world);
 /* Per-shard half of queryKNN: Steps A-E2 over this rank's candidates only.
- * val/idx: DEVICE [QN][max_vec]; slots owned by other ranks hold +inf / 0 so that
- * an element-wise min / max across ranks (one reduce-scatter or all-reduce)
- * assembles exactly the single-GPU candidate arrays. */
+ * val/idx: DEVICE [QN][max_vec]; slots owned by other ranks hold +inf / INT32_MIN
+ * (0x80000000) so that an element-wise float MIN / signed-int32 MAX across ranks
+ * (one reduce-scatter or all-reduce each) assembles exactly the single-GPU
+ * candidate arrays (vector ids must stay below 2^31 in sharded mode). */
 int pqt_query_scan_shard(pqt_index *h, const float *Q, int q_on_device, uint32_t QN, uint32_t k,
                          float *val, uint32_t *idx);
 /* Ranking half: bitonic network over assembled val/idx (DEVICE [QN][max_vec]) and

@@ -7,6 +7,9 @@ namespace pqtb {
 
 constexpr uint32_t kNumDistSeq = 65536;  // pqt/ProTree.hh:9 NUM_DISTSEQ
 constexpr uint32_t kPadIdx = 0xFFFFFFFFu;
+// id written by a shard into candidate slots it does not own: INT32_MIN, so that an
+// element-wise signed MAX across shards keeps the owner's id (ids < 2^31) or PAD (-1)
+constexpr uint32_t kNotMineIdx = 0x80000000u;
 constexpr float kPadDist = 10000000.f;   // pqt/PerturbationProTree.cu:5333
 constexpr float kPadSortA = 10000000.f;  // :7185
 constexpr float kPadSortC = 1000000000.f;  // :1627

@@ -615,8 +615,26 @@ int pqt_get_tree(const pqt_index* h, float* cb1, float* cb2) {
 // ---- DB -----------------------------------------------------------------------------
 int pqt_set_shard(pqt_index* h, uint32_t rank, uint32_t world) {
   if (!h || !world || rank >= world) return PQT_ERR_INVALID;
-  if (h->has_db && (rank != h->rank || world != h->world))
-    return fail(h, PQT_ERR_STATE, "pqt_set_shard must precede pqt_set_db");
+  if (h->has_db) {
+    CU_TRY(h, cudaSetDevice(h->device));
+    const uint32_t lo = (uint32_t)((uint64_t)h->N * rank / world);
+    const uint32_t hi = (uint32_t)((uint64_t)h->N * (rank + 1) / world);
+    if (h->has_lines) {
+      // trim the resident codes to the new slice (it must lie inside the current one)
+      if (lo < h->pos_lo || hi > h->pos_hi)
+        return fail(h, PQT_ERR_STATE, "pqt_set_shard can only narrow the resident slice; reload the line codes");
+      DevBuf nb;
+      const size_t bytes = (size_t)(hi - lo) * h->LP * 4;
+      CU_TRY(h, nb.ensure(std::max<size_t>(bytes, 16)));
+      CU_TRY(h, cudaMemcpyAsync(nb.p, h->d_codes.as<uint32_t>() + (size_t)(lo - h->pos_lo) * h->LP, bytes,
+                                cudaMemcpyDeviceToDevice, h->stream));
+      CU_TRY(h, cudaStreamSynchronize(h->stream));
+      h->d_codes.release();
+      h->d_codes = nb;
+    }
+    h->pos_lo = lo;
+    h->pos_hi = hi;
+  }
   h->rank = rank;
   h->world = world;
   return PQT_OK;

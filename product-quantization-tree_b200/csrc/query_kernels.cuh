@@ -453,16 +453,18 @@ __global__ void __launch_bounds__(kScanThreads, 1) adc_scan_kernel(ScanArgs a) {
         id = myid;
       } else if (valid) {  // another shard's candidate
         v = __int_as_float(0x7f800000);
-        id = 0;
+        id = kNotMineIdx;
       } else if (a.owns_pad) {
         v = kPadDist;
         id = kPadIdx;
       } else {
         v = __int_as_float(0x7f800000);
-        id = 0;
+        id = kNotMineIdx;
       }
-      oval[ca] = v;
-      oidx[ca] = id;
+      if (ca < a.max_vec) {  // candidate widths below 32 leave the upper lanes idle
+        oval[ca] = v;
+        oidx[ca] = id;
+      }
     }
     __syncthreads();  // everyone is done with s_lut[buf] before it is refilled
     buf ^= 1;
@@ -527,13 +529,15 @@ __global__ void __launch_bounds__(256) adc_scan_generic_kernel(ScanGenericArgs g
         id = myid;
       } else if (valid || !a.owns_pad) {
         v = __int_as_float(0x7f800000);
-        id = 0;
+        id = kNotMineIdx;
       } else {
         v = kPadDist;
         id = kPadIdx;
       }
-      a.out_val[(size_t)qi * a.max_vec + ca] = v;
-      a.out_idx[(size_t)qi * a.max_vec + ca] = id;
+      if (ca < a.max_vec) {
+        a.out_val[(size_t)qi * a.max_vec + ca] = v;
+        a.out_idx[(size_t)qi * a.max_vec + ca] = id;
+      }
     }
   }
 }

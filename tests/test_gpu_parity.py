@@ -136,8 +136,8 @@ def test_error_behaviour(case_small, tmp_path):
     with pytest.raises(pqt_b200.PqtError) as e:  # the shipped tool_query forgets the lines
         t.queryKNN(c["Q"], 4, 4)
     assert "line codes" in str(e.value)
-    with pytest.raises(pqt_b200.PqtError):
-        t.setLines(c["lines"], c["db_idx"].size, 24)  # not a power of two
+    with pytest.raises(pqt_b200.PqtError):  # lineparts must be a power of two <= 32
+        t.setLines(np.zeros((c["db_idx"].size, 24), np.uint32), c["db_idx"].size, 24)
     t.setLines(c["lines"], c["db_idx"].size, prm.line_parts)
     with pytest.raises(pqt_b200.PqtError):
         t.queryKNN(c["Q"], 4, 8192)  # candidate width > 4096
@@ -204,10 +204,10 @@ def test_sharded_scan_assembles_the_single_gpu_result(case_small):
         i = torch.empty((QN, mv), dtype=torch.int32, device="cuda")
         t.queryScanShard(Qd, QN, k, v, i)
         vals.append(v)
-        idxs.append(i.to(torch.int64) & 0xFFFFFFFF)
+        idxs.append(i)
         t.close()
     val = torch.stack(vals).amin(0).contiguous()
-    idx = torch.stack(idxs).amax(0).to(torch.int32).contiguous()
+    idx = torch.stack(idxs).amax(0).contiguous()  # signed max: INT32_MIN marks "not mine"
     # every slot has exactly one finite owner
     assert int((torch.stack(vals) < float("inf")).sum(0).min()) == 1
     t = make_gpu_index(c)
