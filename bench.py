@@ -337,7 +337,8 @@ def run_b200(a, rank, world, local_rank):
         cand_per_launch /= world  # each rank scans its slice of the candidates
     achieved = cand_per_launch * bytes_per_cand / (scan_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "kernel": "adc_scan_kernel",
+                "frac": achieved / peak, "traffic": None,
+                "kernel": "adc_scan_kernel" if sharded else "rerank_kernel (ADC scan + ranking fused)",
                 "peak_source": peak_src,
                 "ms_per_launch": scan_ms, "candidates_per_launch": cand_per_launch,
                 "bytes_per_candidate": bytes_per_cand,
@@ -378,6 +379,7 @@ def run_b200(a, rank, world, local_rank):
         "gpu_launches": int(st.kernel_launches),
         "clocks": clocks,
         "recall_at_1": recall1,
+        "exact_rank_queries_per_step": st.exact_rank_queries / a.steps,
         "parity_vs_oracle_on_cpu_sample": parity,
     }
     print(json.dumps(out), flush=True)

@@ -78,7 +78,9 @@ typedef struct pqt_stats {
   double ms_sort;           /* exact bitonic ranking + top-k emit           */
   double ms_total;          /* first kernel start .. last kernel end        */
   uint64_t scan_launches;   /* launches of the ADC scan kernel              */
-  uint64_t reserved[7];
+  uint64_t exact_rank_queries; /* queries whose ranking needed the exact bitonic network
+                                  (tied or >= 1e7 distances); all others use the fast sort */
+  uint64_t reserved[6];
 } pqt_stats;
 
 /* ---- lifetime ------------------------------------------------------------- */

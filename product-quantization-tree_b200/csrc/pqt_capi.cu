@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "index_kernels.cuh"
 #include "query_kernels.cuh"
+#include "rerank_kernels.cuh"
 
 using namespace pqtb;
 
@@ -53,6 +54,8 @@ struct pqt_index {
   int num_sms = 148;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // device->host result copies, overlapped with the next slab
+  std::vector<cudaEvent_t> slab_ev;
   mutable std::string err;
   pqt_params prm{};
 
@@ -60,9 +63,11 @@ struct pqt_index {
   uint32_t dim = 0, p = 0, c1 = 0, c2 = 0, vl = 0;
   std::vector<float> h_cb1, h_cb2;
   DevBuf d_cb1, d_cb2;
+  DevBuf d_cb1T, d_cb2T;  // cb1T[dim][c1], cb2T[p][c1][vl][c2] (coalesced reads in tables_warp_kernel)
 
   // traversal order (prepareDistSequence), cached per (m, p)
   DevBuf d_distseq;
+  DevBuf d_seqnib;  // same codes with the rank of part j in nibble j
   std::vector<uint32_t> h_distseq;
   uint32_t seq_m = 0, seq_p = 0;
 
@@ -87,6 +92,7 @@ struct pqt_index {
   bool debug = false;
   uint32_t dbg_QN = 0, dbg_k = 0, dbg_maxvec = 0;
   DevBuf g_assign, g_lut, g_aval, g_aidx, g_bins, g_nbins, g_sel;
+  DevBuf d_exact;  // one uint64: queries ranked by the exact-network fallback
 
   // profiling
   bool profile = false;
@@ -122,6 +128,8 @@ int fail(const pqt_index* h, int code, const char* fmt, ...) {
   } while (0)
 
 bool is_pow2(uint32_t x) { return x && !(x & (x - 1)); }
+
+constexpr uint32_t kSlabQueries = 2048;  // queries per pipelined slab (host outputs)
 
 int check_tree_shape(const pqt_index* h, uint32_t dim, uint32_t p, uint32_t c1, uint32_t c2) {
   if (!dim || !p || !c1 || !c2) return fail(h, PQT_ERR_INVALID, "zero-sized tree shape");
@@ -161,6 +169,18 @@ int ensure_dist_seq(pqt_index* h, uint32_t max_cluster) {
   CU_TRY(h, h->d_distseq.ensure(kNumDistSeq * sizeof(uint32_t)));
   CU_TRY(h, cudaMemcpyAsync(h->d_distseq.p, h->h_distseq.data(), kNumDistSeq * sizeof(uint32_t),
                             cudaMemcpyHostToDevice, h->stream));
+  std::vector<uint32_t> nib(kNumDistSeq, 0u);
+  for (uint32_t i = 0; i < kNumDistSeq; i++) {
+    uint32_t code = h->h_distseq[i], v = 0;
+    for (uint32_t j = 0; j < h->p; j++) v |= ((code / den[j]) % m) << (4 * j);
+    // bins2_kernel layout: batch of kBins2Threads*kProbesPerThread probes stored [r][thread]
+    const uint32_t batch = kBins2Threads * kProbesPerThread;
+    const uint32_t b = i / batch, u = i % batch;
+    nib[b * batch + (u % kProbesPerThread) * kBins2Threads + u / kProbesPerThread] = v;
+  }
+  CU_TRY(h, h->d_seqnib.ensure(kNumDistSeq * sizeof(uint32_t)));
+  CU_TRY(h, cudaMemcpyAsync(h->d_seqnib.p, nib.data(), kNumDistSeq * sizeof(uint32_t),
+                            cudaMemcpyHostToDevice, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   h->seq_m = m;
   h->seq_p = h->p;
@@ -174,6 +194,24 @@ int upload_tree(pqt_index* h) {
                             cudaMemcpyHostToDevice, h->stream));
   CU_TRY(h, cudaMemcpyAsync(h->d_cb2.p, h->h_cb2.data(), h->h_cb2.size() * sizeof(float),
                             cudaMemcpyHostToDevice, h->stream));
+  // transposed copies: lanes run over centroids, so centroid must be the fastest index
+  {
+    const uint32_t dim = h->dim, c1 = h->c1, c2 = h->c2, p = h->p, vl = h->vl;
+    std::vector<float> t1((size_t)dim * c1), t2((size_t)p * c1 * vl * c2);
+    for (uint32_t c = 0; c < c1; c++)
+      for (uint32_t d = 0; d < dim; d++) t1[(size_t)d * c1 + c] = h->h_cb1[(size_t)c * dim + d];
+    for (uint32_t part = 0; part < p; part++)
+      for (uint32_t l1 = 0; l1 < c1; l1++)
+        for (uint32_t l2 = 0; l2 < c2; l2++)
+          for (uint32_t t = 0; t < vl; t++)
+            t2[(((size_t)part * c1 + l1) * vl + t) * c2 + l2] =
+                h->h_cb2[(((size_t)part * c1 + l1) * c2 + l2) * vl + t];
+    CU_TRY(h, h->d_cb1T.ensure(t1.size() * sizeof(float)));
+    CU_TRY(h, h->d_cb2T.ensure(t2.size() * sizeof(float)));
+    CU_TRY(h, cudaMemcpyAsync(h->d_cb1T.p, t1.data(), t1.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->d_cb2T.p, t2.data(), t2.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+  }
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   h->has_lines = false;  // cbDist depends on cb1
   return PQT_OK;
@@ -253,8 +291,11 @@ struct QueryPlan {
 
 // Steps A..E2 (distance part) for QN queries already on the device; fills
 // val/idx [QN][max_vec].  Records profile events ev[0..3] when enabled.
+// With fused_out_* set (single GPU) the scan, the ranking and the first-k emit run in one
+// kernel and d_val/d_idx are not touched.
 int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float* d_val,
-                   uint32_t* d_idx) {
+                   uint32_t* d_idx, float* fused_out_dist = nullptr,
+                   uint32_t* fused_out_idx = nullptr) {
   const uint32_t max_vec = candidate_width(h, k);
   const pqt_params& P = h->prm;
   PQ_TRY(ensure_dist_seq(h, h->c2 * P.k1));  // :8191
@@ -299,39 +340,55 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
       a.dbg_aval = h->g_aval.as<float>();
       a.dbg_aidx = h->g_aidx.as<uint32_t>();
     }
-    const uint32_t npMax = std::max(a.npA, a.npC);
-    size_t smem = (size_t)(h->dim + 2 * h->p * npMax + P.k1 * h->p) * 4;
-    if (smem > 48 * 1024)
-      CU_TRY(h, cudaFuncSetAttribute(tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 16);
-    tables_kernel<<<grid, 128, smem, h->stream>>>(a);
+    const bool warp_path = h->c1 <= 32 && P.k1 <= 32 && (h->LP % h->p) == 0 &&
+                           (h->vl == 8 || h->vl == 16 || h->vl == 32) && a.npC >= 2 && (h->dim % 4) == 0;
+    if (warp_path) {
+      TablesWarpArgs w{};
+      w.t = a;
+      w.cb1T = h->d_cb1T.as<float>();
+      w.cb2T = h->d_cb2T.as<float>();
+      size_t smem = (size_t)(h->dim + h->c1 * 32 + 2 * kTablesWarps * a.npC) * 4;
+      uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 12);
+      switch (h->vl) {
+        case 8: tables_warp_kernel<8><<<grid, kTablesWarps * 32, smem, h->stream>>>(w); break;
+        case 16: tables_warp_kernel<16><<<grid, kTablesWarps * 32, smem, h->stream>>>(w); break;
+        default: tables_warp_kernel<32><<<grid, kTablesWarps * 32, smem, h->stream>>>(w); break;
+      }
+    } else {
+      const uint32_t npMax = std::max(a.npA, a.npC);
+      size_t smem = (size_t)(h->dim + 2 * h->p * npMax + P.k1 * h->p) * 4;
+      if (smem > 48 * 1024)
+        CU_TRY(h, cudaFuncSetAttribute(tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 16);
+      tables_kernel<<<grid, 128, smem, h->stream>>>(a);
+    }
     CU_TRY(h, cudaGetLastError());
     h->stats.kernel_launches++;
   }
   if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[1], h->stream));
   // ---- Steps D+E1
   {
-    BinsArgs a{};
+    Bins2Args a{};
     a.idx16 = h->s_idx16.as<uint32_t>();
-    a.dist_seq = h->d_distseq.as<uint32_t>();
+    a.seq_nib = h->d_seqnib.as<uint32_t>();
     a.dir.bitmap = h->d_bitmap.as<uint32_t>();
     a.dir.rank_base = h->d_rank_base.as<uint32_t>();
     a.dir.cprefix = h->d_cprefix.as<uint32_t>();
-    a.hash = make_fastmod(h->db_hash_size);
-    a.QN = QN; a.p = h->p; a.m = m; a.c1c2 = h->c1 * h->c2;
-    a.max_bins = P.max_bins; a.max_trials = P.max_trials; a.bin_threads = P.bin_threads;
-    a.max_vec_per_bin = P.max_vec_per_bin; a.max_vec = max_vec;
+    a.hash = make_magicmod(h->db_hash_size);
+    a.QN = QN; a.p = h->p; a.c1c2 = h->c1 * h->c2;
+    a.n_probes = P.max_trials * P.bin_threads;
+    a.max_bins = P.max_bins; a.max_vec_per_bin = P.max_vec_per_bin; a.max_vec = max_vec;
     a.cand_pos = h->s_cand.as<uint32_t>();
     a.n_vec = h->s_nvec.as<uint32_t>();
     if (h->debug) {
       a.dbg_bins = h->g_bins.as<uint32_t>();
       a.dbg_nbins = h->g_nbins.as<uint32_t>();
     }
-    size_t smem = (size_t)(P.max_bins + h->p * 16 + 32) * 4;
+    size_t smem = (size_t)(P.max_bins + ((h->p + 1) / 2) * 256 + 32) * 4;
     if (smem > 48 * 1024)
-      CU_TRY(h, cudaFuncSetAttribute(bins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU_TRY(h, cudaFuncSetAttribute(bins2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 8);
-    bins_kernel<<<grid, kBinsThreads, smem, h->stream>>>(a);
+    bins2_kernel<<<grid, kBins2Threads, smem, h->stream>>>(a);
     CU_TRY(h, cudaGetLastError());
     h->stats.kernel_launches++;
   }
@@ -352,7 +409,31 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
     a.out_val = d_val;
     a.out_idx = d_idx;
     size_t smem = ((size_t)h->c1 * h->c1 * 32 + 2 * (size_t)h->c1 * 32) * 4 + 64;
-    if (smem <= 220 * 1024) {
+    const size_t smem_fused = smem + 3 * (size_t)max_vec * 4;
+    if (fused_out_dist && smem_fused <= 220 * 1024) {
+      RerankArgs g{};
+      g.s = a;
+      g.k = k;
+      g.out_dist = fused_out_dist;
+      g.out_idx = fused_out_idx;
+      g.exact_counter = h->d_exact.as<unsigned long long>();
+      uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms);
+#define LAUNCH_RERANK(LPV)                                                                       \
+  do {                                                                                           \
+    CU_TRY(h, cudaFuncSetAttribute(rerank_kernel<LPV>,                                           \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused)); \
+    rerank_kernel<LPV><<<grid, kScanThreads, smem_fused, h->stream>>>(g);                        \
+  } while (0)
+      switch (h->LP) {
+        case 1: LAUNCH_RERANK(1); break;
+        case 2: LAUNCH_RERANK(2); break;
+        case 4: LAUNCH_RERANK(4); break;
+        case 8: LAUNCH_RERANK(8); break;
+        case 16: LAUNCH_RERANK(16); break;
+        default: LAUNCH_RERANK(32); break;
+      }
+#undef LAUNCH_RERANK
+    } else if (smem <= 220 * 1024) {
       uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms);
 #define LAUNCH_SCAN(LPV)                                                                         \
   do {                                                                                           \
@@ -393,13 +474,15 @@ int run_rank(pqt_index* h, const float* d_val, const uint32_t* d_idx, uint32_t Q
   if (!is_pow2(max_vec) || max_vec > 4096)
     return fail(h, PQT_ERR_INVALID, "candidate width %u must be a power of two <= 4096", max_vec);
   if (k > max_vec) return fail(h, PQT_ERR_INVALID, "k %u > candidate width %u", k, max_vec);
-  RankArgs a{};
+  Rank2Args a{};
   a.val = d_val; a.idx = d_idx; a.QN = QN; a.max_vec = max_vec; a.k = k;
   a.out_dist = d_out_dist; a.out_idx = d_out_idx;
-  size_t smem = (size_t)max_vec * 8;
-  uint32_t threads = std::min<uint32_t>(kRankThreads, std::max<uint32_t>(32, max_vec / 2));
-  uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 4);
-  rank_kernel<<<grid, threads, smem, h->stream>>>(a);
+  a.exact_counter = h->d_exact.as<unsigned long long>();
+  size_t smem = (size_t)max_vec * 12 + 16;
+  if (smem > 48 * 1024)
+    CU_TRY(h, cudaFuncSetAttribute(rank2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 2);
+  rank2_kernel<<<grid, kScanThreads, smem, h->stream>>>(a);
   CU_TRY(h, cudaGetLastError());
   h->stats.kernel_launches++;
   return PQT_OK;
@@ -494,7 +577,16 @@ int pqt_create(uint32_t dim, uint32_t p, uint32_t p2, int device, pqt_index** ou
     return PQT_ERR_CUDA;
   }
   h->stream = h->own_stream;
+  if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaStreamDestroy(h->own_stream);
+    delete h;
+    return PQT_ERR_CUDA;
+  }
   for (auto& e : h->ev) cudaEventCreate(&e);
+  if (h->d_exact.ensure(8) != cudaSuccess || cudaMemset(h->d_exact.p, 0, 8) != cudaSuccess) {
+    pqt_destroy(h);
+    return PQT_ERR_CUDA;
+  }
   *out = h;
   return PQT_OK;
 }
@@ -503,13 +595,15 @@ int pqt_destroy(pqt_index* h) {
   if (!h) return PQT_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  for (DevBuf* b : {&h->d_cb1, &h->d_cb2, &h->d_distseq, &h->d_bitmap, &h->d_rank_base, &h->d_cprefix,
+  for (DevBuf* b : {&h->d_cb1, &h->d_cb2, &h->d_cb1T, &h->d_cb2T, &h->d_distseq, &h->d_seqnib, &h->d_bitmap, &h->d_rank_base, &h->d_cprefix,
                     &h->d_dbidx, &h->d_codes, &h->d_cbd, &h->d_cbd_dup, &h->s_q, &h->s_lut, &h->s_idx16,
                     &h->s_cand, &h->s_nvec, &h->s_val, &h->s_idx, &h->s_outd, &h->s_outi, &h->g_assign,
-                    &h->g_lut, &h->g_aval, &h->g_aidx, &h->g_bins, &h->g_nbins, &h->g_sel})
+                    &h->g_lut, &h->g_aval, &h->g_aidx, &h->g_bins, &h->g_nbins, &h->g_sel, &h->d_exact})
     b->release();
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : h->slab_ev) cudaEventDestroy(e);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return PQT_OK;
@@ -850,8 +944,6 @@ int pqt_query_knn(pqt_index* h, const float* Q, int q_on_device, uint32_t QN, ui
     CU_TRY(h, cudaMemcpyAsync(h->s_q.p, Q, (size_t)QN * h->dim * 4, cudaMemcpyHostToDevice, h->stream));
     dQ = h->s_q.as<float>();
   }
-  CU_TRY(h, h->s_val.ensure((size_t)QN * max_vec * 4));
-  CU_TRY(h, h->s_idx.ensure((size_t)QN * max_vec * 4));
   float* d_out_dist = dist;
   uint32_t* d_out_idx = idx;
   if (!out_on_device) {
@@ -860,16 +952,60 @@ int pqt_query_knn(pqt_index* h, const float* Q, int q_on_device, uint32_t QN, ui
     d_out_dist = h->s_outd.as<float>();
     d_out_idx = h->s_outi.as<uint32_t>();
   }
-  PQ_TRY(run_scan_chain(h, dQ, QN, k, h->s_val.as<float>(), h->s_idx.as<uint32_t>()));
-  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
-  PQ_TRY(run_rank(h, h->s_val.as<float>(), h->s_idx.as<uint32_t>(), QN, max_vec, k, d_out_dist, d_out_idx));
-  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+  const bool fused = ((size_t)h->c1 * h->c1 * 32 + 2 * (size_t)h->c1 * 32 + 3 * (size_t)max_vec) * 4 + 64 <= 220 * 1024;
+  // Host outputs: queries go through in slabs so that the device->host copy of one slab
+  // (on the copy stream) overlaps the kernels of the next.  Device outputs / debug
+  // recording: one pass.
+  const uint32_t slab = (out_on_device || h->debug) ? QN : std::min<uint32_t>(QN, kSlabQueries);
+  const uint32_t nslabs = (QN + slab - 1) / slab;
   if (!out_on_device) {
-    CU_TRY(h, cudaMemcpyAsync(idx, d_out_idx, (size_t)QN * k * 4, cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(dist, d_out_dist, (size_t)QN * k * 4, cudaMemcpyDeviceToHost, h->stream));
+    while (h->slab_ev.size() < nslabs) {
+      cudaEvent_t e;
+      CU_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->slab_ev.push_back(e);
+    }
+  }
+  auto issue_copy = [&](uint32_t s) -> int {
+    const uint32_t q0 = s * slab, n = std::min(slab, QN - q0);
+    CU_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->slab_ev[s], 0));
+    CU_TRY(h, cudaMemcpyAsync(idx + (size_t)q0 * k, d_out_idx + (size_t)q0 * k, (size_t)n * k * 4,
+                              cudaMemcpyDeviceToHost, h->copy_stream));
+    CU_TRY(h, cudaMemcpyAsync(dist + (size_t)q0 * k, d_out_dist + (size_t)q0 * k, (size_t)n * k * 4,
+                              cudaMemcpyDeviceToHost, h->copy_stream));
+    return PQT_OK;
+  };
+  for (uint32_t s = 0; s < nslabs; s++) {
+    const uint32_t q0 = s * slab, n = std::min(slab, QN - q0);
+    const float* q = dQ + (size_t)q0 * h->dim;
+    float* od = d_out_dist + (size_t)q0 * k;
+    uint32_t* oi = d_out_idx + (size_t)q0 * k;
+    if (fused) {
+      PQ_TRY(run_scan_chain(h, q, n, k, nullptr, nullptr, od, oi));
+      if (h->profile) {
+        CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
+        CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+      }
+    } else {
+      CU_TRY(h, h->s_val.ensure((size_t)n * max_vec * 4));
+      CU_TRY(h, h->s_idx.ensure((size_t)n * max_vec * 4));
+      PQ_TRY(run_scan_chain(h, q, n, k, h->s_val.as<float>(), h->s_idx.as<uint32_t>()));
+      if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
+      PQ_TRY(run_rank(h, h->s_val.as<float>(), h->s_idx.as<uint32_t>(), n, max_vec, k, od, oi));
+      if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+    }
+    if (!out_on_device) CU_TRY(h, cudaEventRecord(h->slab_ev[s], h->stream));
+    if (h->profile) {
+      CU_TRY(h, cudaStreamSynchronize(h->stream));
+      accumulate_profile(h, n, true);
+    }
+    // the previous slab's copy is issued after this slab's kernels are in flight
+    if (!out_on_device && s > 0) PQ_TRY(issue_copy(s - 1));
+  }
+  if (!out_on_device) {
+    PQ_TRY(issue_copy(nslabs - 1));
+    CU_TRY(h, cudaStreamSynchronize(h->copy_stream));
   }
   CU_TRY(h, cudaStreamSynchronize(h->stream));
-  if (h->profile) accumulate_profile(h, QN, true);
   return PQT_OK;
 }
 
@@ -928,11 +1064,19 @@ int pqt_profile_enable(pqt_index* h, int on) {
 int pqt_get_stats(const pqt_index* h, pqt_stats* st) {
   if (!h || !st) return PQT_ERR_INVALID;
   *st = h->stats;
+  unsigned long long ex = 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  cudaMemcpy(&ex, h->d_exact.p, 8, cudaMemcpyDeviceToHost);
+  st->exact_rank_queries = ex;
   return PQT_OK;
 }
 int pqt_reset_stats(pqt_index* h) {
   if (!h) return PQT_ERR_INVALID;
   std::memset(&h->stats, 0, sizeof(h->stats));
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  cudaMemset(h->d_exact.p, 0, 8);
   return PQT_OK;
 }
 int pqt_debug_enable(pqt_index* h, int on) {

@@ -28,7 +28,7 @@ __device__ __forceinline__ void bitonic_smem(float* val, uint32_t* idx, uint32_t
     for (uint32_t j = k >> 1; j > 0; j >>= 1) {
       for (uint32_t e = threadIdx.x; e < total; e += blockDim.x) {
         uint32_t arr = e / half, t = e - arr * half;
-        uint32_t i = ((t / j) * (j << 1)) + (t % j);  // (i & j) == 0
+        uint32_t i = 2 * t - (t & (j - 1));  // t = q*j + r -> i = q*2j + r, (i & j) == 0
         uint32_t a = arr * n + i, b = a + j;
         float va = val[a], vb = val[b];
         bool sw = ((i & k) == 0) ? (va > vb) : (va < vb);
@@ -584,6 +584,176 @@ __global__ void gather_select_idx_kernel(const uint32_t* cand_pos, const uint32_
        e += (size_t)gridDim.x * blockDim.x) {
     uint32_t qi = (uint32_t)(e / max_vec), ca = (uint32_t)(e - (size_t)qi * max_vec);
     out[e] = (ca < n_vec[qi]) ? ids[cand_pos[e]] : 0u;
+  }
+}
+
+// ============================================================================
+// tables_warp_kernel: Steps A+B+C, warp-per-(query, part) version for the common
+// shapes (c1 <= 32, LP % p == 0, vl in {8,16,32,64}).  Same arithmetic as
+// tables_kernel; what changes is the mapping:
+//   * lanes run over centroids and read TRANSPOSED codebooks (cb1T[dim][c1],
+//     cb2T[p][c1][vl][c2]) so that every load is one coalesced 128-byte request;
+//   * the squared differences of a part are formed once in registers and feed both
+//     the Step-A tree (over vl) and the Step-B trees (over dim/LP);
+//   * the Step-A network runs on shuffles, the Step-C network in a warp-private
+//     shared-memory array (no block barriers).
+// ============================================================================
+struct TablesWarpArgs {
+  TablesArgs t;
+  const float* cb1T;  // [dim][c1]
+  const float* cb2T;  // [p][c1][vl][c2]
+};
+
+constexpr int kTablesWarps = 4;
+
+// warp-private bitonic network over n (power of two >= 2) elements in shared memory
+__device__ __forceinline__ void bitonic_warp_smem(float* val, uint32_t* idx, uint32_t n,
+                                                  uint32_t lane) {
+  const uint32_t half = n >> 1;
+  for (uint32_t k = 2; k <= n; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = lane; t < half; t += 32) {
+        uint32_t i = 2 * t - (t & (j - 1));
+        uint32_t b = i + j;
+        float va = val[i], vb = val[b];
+        bool sw = ((i & k) == 0) ? (va > vb) : (va < vb);
+        if (sw) {
+          val[i] = vb;
+          val[b] = va;
+          uint32_t ia = idx[i];
+          idx[i] = idx[b];
+          idx[b] = ia;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <int VL>
+__global__ void __launch_bounds__(kTablesWarps * 32) tables_warp_kernel(TablesWarpArgs w) {
+  const TablesArgs& a = w.t;
+  extern __shared__ float smem_f[];
+  float* sq = smem_f;                                   // [dim]
+  float* s_lut = sq + a.dim;                            // [c1*32]
+  float* s_sortv = s_lut + a.c1 * 32;                   // [warps][npC]
+  uint32_t* s_sorti = reinterpret_cast<uint32_t*>(s_sortv + kTablesWarps * a.npC);
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t segs = a.LP / a.p;  // line segments inside one part
+  const uint32_t R = 32 / a.LP;
+  const uint32_t n = a.k1 * a.c2;
+
+  for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < a.dim; t += blockDim.x) sq[t] = a.Q[(size_t)qi * a.dim + t];
+    __syncthreads();
+
+    for (uint32_t part = warp; part < a.p; part += kTablesWarps) {
+      float qreg[VL];
+#pragma unroll
+      for (int t = 0; t < VL; t++) qreg[t] = sq[part * VL + t];
+
+      // ---- Steps A + B: lane = L1 centroid
+      float va = kPadSortA;
+      uint32_t ia = kPadIdx;
+      if (lane < a.c1) {
+        float s[VL], tb[VL];
+        const float* cb = w.cb1T + (size_t)(part * VL) * a.c1 + lane;
+#pragma unroll
+        for (int t = 0; t < VL; t++) {
+          float d = __fsub_rn(qreg[t], __ldg(cb + (size_t)t * a.c1));
+          s[t] = __fmul_rn(d, d);
+          tb[t] = s[t];
+        }
+        // Step B trees over sl = VL / segs elements (:7764-7776)
+#pragma unroll
+        for (int stride = VL / 2; stride > 0; stride >>= 1) {
+          if ((uint32_t)stride < a.sl) {
+#pragma unroll
+            for (int j = 0; j + stride < VL; j++)
+              if (((uint32_t)j & (a.sl - 1)) < (uint32_t)stride) tb[j] = __fadd_rn(tb[j], tb[j + stride]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < VL; j++) {
+          if (((uint32_t)j & (a.sl - 1)) == 0) {
+            const uint32_t lp = part * segs + (uint32_t)j / a.sl;
+            for (uint32_t r = 0; r < R; r++) s_lut[lane * 32 + r * a.LP + lp] = tb[j];
+            if (a.dbg_lut) a.dbg_lut[((size_t)qi * a.LP + lp) * a.c1 + lane] = tb[j];
+          }
+        }
+        // Step A tree over vl (:7151-7159)
+#pragma unroll
+        for (int stride = VL / 2; stride > 0; stride >>= 1) {
+#pragma unroll
+          for (int j = 0; j < stride; j++) s[j] = __fadd_rn(s[j], s[j + stride]);
+        }
+        va = s[0];
+        ia = lane;
+      }
+      // bitonic network over npA <= 32 lanes (pqt/bitonicSort.cuh:16-44)
+      for (uint32_t k = 2; k <= a.npA; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+          float ov = __shfl_xor_sync(0xffffffffu, va, j);
+          uint32_t oi = __shfl_xor_sync(0xffffffffu, ia, j);
+          const bool lower = (lane & j) == 0;
+          const float lo = lower ? va : ov, hi = lower ? ov : va;
+          const bool sw = ((lane & k) == 0) ? (lo > hi) : (lo < hi);
+          if (sw && lane < a.npA) {
+            va = ov;
+            ia = oi;
+          }
+        }
+      }
+      if (a.dbg_assign && lane < a.k1) a.dbg_assign[(size_t)qi * a.k1 * a.p + lane * a.p + part] = ia;
+
+      // ---- Step C: entry e = k*c2 + l2, lanes over e (coalesced over l2)
+      float* sv = s_sortv + warp * a.npC;
+      uint32_t* si = s_sorti + warp * a.npC;
+      for (uint32_t e0 = 0; e0 < a.npC; e0 += 32) {
+        const uint32_t e = e0 + lane;
+        float v = kPadSortC;
+        uint32_t id = kPadIdx;
+        // all lanes take part in the shuffle; k is warp-uniform only when c2 >= 32
+        const uint32_t k = e < n ? e / a.c2 : 0, l2 = e < n ? e - k * a.c2 : 0;
+        const uint32_t l1 = __shfl_sync(0xffffffffu, ia, k);
+        if (e < n) {
+          const float* cb = w.cb2T + ((size_t)(part * a.c1 + l1) * VL) * a.c2 + l2;
+          float s[VL];
+#pragma unroll
+          for (int t = 0; t < VL; t++) {
+            float d = __fsub_rn(qreg[t], __ldg(cb + (size_t)t * a.c2));
+            s[t] = __fmul_rn(d, d);
+          }
+#pragma unroll
+          for (int stride = VL / 2; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int j = 0; j < stride; j++) s[j] = __fadd_rn(s[j], s[j + stride]);
+          }
+          v = s[0];
+          id = l2 + l1 * a.c2;
+        }
+        if (e < a.npC) {
+          sv[e] = v;
+          si[e] = id;
+        }
+      }
+      __syncwarp();
+      bitonic_warp_smem(sv, si, a.npC, lane);
+      if (lane < 16) a.idx16[((size_t)qi * a.p + part) * 16 + lane] = (lane < a.m) ? si[lane] : 0u;
+      if (a.dbg_aval) {
+        for (uint32_t e = lane; e < n; e += 32) {
+          a.dbg_aval[((size_t)qi * a.p + part) * n + e] = sv[e];
+          a.dbg_aidx[((size_t)qi * a.p + part) * n + e] = si[e];
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    // LUT rows out, coalesced
+    float4* dst = reinterpret_cast<float4*>(a.lut_dup + (size_t)qi * a.c1 * 32);
+    const float4* src = reinterpret_cast<const float4*>(s_lut);
+    for (uint32_t e = threadIdx.x; e < a.c1 * 8; e += blockDim.x) dst[e] = src[e];
   }
 }
 

@@ -1,0 +1,520 @@
+// rerank_kernels.cuh -- second-generation per-query kernels:
+//
+//   bins2_kernel    Steps D+E1 with nibble-packed traversal codes, per-query pair
+//                   tables for the Horner hash, multiply-shift modulo, and all probes
+//                   of a query issued in a few large batches (no per-trial barriers)
+//   rerank_kernel   Step E2 fused: ADC scan -> shared memory -> ranking -> first k,
+//                   one persistent CTA per SM; the (val, idx) candidate arrays never
+//                   touch HBM
+//   rank2_kernel    ranking only (multi-GPU path: after the shards are assembled)
+//
+// Ranking.  The reference ranks with a bitonic network (pqt/bitonicSort.cuh:16-78),
+// whose output is a plain ascending sort whenever all keys are distinct; only ties
+// make the network's own (unstable) order observable.  So the kernels sort the nVec
+// real candidates with a register/shuffle bitonic sort of pow2ceil(nVec) elements,
+// then check (a) every real distance < 1e7 (the pad value) and (b) no two adjacent
+// sorted distances are equal unless they belong to the same vector id.  If either check fails the query is re-ranked with the
+// exact max_vec-wide network in shared memory, candidate order restored first.  Both
+// paths therefore return exactly what the reference's network returns.
+#pragma once
+#include "common.cuh"
+#include "query_kernels.cuh"
+
+namespace pqtb {
+
+// ---- exact x / d, x % d by multiply-shift when a 32-bit magic exists ----------------
+struct MagicMod {
+  uint32_t d, magic, shift, use64;
+  FastMod f64;
+};
+inline MagicMod make_magicmod(uint32_t d) {
+  MagicMod m{};
+  m.d = d;
+  m.f64 = make_fastmod(d);
+  m.use64 = 1;
+  if (d <= 1) return m;
+  // q = umulhi(x, magic) >> shift is exact for all 32-bit x iff
+  // magic*d - 2^(32+shift) <= 2^shift  (Granlund-Montgomery)
+  for (uint32_t s = 0; s < 32; s++) {
+    unsigned __int128 p = (unsigned __int128)1 << (32 + s);
+    unsigned __int128 mg = (p + d - 1) / d;
+    if (mg >> 32) continue;
+    unsigned __int128 e = mg * d - p;
+    if (e <= ((unsigned __int128)1 << s)) {
+      m.magic = (uint32_t)mg;
+      m.shift = s;
+      m.use64 = 0;
+      break;
+    }
+  }
+  return m;
+}
+__device__ __forceinline__ uint32_t magicmod(uint32_t x, const MagicMod& m) {
+  if (m.use64) return fastmod(x, m.f64);
+  uint32_t q = __umulhi(x, m.magic) >> m.shift;
+  return x - q * m.d;
+}
+
+// ============================================================================
+// Steps D + E1, v2.
+// Step D's trial structure only decides where the walk stops, and a stop can only
+// happen once max_bins bins are kept -- after which nothing is written any more.
+// Net effect: walk the first max_trials*bin_threads traversal
+// codes in order, keep the non-empty bins at 1-based slots < max_bins,
+// nBins = min(#kept, max_bins).  The kernel walks them in batches of
+// kBins2Threads*kProbesPerThread probes (consecutive per thread, so one block scan
+// per batch orders them) and stops early once max_bins are kept.
+// ============================================================================
+struct Bins2Args {
+  const uint32_t* idx16;    // [QN][p][16]
+  const uint32_t* seq_nib;  // [65536] traversal codes, nibble j = rank in part j; stored per
+                            // batch as [r][thread] so that thread-consecutive probes
+                            // (t = b0 + thread*16 + r) are read with coalesced loads
+  BinDir dir;
+  MagicMod hash;
+  uint32_t QN, p, c1c2;
+  uint32_t n_probes;  // max_trials * bin_threads
+  uint32_t max_bins, max_vec_per_bin, max_vec;
+  uint32_t* cand_pos;
+  uint32_t* n_vec;
+  uint32_t* dbg_bins;
+  uint32_t* dbg_nbins;
+};
+
+constexpr int kBins2Threads = 256;
+constexpr int kProbesPerThread = 16;
+
+// dynamic smem: list[max_bins] | pair tables [npairs][256] | warp_sums[32]
+__global__ void __launch_bounds__(kBins2Threads) bins2_kernel(Bins2Args a) {
+  extern __shared__ uint32_t smem_u[];
+  uint32_t* list = smem_u;
+  uint32_t* pairs = list + a.max_bins;
+  const uint32_t npairs = (a.p + 1) >> 1;
+  uint32_t* warp_sums = pairs + npairs * 256;
+  const uint32_t K = a.c1c2;
+  // multiplier that shifts a value past one pair / one single part in the Horner chain
+  const uint32_t K2 = K * K;
+
+  for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
+    __syncthreads();
+    // pair tables: T[pr][r0 | r1 << 4] = idx[2pr][r0] * K + idx[2pr+1][r1]  (uint32 wrap)
+    const uint32_t* gi = a.idx16 + (size_t)qi * a.p * 16;
+    for (uint32_t e = threadIdx.x; e < npairs * 256; e += blockDim.x) {
+      uint32_t pr = e >> 8, r0 = e & 15, r1 = (e >> 4) & 15;
+      uint32_t j0 = 2 * pr, j1 = j0 + 1;
+      uint32_t v = __ldg(gi + j0 * 16 + r0);
+      if (j1 < a.p) v = v * K + __ldg(gi + j1 * 16 + r1);
+      pairs[e] = v;
+    }
+    if (threadIdx.x == 0) list[0] = 0;  // slot 0 keeps the memset value (:3561)
+    __syncthreads();
+
+    uint32_t n_out = 0;
+    const uint32_t batch = kBins2Threads * kProbesPerThread;
+    for (uint32_t b0 = 0; b0 < a.n_probes && n_out < a.max_bins; b0 += batch) {
+      const uint32_t t0 = b0 + threadIdx.x * kProbesPerThread;
+      uint32_t bins[kProbesPerThread];
+      uint32_t words[kProbesPerThread];
+#pragma unroll
+      for (int r = 0; r < kProbesPerThread; r++) {
+        const uint32_t t = t0 + r;
+        uint32_t bin = 0, word = 0;
+        if (t < a.n_probes) {
+          const uint32_t s = __ldg(a.seq_nib + b0 + r * kBins2Threads + threadIdx.x);
+          uint32_t o = pairs[s & 0xFF];
+          for (uint32_t pr = 1; pr < npairs; pr++) {
+            const bool full = (2 * pr + 1) < a.p;
+            o = o * (full ? K2 : K) + pairs[pr * 256 + ((s >> (8 * pr)) & 0xFF)];
+          }
+          bin = magicmod(o, a.hash);
+          word = __ldg(a.dir.bitmap + (bin >> 5));
+        }
+        bins[r] = bin;
+        words[r] = word;
+      }
+      uint32_t keep_mask = 0;
+#pragma unroll
+      for (int r = 0; r < kProbesPerThread; r++) {
+        const bool keep = (t0 + r < a.n_probes) && ((words[r] >> (bins[r] & 31)) & 1u);
+        keep_mask |= (keep ? 1u : 0u) << r;
+      }
+      uint32_t total;
+      uint32_t pos = n_out + block_exscan(__popc(keep_mask), warp_sums, total);
+#pragma unroll
+      for (int r = 0; r < kProbesPerThread; r++) {
+        if ((keep_mask >> r) & 1u) {
+          pos++;  // inclusive-scan position: 1-based (:3504-3510)
+          if (pos < a.max_bins) list[pos] = bins[r];
+        }
+      }
+      n_out += total;
+    }
+    __syncthreads();
+    const uint32_t nb = n_out < a.max_bins ? n_out : a.max_bins;
+    if (a.dbg_bins) {
+      for (uint32_t e = threadIdx.x; e < a.max_bins; e += blockDim.x)
+        a.dbg_bins[(size_t)qi * a.max_bins + e] =
+            (e == 0) ? 0u : ((e <= n_out && e < a.max_bins) ? list[e] : 0u);
+      if (threadIdx.x == 0) a.dbg_nbins[qi] = nb;
+    }
+
+    // ---- Step E1 (:4339-4417)
+    uint32_t offset = 0;
+    uint32_t* cand = a.cand_pos + (size_t)qi * a.max_vec;
+    for (uint32_t b0 = 0; b0 < nb && offset < a.max_vec; b0 += blockDim.x) {
+      uint32_t b = b0 + threadIdx.x;
+      uint32_t start = 0, nv = 0;
+      if (b < nb) {
+        uint32_t cnt;
+        dir_lookup(a.dir, list[b], start, cnt);
+        nv = cnt < a.max_vec_per_bin ? cnt : a.max_vec_per_bin;
+      }
+      uint32_t total;
+      uint32_t pos = offset + block_exscan(nv, warp_sums, total);
+      if (pos + nv > a.max_vec) nv = (pos >= a.max_vec) ? 0 : (a.max_vec - pos);
+      for (uint32_t v = 0; v < nv; v++) cand[pos + v] = start + v;
+      offset += total;
+    }
+    if (threadIdx.x == 0) a.n_vec[qi] = offset < a.max_vec ? offset : a.max_vec;
+  }
+}
+
+// ============================================================================
+// CTA-wide ascending sort of n2 (power of two, 32 <= n2 <= 1024*E) (val, pay) pairs
+// held in shared memory.  Thread t owns elements t*E .. t*E+E-1 in registers;
+// compare-exchange distance j < E runs in registers, E <= j < 32E on shuffles,
+// j >= 32E through shared memory.  Any correct sort would do here (see the header
+// comment); the bitonic schedule is used because it needs no data-dependent control.
+// All threads of the CTA must call (block barriers inside).
+// ============================================================================
+template <int E>
+__device__ __forceinline__ void cta_sort_pairs(float* sv, uint32_t* sp, uint32_t n2) {
+  const uint32_t t = threadIdx.x, lane = t & 31;
+  const bool active = t * E < n2;
+  float v[E];
+  uint32_t p[E];
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+      v[r] = sv[t * E + r];
+      p[r] = sp[t * E + r];
+    }
+  }
+  for (uint32_t k = 2; k <= n2; k <<= 1) {
+    uint32_t j = k >> 1;
+    // ---- distances that cross warps: through shared memory
+    if (j >= 32u * E) {
+      if (active) {
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+          sv[t * E + r] = v[r];
+          sp[t * E + r] = p[r];
+        }
+      }
+      __syncthreads();
+      for (; j >= 32u * E; j >>= 1) {
+        for (uint32_t e = t; e < (n2 >> 1); e += blockDim.x) {
+          const uint32_t i = 2 * e - (e & (j - 1)), b = i + j;
+          const float va = sv[i], vb = sv[b];
+          const bool sw = ((i & k) == 0) ? (va > vb) : (va < vb);
+          if (sw) {
+            sv[i] = vb;
+            sv[b] = va;
+            const uint32_t pa = sp[i];
+            sp[i] = sp[b];
+            sp[b] = pa;
+          }
+        }
+        __syncthreads();
+      }
+      if (active) {
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+          v[r] = sv[t * E + r];
+          p[r] = sp[t * E + r];
+        }
+      }
+    }
+    if (active) {
+      // ---- distances inside a warp: shuffles
+      for (; j >= (uint32_t)E; j >>= 1) {
+        const uint32_t lj = j / E;  // lane distance
+        const bool lower = (lane & lj) == 0;
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+          const uint32_t i = t * E + r;
+          const float ov = __shfl_xor_sync(0xffffffffu, v[r], lj);
+          const uint32_t op = __shfl_xor_sync(0xffffffffu, p[r], lj);
+          const float lo = lower ? v[r] : ov, hi = lower ? ov : v[r];
+          const bool sw = ((i & k) == 0) ? (lo > hi) : (lo < hi);
+          if (sw) {
+            v[r] = ov;
+            p[r] = op;
+          }
+        }
+      }
+      // ---- distances inside a thread: registers
+#pragma unroll
+      for (int jj = E >> 1; jj > 0; jj >>= 1) {
+        if ((uint32_t)jj <= j) {
+#pragma unroll
+          for (int r = 0; r < E; r++) {
+            if ((r & jj) == 0) {
+              const uint32_t i = t * E + r;
+              const bool sw = ((i & k) == 0) ? (v[r] > v[r + jj]) : (v[r] < v[r + jj]);
+              if (sw) {
+                const float tv = v[r];
+                v[r] = v[r + jj];
+                v[r + jj] = tv;
+                const uint32_t tp = p[r];
+                p[r] = p[r + jj];
+                p[r + jj] = tp;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+      sv[t * E + r] = v[r];
+      sp[t * E + r] = p[r];
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void cta_sort_dispatch(float* sv, uint32_t* sp, uint32_t n2) {
+  if (n2 <= 1024)
+    cta_sort_pairs<1>(sv, sp, n2);
+  else if (n2 <= 2048)
+    cta_sort_pairs<2>(sv, sp, n2);
+  else
+    cta_sort_pairs<4>(sv, sp, n2);
+}
+
+// Ranks the candidates of one query held in shared memory and writes the first k.
+//   s_val[a], s_id[a] for a < nv: ADC distance / vector id in candidate order
+//   s_pay: scratch [max_vec]; s_flag: one word.  blockDim.x == 1024.
+__device__ __forceinline__ void rank_and_emit(float* s_val, uint32_t* s_pay, const uint32_t* s_id,
+                                              uint32_t* s_flag, uint32_t nv, uint32_t max_vec,
+                                              uint32_t k, float* out_dist, uint32_t* out_idx,
+                                              unsigned long long* exact_counter) {
+  const uint32_t t = threadIdx.x;
+  uint32_t n2 = pow2ceil(nv < 32 ? 32 : nv);
+  if (n2 > max_vec) n2 = max_vec;  // max_vec < 32: tiny widths
+  if (t == 0) *s_flag = 0;
+  __syncthreads();
+  // payload = candidate position; pads (+inf) behind the real candidates
+  bool bad = false;
+  for (uint32_t e = t; e < n2; e += blockDim.x) {
+    if (e < nv) {
+      s_pay[e] = e;
+      bad |= !(s_val[e] < kPadDist);  // >= 1e7, inf or NaN: pad order matters -> exact path
+    } else {
+      s_val[e] = __int_as_float(0x7f800000);
+      s_pay[e] = 0xFFFFFFFFu;
+    }
+  }
+  if (bad) atomicOr(s_flag, 1u);
+  __syncthreads();
+  if (n2 >= 32) cta_sort_dispatch(s_val, s_pay, n2);
+  // ties between copies of the same vector are harmless (the same bin can be listed more
+  // than once: the uint32 Horner hash keeps only idx_0 mod 4 of the first part); ties
+  // between different ids expose the network's order -> exact path
+  for (uint32_t e = t + 1; e < nv; e += blockDim.x)
+    if (s_val[e] == s_val[e - 1] && s_id[s_pay[e]] != s_id[s_pay[e - 1]]) atomicOr(s_flag, 1u);
+  __syncthreads();
+  if (*s_flag || n2 < 32) {
+    if (t == 0 && exact_counter) atomicAdd(exact_counter, 1ull);
+    // ---- exact path: restore candidate order, pad to max_vec with 1e7, run the
+    // reference's network (:5331-5340)
+    float rv[4];
+    uint32_t rp[4];
+    int cnt = 0;
+    for (uint32_t e = t; e < n2; e += blockDim.x, cnt++) {
+      rv[cnt] = s_val[e];
+      rp[cnt] = s_pay[e];
+    }
+    __syncthreads();
+    for (int c = 0; c < cnt; c++)
+      if (rp[c] != 0xFFFFFFFFu) s_val[rp[c]] = rv[c];
+    __syncthreads();
+    for (uint32_t e = t; e < max_vec; e += blockDim.x) {
+      if (e >= nv) s_val[e] = kPadDist;
+      s_pay[e] = e < nv ? e : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    bitonic_smem(s_val, s_pay, max_vec, 1);
+    for (uint32_t e = t; e < k; e += blockDim.x) {
+      const uint32_t a = s_pay[e];
+      out_dist[e] = s_val[e];
+      out_idx[e] = (a == 0xFFFFFFFFu) ? kPadIdx : s_id[a];
+    }
+  } else {
+    for (uint32_t e = t; e < k; e += blockDim.x) {
+      if (e < nv) {
+        out_dist[e] = s_val[e];
+        out_idx[e] = s_id[s_pay[e]];
+      } else {
+        out_dist[e] = kPadDist;
+        out_idx[e] = kPadIdx;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ============================================================================
+// Fused Step E2: scan + rank + emit.  Same scan arithmetic and lane mapping as
+// adc_scan_kernel (see there); single-GPU only (all candidates are local).
+// ============================================================================
+struct RerankArgs {
+  ScanArgs s;
+  uint32_t k;
+  float* out_dist;    // [QN][k]
+  uint32_t* out_idx;  // [QN][k]
+  unsigned long long* exact_counter;  // queries ranked by the exact network (may be null)
+};
+
+template <int LP>
+__global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
+  const ScanArgs& a = g.s;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t lut_floats = a.c1 * 32;
+  const uint32_t cbd_floats = a.c1 * a.c1 * 32;
+  float* s_cbd = reinterpret_cast<float*>(smem_raw);
+  float* s_lut0 = s_cbd + cbd_floats;
+  float* s_lut1 = s_lut0 + lut_floats;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lut1 + lut_floats);  // 128-byte aligned
+  uint32_t* s_flag = reinterpret_cast<uint32_t*>(bars + 3);
+  float* s_val = reinterpret_cast<float*>(bars + 4);
+  uint32_t* s_pay = reinterpret_cast<uint32_t*>(s_val + a.max_vec);
+  uint32_t* s_id = s_pay + a.max_vec;
+
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const uint32_t lp = lane & (LP - 1);
+  const uint32_t grp_base = lane & ~(uint32_t)(LP - 1);
+  if (blockIdx.x >= a.QN) return;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t cbd_bytes = cbd_floats * 4;
+    mbar_expect_tx(&bars[2], cbd_bytes);
+    for (uint32_t off = 0; off < cbd_bytes; off += 32768) {
+      uint32_t n = cbd_bytes - off < 32768 ? cbd_bytes - off : 32768;
+      tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_cbd) + off,
+                   reinterpret_cast<const unsigned char*>(a.cbd_dup) + off, n, &bars[2]);
+    }
+    mbar_expect_tx(&bars[0], lut_floats * 4);
+    tma_bulk_g2s(s_lut0, a.lut_dup + (size_t)blockIdx.x * lut_floats, lut_floats * 4, &bars[0]);
+  }
+  mbar_wait(&bars[2], 0);
+
+  uint32_t buf = 0, phase0 = 0, phase1 = 0;
+  for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
+    const uint32_t qn = qi + gridDim.x;
+    if (threadIdx.x == 0 && qn < a.QN) {
+      uint64_t* nb = &bars[buf ^ 1];
+      mbar_expect_tx(nb, lut_floats * 4);
+      tma_bulk_g2s(buf ? s_lut0 : s_lut1, a.lut_dup + (size_t)qn * lut_floats, lut_floats * 4, nb);
+    }
+    const float* s_lut = buf ? s_lut1 : s_lut0;
+    mbar_wait(&bars[buf], buf ? phase1 : phase0);
+    if (buf)
+      phase1 ^= 1;
+    else
+      phase0 ^= 1;
+
+    const uint32_t nv = min(__ldg(a.n_vec + qi), a.max_vec);
+    const uint32_t* cand = a.cand_pos + (size_t)qi * a.max_vec;
+
+    // ---- scan: only chunks that hold real candidates
+    for (uint32_t base = warp * 32; base < nv; base += nwarps * 32) {
+      const uint32_t ca = base + lane;
+      const bool valid = ca < nv;
+      const uint32_t pos = valid ? __ldg(cand + ca) : 0u;
+      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+      const uint32_t myid = valid ? __ldg(a.ids + pos) : 0u;
+      uint32_t w[LP];
+#pragma unroll
+      for (int s = 0; s < LP; s++) {
+        const uint32_t src = grp_base + s;
+        const uint32_t cpos = __shfl_sync(0xffffffffu, pos, src);
+        w[s] = ((vmask >> src) & 1u) ? __ldg(a.codes + (size_t)cpos * LP + lp) : 0u;
+      }
+      float myval = 0.f;
+#pragma unroll
+      for (int s = 0; s < LP; s++) {
+        const uint32_t p1 = w[s] & 0xFFu;
+        const uint32_t p2 = (w[s] >> 8) & 0xFFu;
+        const float lam = lambda_of(w[s]);
+        const float a2 = s_lut[p1 * 32 + lane];
+        const float b2 = s_lut[p2 * 32 + lane];
+        const float c2 = s_cbd[(p2 * a.c1 + p1) * 32 + lane];
+        float d = tri_dist(a2, b2, c2, lam);
+#pragma unroll
+        for (int st = LP >> 1; st > 0; st >>= 1)
+          d = __fadd_rn(d, __shfl_xor_sync(0xffffffffu, d, st));
+        if (lp == (uint32_t)s) myval = d;
+      }
+      if (valid) {
+        s_val[ca] = myval;
+        s_id[ca] = myid;
+      }
+    }
+    __syncthreads();
+    rank_and_emit(s_val, s_pay, s_id, s_flag, nv, a.max_vec, g.k, g.out_dist + (size_t)qi * g.k,
+                  g.out_idx + (size_t)qi * g.k, g.exact_counter);
+    buf ^= 1;
+  }
+}
+
+// ranking only: candidates already assembled in global memory (multi-GPU path)
+struct Rank2Args {
+  const float* val;     // [QN][max_vec]
+  const uint32_t* idx;  // [QN][max_vec]
+  uint32_t QN, max_vec, k;
+  float* out_dist;
+  uint32_t* out_idx;
+  unsigned long long* exact_counter;
+};
+
+__global__ void __launch_bounds__(kScanThreads) rank2_kernel(Rank2Args a) {
+  extern __shared__ float smem_f[];
+  float* s_val = smem_f;
+  uint32_t* s_pay = reinterpret_cast<uint32_t*>(s_val + a.max_vec);
+  uint32_t* s_id = s_pay + a.max_vec;
+  uint32_t* s_flag = s_id + a.max_vec;
+  uint32_t* s_nv = s_flag + 1;
+  for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x == 0) *s_nv = 0;
+    __syncthreads();
+    // real candidates form a prefix: slots >= nVec hold (1e7, PAD)
+    uint32_t local = 0;
+    for (uint32_t e = threadIdx.x; e < a.max_vec; e += blockDim.x) {
+      const float v = a.val[(size_t)qi * a.max_vec + e];
+      const uint32_t id = a.idx[(size_t)qi * a.max_vec + e];
+      s_val[e] = v;
+      s_id[e] = id;
+      if (!(id == kPadIdx && v == kPadDist)) local = e + 1;
+    }
+    atomicMax(s_nv, local);
+    __syncthreads();
+    const uint32_t nv = *s_nv;
+    __syncthreads();
+    rank_and_emit(s_val, s_pay, s_id, s_flag, nv, a.max_vec, a.k, a.out_dist + (size_t)qi * a.k,
+                  a.out_idx + (size_t)qi * a.k, a.exact_counter);
+  }
+}
+
+}  // namespace pqtb

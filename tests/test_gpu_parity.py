@@ -79,6 +79,41 @@ def test_k_sweep(case_small, k):
     t.close()
 
 
+def test_tied_distances_follow_the_network_order():
+    """Duplicate DB vectors give bit-equal ADC distances; the result order of ties is then
+    whatever the reference's bitonic network produces (not a stable sort).  Exercises the
+    exact-network fallback of the ranking kernels."""
+    import conftest
+    c = conftest.make_case(N=6000, QN=48, hash_size=65537, seed=11)
+    # make every vector appear 4 times: rebuild the index over the duplicated set
+    X = np.concatenate([c["X"][:1500]] * 4)
+    rng = np.random.default_rng(3)
+    X = X[rng.permutation(X.shape[0])]
+    idx = po.build_index(c["prm"], c["cb1"], c["cb2"], X, k1_build=16)
+    c.update(X=X, **idx)
+    for k in (64, 1024, 4096):
+        d0, i0 = oracle_query(c, k)
+        ties = sum(int(np.sum(np.diff(d0[q][i0[q] != po.PAD_IDX]) == 0)) for q in range(48))
+        assert ties > 100  # the case really has ties
+        t = make_gpu_index(c)
+        i1, d1 = t.queryKNN(c["Q"], 48, k)
+        assert np.array_equal(d1, d0)
+        assert np.array_equal(i1, i0)
+        t.close()
+
+
+def test_distances_at_or_above_the_pad_value(case_small):
+    """Distances >= 1e7 sort behind / among the 1e7 padding in the reference's network."""
+    c = dict(case_small)
+    c["Q"] = (case_small["Q"] * 40.0).astype(np.float32)  # far away queries: huge distances
+    d0, i0 = oracle_query(c, 512)
+    assert (d0[i0 != po.PAD_IDX] >= 1e7).any()
+    t = make_gpu_index(c)
+    i1, d1 = t.queryKNN(c["Q"], c["Q"].shape[0], 512)
+    assert np.array_equal(d1, d0) and np.array_equal(i1, i0)
+    t.close()
+
+
 def test_truncation_budgets(case_small):
     _check_all_stages(case_small, 64, max_bins=8, max_vec_per_bin=3)
     _check_all_stages(case_small, 64, max_trials=1)
