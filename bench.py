@@ -28,7 +28,7 @@ import numpy as np  # noqa: E402
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=1000000, help="database vectors")
@@ -56,52 +56,53 @@ def workload_name(a):
 
 
 class ClockSampler:
-    """nvidia-smi clocks line of /opt/skills/guides/B200_PROFILING.md, sampled while timing."""
+    """SM clock + throttle reasons sampled DURING the timed region (NVML, every 5 ms; the
+    same fields as the nvidia-smi clocks line of /opt/skills/guides/B200_PROFILING.md)."""
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
-        self.proc = None
+        self.sm = []
+        self.reasons = set()
+        self.max_sm = None
+        self.stop_flag = threading.Event()
+        self.thr = None
+        self.err = None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {
+                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            }
+            while not self.stop_flag.is_set():
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nme in names.items():
+                    if r & bit:
+                        self.reasons.add(nme)
+                time.sleep(0.005)
+        except Exception as e:  # NVML missing: report it, never fake a number
+            self.err = repr(e)
 
     def start(self):
-        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
-            return
-        self.thr = threading.Thread(target=self._read, daemon=True)
+        self.thr = threading.Thread(target=self._run, daemon=True)
         self.thr.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 9:
-                for nme, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nme)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self.stop_flag.set()
+        if self.thr:
+            self.thr.join(timeout=2)
+        if self.err or not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["nvml unavailable: %s" % self.err],
+                    "samples": 0}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 def measured_peak_hbm():
@@ -215,6 +216,7 @@ def run_b200(a, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import pqt_b200
+    from pqt_b200 import sharding
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -256,8 +258,7 @@ def run_b200(a, rank, world, local_rank):
     def step_device():
         if sharded:
             t.queryScanShard(Qd, QN, k, val, idx)
-            dist.reduce_scatter_tensor(val_s, val, op=dist.ReduceOp.MIN)
-            dist.reduce_scatter_tensor(idx_s, idx, op=dist.ReduceOp.MAX)
+            sharding.exchange(val, idx, val_s, idx_s, rank, world)
             t.rankCandidates(val_s, idx_s, nq_out, mv, k, out_i, out_d)
         else:
             t.queryKNN(Qd[q_lo:q_hi], nq_out, k, out_i, out_d)
@@ -267,8 +268,7 @@ def run_b200(a, rank, world, local_rank):
         if sharded:
             Qdev = Qh.to(device, non_blocking=True)
             t.queryScanShard(Qdev, QN, k, val, idx)
-            dist.reduce_scatter_tensor(val_s, val, op=dist.ReduceOp.MIN)
-            dist.reduce_scatter_tensor(idx_s, idx, op=dist.ReduceOp.MAX)
+            sharding.exchange(val, idx, val_s, idx_s, rank, world)
             t.rankCandidates(val_s, idx_s, nq_out, mv, k, pin_i, pin_d)
         else:
             t.queryKNN(Qh[q_lo:q_hi], nq_out, k, pin_i, pin_d)
