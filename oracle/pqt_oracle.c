@@ -96,8 +96,19 @@ float pqto_project(float a2, float b2, float c2) {
   return n / c2;
 }
 
-/* pqt/triangle.cuh:102-110 (the volatile out-parameter keeps d2 uncontracted) */
+/* pqt/triangle.cuh:102-110 in the form the device code takes: nvcc emits mul, mul, sub
+ * for d2 (the volatile out-parameter blocks the front-end contraction) and ptxas then
+ * fuses the last two into FFMA d2 = fma(-c2, l*l, b2) (verified in the SASS for sm_100a
+ * and against the reference's lineClusterKernelFast on the GPU, tests/test_ref_gpu.py). */
 float pqto_project_d(float a2, float b2, float c2, float *d2) {
+  float lambda = pqto_project(a2, b2, c2);
+  volatile float l2 = lambda * lambda;
+  *d2 = fmaf(-c2, l2, b2);
+  return lambda;
+}
+
+/* same with every operation rounded separately (host compilation of triangle.cuh) */
+float pqto_project_d_host(float a2, float b2, float c2, float *d2) {
   float lambda = pqto_project(a2, b2, c2);
   volatile float l2 = lambda * lambda;
   volatile float t = c2 * l2;

@@ -59,7 +59,8 @@ float pqto_to_float(uint16_t s);               /* pqt/triangle.cuh:14-18        
 float pqto_dist(float a2, float b2, float c2, float lambda); /* :55-63, device (FMA-contracted) form */
 float pqto_dist_host(float a2, float b2, float c2, float lambda); /* :55-63, uncontracted host form  */
 float pqto_project(float a2, float b2, float c2);            /* :80-82            */
-float pqto_project_d(float a2, float b2, float c2, float *d2); /* :102-110       */
+float pqto_project_d(float a2, float b2, float c2, float *d2); /* :102-110, device (FFMA) form */
+float pqto_project_d_host(float a2, float b2, float c2, float *d2); /* :102-110, host form */
 
 /* ---- bitonicSort.cuh ---------------------------------------------------------- */
 /* ascending key/value bitonic network over n = power of two (bitonic3 / bitonicLarge,

@@ -58,8 +58,9 @@ def lib():
             getattr(L, n).argtypes = [C.c_float] * 4
         L.pqto_project.restype = C.c_float
         L.pqto_project.argtypes = [C.c_float] * 3
-        L.pqto_project_d.restype = C.c_float
-        L.pqto_project_d.argtypes = [C.c_float] * 3 + [C.POINTER(C.c_float)]
+        for n in ("pqto_project_d", "pqto_project_d_host"):
+            getattr(L, n).restype = C.c_float
+            getattr(L, n).argtypes = [C.c_float] * 3 + [C.POINTER(C.c_float)]
         L.pqto_seg_dist.restype = C.c_float
         L.pqto_seg_dist.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.pqto_dist_seq.restype = C.c_uint32

@@ -78,12 +78,13 @@ __device__ __forceinline__ float tri_dist(float a2, float b2, float c2, float l)
   return __fmaf_rn(u, l, t);
 }
 
-// pqt/triangle.cuh:102-110 project() with the d2 output (uncontracted, the
-// reference stores d2 through a volatile reference)
+// pqt/triangle.cuh:102-110 project() with the d2 output, in the form the reference's
+// device code takes: lambda = (-0.5 * ((a2 - b2) - c2)) / c2 (IEEE division) and
+// d2 = fma(-c2, lambda*lambda, b2) (ptxas fuses the trailing mul + sub into one FFMA)
 __device__ __forceinline__ float tri_project(float a2, float b2, float c2, float& d2) {
   float u = __fsub_rn(__fsub_rn(a2, b2), c2);
   float l = __fdiv_rn(__fmul_rn(-0.5f, u), c2);
-  d2 = __fsub_rn(b2, __fmul_rn(c2, __fmul_rn(l, l)));
+  d2 = __fmaf_rn(-c2, __fmul_rn(l, l), b2);
   return l;
 }
 

@@ -34,6 +34,8 @@ def test_run_cu_triangle_cases(a2, b2, c2, lam, d2):
     l = L.pqto_project_d(a2, b2, c2, C.byref(d))
     assert abs(l - lam) < 1e-5
     assert abs(d.value - d2) < 1e-5
+    dh = C.c_float()
+    assert L.pqto_project_d_host(a2, b2, c2, C.byref(dh)) == l and abs(dh.value - d2) < 1e-5
     # "d2 == dist(lambda)" identity of run.cu, for the device (FMA) and host forms
     assert abs(L.pqto_dist(a2, b2, c2, l) - d.value) < 1e-5
     assert abs(L.pqto_dist_host(a2, b2, c2, l) - d.value) < 1e-5
@@ -118,9 +120,13 @@ def test_triangle_bitwise_against_reference_header():
         assert L.pqto_dist_host(a2, b2, c2, lam) == ref.ref_dist(a2, b2, c2, lam)
         assert L.pqto_project(a2, b2, c2) == ref.ref_project(a2, b2, c2)
         d0, d1 = C.c_float(), C.c_float()
-        l0 = L.pqto_project_d(a2, b2, c2, C.byref(d0))
+        l0 = L.pqto_project_d_host(a2, b2, c2, C.byref(d0))
         l1 = ref.ref_project_d(a2, b2, c2, C.byref(d1))
         assert l0 == l1 and d0.value == d1.value
+        # device form: the final mul+sub is one FFMA there
+        d2 = C.c_float()
+        assert L.pqto_project_d(a2, b2, c2, C.byref(d2)) == l1
+        assert abs(d2.value - d1.value) <= 1e-6 * max(1.0, abs(float(b2)), abs(float(c2)) * l1 * l1)
         # the device form differs from the host form by FMA rounding only
         dev = L.pqto_dist(a2, b2, c2, lam)
         host = ref.ref_dist(a2, b2, c2, lam)
