@@ -19,25 +19,22 @@ REF_LIB = os.path.join(conftest.ROOT, "oracle", "_ref", "libpqt_ref_gpu.so")
 HASH = 400000000  # compiled into the reference (pqt/PerturbationProTree.hh:12)
 
 
-@pytest.fixture(scope="module")
-def ref_run(tmp_path_factory):
-    if not os.path.exists(REF_LIB):
-        pytest.skip("oracle/_ref/libpqt_ref_gpu.so was not built (no reference tree at build time)")
-    tmp = tmp_path_factory.mktemp("refgpu")
-    N, QN, dim, p, c1, c2, LP, k1, k = 20000, 48, 128, 4, 16, 8, 16, 8, 1024
-    mu = synth.centres(256, dim)
-    X = synth.db_vectors(0, N, dim, 256, mu=mu).astype(np.float32)
-    Q = synth.query_vectors(QN, N, dim, 256, mu=mu)[0].astype(np.float32)
+def _run_case(tmp, N, QN, seed):
+    dim, p, c1, c2, LP, k1, k = 128, 4, 16, 8, 16, 8, 1024
+    mu = synth.centres(256, dim, synth.DB_SEED + seed)
+    X = synth.db_vectors(0, N, dim, 256, synth.DB_SEED + seed, mu).astype(np.float32)
+    Q = synth.query_vectors(QN, N, dim, 256, synth.DB_SEED + seed, synth.QUERY_SEED + seed,
+                            mu)[0].astype(np.float32)
     cb1, cb2 = synth.train_tree(X[:5000], p, c1, c2, iters=6, seed=5)
-    ppqt = str(tmp / "ref_128_4_16_8.ppqt")
+    ppqt = str(tmp / ("ref%d_128_4_16_8.ppqt" % seed))
     formats.write_ppqt(ppqt, dim, p, cb1, cb2)
     prm = po.default_params(dim, p, c1, c2, LP, hash_size=HASH)
     index = po.build_index(prm, cb1, cb2, X, k1_build=16)
     nz = np.nonzero(index["counts"])[0].astype(np.uint32)
-    case = str(tmp / "case.npz")
+    case = str(tmp / ("case%d.npz" % seed))
     np.savez(case, X=X, Q=Q, dim=dim, p=p, c1=c1, c2=c2, LP=LP, k1=k1, k=k, hash_size=HASH,
              nz_bins=nz, nz_counts=index["counts"][nz], db_idx=index["db_idx"], lines=index["lines"])
-    out = str(tmp / "out.npz")
+    out = str(tmp / ("out%d.npz" % seed))
     runner = os.path.join(conftest.ROOT, "tests", "ref_gpu_runner.py")
     try:
         r = subprocess.run([sys.executable, runner, case, out, ppqt], capture_output=True,
@@ -53,6 +50,22 @@ def ref_run(tmp_path_factory):
                                index["lines"], Q, k, stages=True)
     return dict(prm=prm, index=index, stages=stages, full=full, oracle=(d0, i0, st0), X=X, Q=Q,
                 cb1=cb1, cb2=cb2, k=k)
+
+
+@pytest.fixture(scope="module")
+def ref_run(tmp_path_factory):
+    if not os.path.exists(REF_LIB):
+        pytest.skip("oracle/_ref/libpqt_ref_gpu.so was not built (no reference tree at build time)")
+    return _run_case(tmp_path_factory.mktemp("refgpu"), 20000, 48, 0)
+
+
+@pytest.fixture(scope="module")
+def ref_run_sparse(tmp_path_factory):
+    """few vectors -> short candidate lists: the regime in which the reference's
+    rerankKernelFast is free of its shared-memory race (see the end-to-end test)"""
+    if not os.path.exists(REF_LIB):
+        pytest.skip("oracle/_ref/libpqt_ref_gpu.so was not built (no reference tree at build time)")
+    return _run_case(tmp_path_factory.mktemp("refgpu_sparse"), 6000, 96, 9)
 
 
 def test_reference_kernels_steps_a_to_d(ref_run):
@@ -79,12 +92,48 @@ def test_reference_index_build(ref_run):
     assert np.array_equal(st["build_lines16"], index["lines"])          # lineDist encoder
 
 
+# rerankKernelFast (pqt/PerturbationProTree.cu:5189-5351) hands out candidates to groups of
+# LP lanes through shared memory without a barrier (laneA[], idx[]: "fetch next a", :5285-5326).
+# The first round (blockDim / LP = 64 candidates with the launch shape of rerankKBestVectors)
+# is written before any lane reads; from the second round on the other lanes of a group race
+# with the writer.  On B200 (independent thread scheduling) exactly the candidates beyond
+# the first 64 come out with run-to-run varying distances (observed; SURVEY.md section 5
+# predicts it).  So the reference's own output pins: the candidate ids of every query
+# (Step E1), and ids + distances + order wherever nVec <= 64.
+RACE_FREE = 64
+
+
+def _check_end_to_end(run):
+    if run["full"] is None:
+        pytest.xfail("the reference's queryKNN did not complete on this GPU")
+    full, (d0, i0, st0), k = run["full"], run["oracle"], run["k"]
+    nvec = st0["n_vec"]
+    exact = 0
+    for q in range(i0.shape[0]):
+        n = int(nvec[q])
+        # Step E1: same candidates (the reference leaves stale ids in padded slots)
+        assert sorted(full["idx"][q, :n]) == sorted(i0[q, :n])
+        assert np.all(full["dist"][q, n:] == np.float32(1e7)) and np.all(d0[q, n:] == np.float32(1e7))
+        ref_pairs = set(zip(full["dist"][q, :n].tolist(), full["idx"][q, :n].tolist()))
+        ora_pairs = set(zip(d0[q, :n].tolist(), i0[q, :n].tolist()))
+        if n <= RACE_FREE:
+            assert np.array_equal(full["dist"][q], d0[q])
+            assert np.array_equal(full["idx"][q, :n], i0[q, :n])
+            exact += 1
+        else:
+            # the race-free first round must still agree
+            assert len(ref_pairs & ora_pairs) >= min(len(ora_pairs), RACE_FREE) - (n - len(ora_pairs))
+    return exact
+
+
 def test_reference_query_knn_end_to_end(ref_run):
-    if ref_run["full"] is None:
-        pytest.xfail("the reference's rerankKernelFast did not complete on this GPU (its "
-                     "warp-synchronous shuffle loop is undefined under independent thread "
-                     "scheduling, SURVEY.md section 5)")
-    full, (d0, i0, st0), k = ref_run["full"], ref_run["oracle"], ref_run["k"]
-    real = i0 != po.PAD_IDX                       # padded ids are stale shared memory there
-    assert np.array_equal(full["dist"], d0)
-    assert np.array_equal(full["idx"][real], i0[real])
+    _check_end_to_end(ref_run)
+
+
+def test_reference_query_knn_end_to_end_race_free_regime(ref_run_sparse):
+    exact = _check_end_to_end(ref_run_sparse)
+    assert exact >= 20  # enough queries compared bit-for-bit against the reference's output
+
+
+def test_reference_kernels_steps_a_to_d_sparse(ref_run_sparse):
+    test_reference_kernels_steps_a_to_d(ref_run_sparse)
