@@ -68,6 +68,7 @@ struct pqt_index {
   // traversal order (prepareDistSequence), cached per (m, p)
   DevBuf d_distseq;
   DevBuf d_seqnib;  // same codes with the rank of part j in nibble j
+  DevBuf d_seqsorted;  // per 4096-batch, sorted by the ranks of all parts but the last (bins3)
   std::vector<uint32_t> h_distseq;
   uint32_t seq_m = 0, seq_p = 0;
 
@@ -177,6 +178,29 @@ int ensure_dist_seq(pqt_index* h, uint32_t max_cluster) {
     const uint32_t batch = kBins2Threads * kProbesPerThread;
     const uint32_t b = i / batch, u = i % batch;
     nib[b * batch + (u % kProbesPerThread) * kBins2Threads + u / kProbesPerThread] = v;
+  }
+  if (h->p <= 4) {
+    // bins3_kernel: inside each batch visit the probes sorted by (ranks of parts 0..p-2,
+    // rank of the last part); entry = (rank inside the batch << 16) | nibble code
+    std::vector<uint32_t> sorted(kNumDistSeq, 0u);
+    const uint32_t batch = kBins3Batch;
+    const uint32_t last_shift = 4 * (h->p - 1);
+    std::vector<std::pair<uint32_t, uint32_t>> key(batch);
+    for (uint32_t b = 0; b < kNumDistSeq / batch; b++) {
+      for (uint32_t u = 0; u < batch; u++) {
+        uint32_t code = h->h_distseq[b * batch + u], v = 0;
+        for (uint32_t j = 0; j < h->p; j++) v |= ((code / den[j]) % m) << (4 * j);
+        uint32_t prefix = v & ((1u << last_shift) - 1u), last = v >> last_shift;
+        key[u] = std::make_pair((prefix << 4) | last, (u << 16) | v);
+      }
+      std::sort(key.begin(), key.end());
+      // thread-major storage [r][thread]: lane-consecutive reads hit consecutive entries
+      for (uint32_t e = 0; e < batch; e++) sorted[b * batch + e] = key[e].second;
+    }
+    CU_TRY(h, h->d_seqsorted.ensure(kNumDistSeq * sizeof(uint32_t)));
+    CU_TRY(h, cudaMemcpyAsync(h->d_seqsorted.p, sorted.data(), kNumDistSeq * sizeof(uint32_t),
+                              cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
   }
   CU_TRY(h, h->d_seqnib.ensure(kNumDistSeq * sizeof(uint32_t)));
   CU_TRY(h, cudaMemcpyAsync(h->d_seqnib.p, nib.data(), kNumDistSeq * sizeof(uint32_t),
@@ -367,7 +391,37 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
   }
   if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[1], h->stream));
   // ---- Steps D+E1
-  {
+  if (h->p <= 4) {
+    Bins3Args a{};
+    a.idx16 = h->s_idx16.as<uint32_t>();
+    a.seq_sorted = h->d_seqsorted.as<uint32_t>();
+    a.dir.bitmap = h->d_bitmap.as<uint32_t>();
+    a.dir.rank_base = h->d_rank_base.as<uint32_t>();
+    a.dir.cprefix = h->d_cprefix.as<uint32_t>();
+    a.hash = make_magicmod(h->db_hash_size);
+    a.QN = QN; a.p = h->p; a.c1c2 = h->c1 * h->c2;
+    a.n_probes = P.max_trials * P.bin_threads;
+    a.max_bins = P.max_bins; a.max_vec_per_bin = P.max_vec_per_bin; a.max_vec = max_vec;
+    a.cand_pos = h->s_cand.as<uint32_t>();
+    a.n_vec = h->s_nvec.as<uint32_t>();
+    if (h->debug) {
+      a.dbg_bins = h->g_bins.as<uint32_t>();
+      a.dbg_nbins = h->g_nbins.as<uint32_t>();
+    }
+    size_t smem = (size_t)(P.max_bins + kBins3Batch + 2 * 256 + kBins3Batch / 32 + 32) * 4;
+    uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 6);
+    if (h->p <= 2) {
+      if (smem > 48 * 1024)
+        CU_TRY(h, cudaFuncSetAttribute(bins3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      bins3_kernel<1><<<grid, kBins2Threads, smem, h->stream>>>(a);
+    } else {
+      if (smem > 48 * 1024)
+        CU_TRY(h, cudaFuncSetAttribute(bins3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      bins3_kernel<2><<<grid, kBins2Threads, smem, h->stream>>>(a);
+    }
+    CU_TRY(h, cudaGetLastError());
+    h->stats.kernel_launches++;
+  } else {
     Bins2Args a{};
     a.idx16 = h->s_idx16.as<uint32_t>();
     a.seq_nib = h->d_seqnib.as<uint32_t>();
@@ -409,15 +463,17 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
     a.out_val = d_val;
     a.out_idx = d_idx;
     size_t smem = ((size_t)h->c1 * h->c1 * 32 + 2 * (size_t)h->c1 * 32) * 4 + 64;
-    const size_t smem_fused = smem + 3 * (size_t)max_vec * 4;
-    if (fused_out_dist && smem_fused <= 220 * 1024) {
+    // cbd + per group (2 LUT buffers + 3 candidate arrays) + barriers/flags
+    const size_t smem_fused = ((size_t)h->c1 * h->c1 * 32 + kRerankGroups * 2 * (size_t)h->c1 * 32 +
+                               0) * 4 + kRerankGroups * (((size_t)10 * max_vec + 15) & ~(size_t)15) + 128;
+    if (fused_out_dist && smem_fused <= 227 * 1024) {
       RerankArgs g{};
       g.s = a;
       g.k = k;
       g.out_dist = fused_out_dist;
       g.out_idx = fused_out_idx;
       g.exact_counter = h->d_exact.as<unsigned long long>();
-      uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms);
+      uint32_t grid = std::min<uint32_t>((QN + kRerankGroups - 1) / kRerankGroups, (uint32_t)h->num_sms);
 #define LAUNCH_RERANK(LPV)                                                                       \
   do {                                                                                           \
     CU_TRY(h, cudaFuncSetAttribute(rerank_kernel<LPV>,                                           \
@@ -478,11 +534,11 @@ int run_rank(pqt_index* h, const float* d_val, const uint32_t* d_idx, uint32_t Q
   a.val = d_val; a.idx = d_idx; a.QN = QN; a.max_vec = max_vec; a.k = k;
   a.out_dist = d_out_dist; a.out_idx = d_out_idx;
   a.exact_counter = h->d_exact.as<unsigned long long>();
-  size_t smem = (size_t)max_vec * 12 + 16;
+  size_t smem = (size_t)max_vec * 10 + 16;
   if (smem > 48 * 1024)
     CU_TRY(h, cudaFuncSetAttribute(rank2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 2);
-  rank2_kernel<<<grid, kScanThreads, smem, h->stream>>>(a);
+  uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 4);
+  rank2_kernel<<<grid, kRerankGroupThreads, smem, h->stream>>>(a);
   CU_TRY(h, cudaGetLastError());
   h->stats.kernel_launches++;
   return PQT_OK;
@@ -595,7 +651,7 @@ int pqt_destroy(pqt_index* h) {
   if (!h) return PQT_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  for (DevBuf* b : {&h->d_cb1, &h->d_cb2, &h->d_cb1T, &h->d_cb2T, &h->d_distseq, &h->d_seqnib, &h->d_bitmap, &h->d_rank_base, &h->d_cprefix,
+  for (DevBuf* b : {&h->d_cb1, &h->d_cb2, &h->d_cb1T, &h->d_cb2T, &h->d_distseq, &h->d_seqnib, &h->d_seqsorted, &h->d_bitmap, &h->d_rank_base, &h->d_cprefix,
                     &h->d_dbidx, &h->d_codes, &h->d_cbd, &h->d_cbd_dup, &h->s_q, &h->s_lut, &h->s_idx16,
                     &h->s_cand, &h->s_nvec, &h->s_val, &h->s_idx, &h->s_outd, &h->s_outi, &h->g_assign,
                     &h->g_lut, &h->g_aval, &h->g_aidx, &h->g_bins, &h->g_nbins, &h->g_sel, &h->d_exact})
@@ -952,7 +1008,8 @@ int pqt_query_knn(pqt_index* h, const float* Q, int q_on_device, uint32_t QN, ui
     d_out_dist = h->s_outd.as<float>();
     d_out_idx = h->s_outi.as<uint32_t>();
   }
-  const bool fused = ((size_t)h->c1 * h->c1 * 32 + 2 * (size_t)h->c1 * 32 + 3 * (size_t)max_vec) * 4 + 64 <= 220 * 1024;
+  const bool fused = ((size_t)h->c1 * h->c1 * 32 + kRerankGroups * 2 * (size_t)h->c1 * 32 +
+                      0) * 4 + kRerankGroups * (((size_t)10 * max_vec + 15) & ~(size_t)15) + 128 <= 227 * 1024;
   // Host outputs: queries go through in slabs so that the device->host copy of one slab
   // (on the copy stream) overlaps the kernels of the next.  Device outputs / debug
   // recording: one pass.

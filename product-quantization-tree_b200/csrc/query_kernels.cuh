@@ -30,15 +30,13 @@ __device__ __forceinline__ void bitonic_smem(float* val, uint32_t* idx, uint32_t
         uint32_t arr = e / half, t = e - arr * half;
         uint32_t i = 2 * t - (t & (j - 1));  // t = q*j + r -> i = q*2j + r, (i & j) == 0
         uint32_t a = arr * n + i, b = a + j;
-        float va = val[a], vb = val[b];
-        bool sw = ((i & k) == 0) ? (va > vb) : (va < vb);
-        if (sw) {
-          val[a] = vb;
-          val[b] = va;
-          uint32_t ia = idx[a];
-          idx[a] = idx[b];
-          idx[b] = ia;
-        }
+        const float va = val[a], vb = val[b];
+        const uint32_t ia = idx[a], ib = idx[b];
+        const bool sw = ((i & k) == 0) ? (va > vb) : (va < vb);
+        val[a] = sw ? vb : va;  // branch-free: divergent swaps cost more than the stores
+        val[b] = sw ? va : vb;
+        idx[a] = sw ? ib : ia;
+        idx[b] = sw ? ia : ib;
       }
       __syncthreads();
     }
@@ -615,15 +613,13 @@ __device__ __forceinline__ void bitonic_warp_smem(float* val, uint32_t* idx, uin
       for (uint32_t t = lane; t < half; t += 32) {
         uint32_t i = 2 * t - (t & (j - 1));
         uint32_t b = i + j;
-        float va = val[i], vb = val[b];
-        bool sw = ((i & k) == 0) ? (va > vb) : (va < vb);
-        if (sw) {
-          val[i] = vb;
-          val[b] = va;
-          uint32_t ia = idx[i];
-          idx[i] = idx[b];
-          idx[b] = ia;
-        }
+        const float va = val[i], vb = val[b];
+        const uint32_t ia = idx[i], ib = idx[b];
+        const bool sw = ((i & k) == 0) ? (va > vb) : (va < vb);
+        val[i] = sw ? vb : va;
+        val[b] = sw ? va : vb;
+        idx[i] = sw ? ib : ia;
+        idx[b] = sw ? ia : ib;
       }
       __syncwarp();
     }

@@ -180,181 +180,350 @@ __global__ void __launch_bounds__(kBins2Threads) bins2_kernel(Bins2Args a) {
 }
 
 // ============================================================================
-// CTA-wide ascending sort of n2 (power of two, 32 <= n2 <= 1024*E) (val, pay) pairs
-// held in shared memory.  Thread t owns elements t*E .. t*E+E-1 in registers;
-// compare-exchange distance j < E runs in registers, E <= j < 32E on shuffles,
-// j >= 32E through shared memory.  Any correct sort would do here (see the header
-// comment); the bitonic schedule is used because it needs no data-dependent control.
-// All threads of the CTA must call (block barriers inside).
+// Steps D + E1, v3 (p <= 4): same walk as bins2_kernel, but inside every batch of 4096
+// traversal codes the probes are visited in a STATIC order sorted by the ranks of all
+// parts but the last.  Probes that share those ranks differ only in the last Horner
+// digit (< c1*c2), so their bins fall into one 128-byte line of the bitmap when
+// c1*c2 <= 1024: neighbouring lanes then share L1 wavefronts instead of touching 32
+// different lines per load (bins2: 77-92 % of the L1 tag bandwidth).  Kept probes are
+// put back into traversal order through a per-batch bit array before the ordered
+// compaction, so the bin list is identical.
 // ============================================================================
-template <int E>
-__device__ __forceinline__ void cta_sort_pairs(float* sv, uint32_t* sp, uint32_t n2) {
-  const uint32_t t = threadIdx.x, lane = t & 31;
-  const bool active = t * E < n2;
-  float v[E];
-  uint32_t p[E];
-  if (active) {
-#pragma unroll
-    for (int r = 0; r < E; r++) {
-      v[r] = sv[t * E + r];
-      p[r] = sp[t * E + r];
+struct Bins3Args {
+  const uint32_t* idx16;       // [QN][p][16]
+  const uint32_t* seq_sorted;  // [16 batches][4096]: (rank inside the batch << 16) | nibble code
+  BinDir dir;
+  MagicMod hash;
+  uint32_t QN, p, c1c2;
+  uint32_t n_probes;
+  uint32_t max_bins, max_vec_per_bin, max_vec;
+  uint32_t* cand_pos;
+  uint32_t* n_vec;
+  uint32_t* dbg_bins;
+  uint32_t* dbg_nbins;
+};
+
+constexpr int kBins3Batch = kBins2Threads * kProbesPerThread;  // 4096
+
+// dynamic smem: list[max_bins] | binbuf[4096] | pairs[2][256] | bits[128] | warp_sums[32]
+template <int NPAIRS>
+__global__ void __launch_bounds__(kBins2Threads) bins3_kernel(Bins3Args a) {
+  extern __shared__ uint32_t smem_u[];
+  uint32_t* list = smem_u;
+  uint32_t* binbuf = list + a.max_bins;
+  uint32_t* pairs = binbuf + kBins3Batch;
+  uint32_t* bits = pairs + 2 * 256;
+  uint32_t* warp_sums = bits + kBins3Batch / 32;
+  const uint32_t K = a.c1c2;
+  const uint32_t p = a.p;
+  // multiplier that moves the first pair past the second pair (or single last part)
+  const uint32_t mul1 = (p == 4) ? K * K : K;
+  const uint32_t n_probes = a.n_probes, max_bins = a.max_bins;
+  const MagicMod hash = a.hash;
+  const uint32_t* __restrict__ bitmap = a.dir.bitmap;
+
+  for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
+    __syncthreads();
+    const uint32_t* gi = a.idx16 + (size_t)qi * p * 16;
+    for (uint32_t e = threadIdx.x; e < NPAIRS * 256; e += blockDim.x) {
+      uint32_t pr = e >> 8, r0 = e & 15, r1 = (e >> 4) & 15;
+      uint32_t j0 = 2 * pr, j1 = j0 + 1;
+      uint32_t v = __ldg(gi + j0 * 16 + r0);
+      if (j1 < p) v = v * K + __ldg(gi + j1 * 16 + r1);
+      pairs[e] = v;
     }
-  }
-  for (uint32_t k = 2; k <= n2; k <<= 1) {
-    uint32_t j = k >> 1;
-    // ---- distances that cross warps: through shared memory
-    if (j >= 32u * E) {
-      if (active) {
+    if (threadIdx.x == 0) list[0] = 0;  // slot 0 keeps the memset value (:3561)
+    __syncthreads();
+
+    uint32_t n_out = 0;
+    for (uint32_t b0 = 0; b0 < n_probes && n_out < max_bins; b0 += kBins3Batch) {
+      if (threadIdx.x < kBins3Batch / 32) bits[threadIdx.x] = 0;
+      __syncthreads();
+      uint32_t bins[kProbesPerThread], words[kProbesPerThread], us[kProbesPerThread];
 #pragma unroll
-        for (int r = 0; r < E; r++) {
-          sv[t * E + r] = v[r];
-          sp[t * E + r] = p[r];
+      for (int r = 0; r < kProbesPerThread; r++) {
+        const uint32_t ent = __ldg(a.seq_sorted + b0 + r * kBins2Threads + threadIdx.x);
+        const uint32_t u = ent >> 16;
+        uint32_t o = pairs[ent & 0xFF];
+        if (NPAIRS == 2) o = o * mul1 + pairs[256 + ((ent >> 8) & 0xFF)];
+        const uint32_t bin = magicmod(o, hash);
+        us[r] = u;
+        bins[r] = bin;
+        words[r] = (b0 + u < n_probes) ? __ldg(bitmap + (bin >> 5)) : 0u;
+      }
+#pragma unroll
+      for (int r = 0; r < kProbesPerThread; r++) {
+        if ((words[r] >> (bins[r] & 31)) & 1u) {
+          atomicOr(&bits[us[r] >> 5], 1u << (us[r] & 31));
+          binbuf[us[r]] = bins[r];
         }
       }
       __syncthreads();
-      for (; j >= 32u * E; j >>= 1) {
-        for (uint32_t e = t; e < (n2 >> 1); e += blockDim.x) {
-          const uint32_t i = 2 * e - (e & (j - 1)), b = i + j;
-          const float va = sv[i], vb = sv[b];
-          const bool sw = ((i & k) == 0) ? (va > vb) : (va < vb);
-          if (sw) {
-            sv[i] = vb;
-            sv[b] = va;
-            const uint32_t pa = sp[i];
-            sp[i] = sp[b];
-            sp[b] = pa;
-          }
-        }
-        __syncthreads();
+      // ordered compaction in traversal order: thread i owns 32 consecutive probes
+      uint32_t w = (threadIdx.x < kBins3Batch / 32) ? bits[threadIdx.x] : 0u;
+      uint32_t total;
+      uint32_t pos = n_out + block_exscan(__popc(w), warp_sums, total);
+      while (w) {
+        const uint32_t bit = __ffs(w) - 1;
+        w &= w - 1;
+        pos++;  // inclusive-scan position: 1-based (:3504-3510)
+        if (pos < max_bins) list[pos] = binbuf[threadIdx.x * 32 + bit];
       }
-      if (active) {
-#pragma unroll
-        for (int r = 0; r < E; r++) {
-          v[r] = sv[t * E + r];
-          p[r] = sp[t * E + r];
-        }
-      }
+      n_out += total;
     }
-    if (active) {
-      // ---- distances inside a warp: shuffles
-      for (; j >= (uint32_t)E; j >>= 1) {
-        const uint32_t lj = j / E;  // lane distance
-        const bool lower = (lane & lj) == 0;
-#pragma unroll
-        for (int r = 0; r < E; r++) {
-          const uint32_t i = t * E + r;
-          const float ov = __shfl_xor_sync(0xffffffffu, v[r], lj);
-          const uint32_t op = __shfl_xor_sync(0xffffffffu, p[r], lj);
-          const float lo = lower ? v[r] : ov, hi = lower ? ov : v[r];
-          const bool sw = ((i & k) == 0) ? (lo > hi) : (lo < hi);
-          if (sw) {
-            v[r] = ov;
-            p[r] = op;
-          }
-        }
-      }
-      // ---- distances inside a thread: registers
-#pragma unroll
-      for (int jj = E >> 1; jj > 0; jj >>= 1) {
-        if ((uint32_t)jj <= j) {
-#pragma unroll
-          for (int r = 0; r < E; r++) {
-            if ((r & jj) == 0) {
-              const uint32_t i = t * E + r;
-              const bool sw = ((i & k) == 0) ? (v[r] > v[r + jj]) : (v[r] < v[r + jj]);
-              if (sw) {
-                const float tv = v[r];
-                v[r] = v[r + jj];
-                v[r + jj] = tv;
-                const uint32_t tp = p[r];
-                p[r] = p[r + jj];
-                p[r + jj] = tp;
-              }
-            }
-          }
-        }
-      }
+    __syncthreads();
+    const uint32_t nb = n_out < max_bins ? n_out : max_bins;
+    if (a.dbg_bins) {
+      for (uint32_t e = threadIdx.x; e < max_bins; e += blockDim.x)
+        a.dbg_bins[(size_t)qi * max_bins + e] =
+            (e == 0) ? 0u : ((e <= n_out && e < max_bins) ? list[e] : 0u);
+      if (threadIdx.x == 0) a.dbg_nbins[qi] = nb;
     }
+
+    // ---- Step E1 (:4339-4417)
+    uint32_t offset = 0;
+    uint32_t* cand = a.cand_pos + (size_t)qi * a.max_vec;
+    for (uint32_t c0 = 0; c0 < nb && offset < a.max_vec; c0 += blockDim.x) {
+      uint32_t b = c0 + threadIdx.x;
+      uint32_t start = 0, nv = 0;
+      if (b < nb) {
+        uint32_t cnt;
+        dir_lookup(a.dir, list[b], start, cnt);
+        nv = cnt < a.max_vec_per_bin ? cnt : a.max_vec_per_bin;
+      }
+      uint32_t total;
+      uint32_t pos = offset + block_exscan(nv, warp_sums, total);
+      if (pos + nv > a.max_vec) nv = (pos >= a.max_vec) ? 0 : (a.max_vec - pos);
+      for (uint32_t v = 0; v < nv; v++) cand[pos + v] = start + v;
+      offset += total;
+    }
+    if (threadIdx.x == 0) a.n_vec[qi] = offset < a.max_vec ? offset : a.max_vec;
   }
-  if (active) {
-#pragma unroll
-    for (int r = 0; r < E; r++) {
-      sv[t * E + r] = v[r];
-      sp[t * E + r] = p[r];
-    }
-  }
-  __syncthreads();
 }
 
-__device__ __forceinline__ void cta_sort_dispatch(float* sv, uint32_t* sp, uint32_t n2) {
-  if (n2 <= 1024)
-    cta_sort_pairs<1>(sv, sp, n2);
-  else if (n2 <= 2048)
-    cta_sort_pairs<2>(sv, sp, n2);
+// ============================================================================
+// Thread group = a contiguous set of warps of a CTA that works on one query and
+// synchronises on its own named barrier (bar.sync id, n).  rerank_kernel runs two
+// groups of 512 threads per CTA on different queries so that the scan phase of one
+// overlaps the ranking phase of the other; rank2_kernel uses one group = the CTA.
+// ============================================================================
+constexpr uint32_t kPayPad = 0xFFFFu;  // payload of a padded sort slot (candidate positions < 4096)
+
+struct Grp {
+  uint32_t t;    // thread index inside the group
+  uint32_t n;    // threads in the group (multiple of 32)
+  uint32_t bar;  // hardware barrier id (0 = the CTA-wide barrier of __syncthreads)
+  __device__ __forceinline__ void sync() const {
+    asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(n) : "memory");
+  }
+};
+
+// the reference's network (pqt/bitonicSort.cuh:16-78) over n elements, run by a group
+__device__ __forceinline__ void bitonic_smem_grp(const Grp& g, float* val, uint16_t* idx, uint32_t n) {
+  const uint32_t half = n >> 1;
+  for (uint32_t k = 2; k <= n; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = g.t; t < half; t += g.n) {
+        const uint32_t i = 2 * t - (t & (j - 1)), b = i + j;
+        const float va = val[i], vb = val[b];
+        const uint32_t ia = idx[i], ib = idx[b];
+        const bool sw = ((i & k) == 0) ? (va > vb) : (va < vb);
+        val[i] = sw ? vb : va;
+        val[b] = sw ? va : vb;
+        idx[i] = (uint16_t)(sw ? ib : ia);
+        idx[b] = (uint16_t)(sw ? ia : ib);
+      }
+      g.sync();
+    }
+  }
+}
+
+// ============================================================================
+// Group-wide ascending sort of n2 (power of two, >= 32) (val, pay) pairs held in shared
+// memory.  A thread works on blocks of E consecutive elements in registers:
+// compare-exchange distance j < E runs in registers, E <= j < 32E on shuffles, j >= 32E
+// through shared memory by the whole group.  When n2 > E * group size the group makes
+// several passes (the register stages of different blocks are independent), which keeps
+// the register footprint at E elements.  Any correct sort would do here (see the header
+// comment); the bitonic schedule is used because it needs no data-dependent control.
+// Every thread of the group must call.
+// ============================================================================
+template <int E>
+__device__ __forceinline__ void sort_reg_stages(float (&v)[E], uint32_t (&p)[E], uint32_t base,
+                                                uint32_t lane, uint32_t k, uint32_t jstart) {
+  uint32_t j = jstart;
+  // ascending block for all elements of this thread once k >= E (base & k ignores r)
+  const bool desc_t = (base & k) != 0;
+  // distances inside a warp: shuffles.  The lane holding the lower index of a pair keeps
+  // the minimum when ascending; `nv != v` is exactly "the pair swaps" (ties keep their
+  // own bits and payload, like the network's strict compare).
+  for (; j >= (uint32_t)E; j >>= 1) {
+    const uint32_t lj = j / E;  // lane distance
+    const bool want_min = ((lane & lj) == 0) != desc_t;
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v[r], lj);
+      const uint32_t op = __shfl_xor_sync(0xffffffffu, p[r], lj);
+      const float nv = want_min ? fminf(v[r], ov) : fmaxf(v[r], ov);
+      const bool sw = nv != v[r];
+      v[r] = sw ? ov : v[r];
+      p[r] = sw ? op : p[r];
+    }
+  }
+  // distances inside a thread: registers
+#pragma unroll
+  for (int jj = E >> 1; jj > 0; jj >>= 1) {
+    if ((uint32_t)jj <= j) {
+#pragma unroll
+      for (int r = 0; r < E; r++) {
+        if ((r & jj) == 0) {
+          const bool desc = ((base + r) & k) != 0;
+          const float lo = v[r], hi = v[r + jj];
+          const uint32_t plo = p[r], phi = p[r + jj];
+          const bool sw = desc ? (lo < hi) : (lo > hi);
+          v[r] = sw ? hi : lo;
+          v[r + jj] = sw ? lo : hi;
+          p[r] = sw ? phi : plo;
+          p[r + jj] = sw ? plo : phi;
+        }
+      }
+    }
+  }
+}
+
+template <int E>
+__device__ __forceinline__ void grp_sort_pairs(const Grp& g, float* sv, uint16_t* sp, uint32_t n2) {
+  const uint32_t t = g.t, lane = t & 31;
+  const uint32_t per = E * g.n;  // elements one pass of the group covers
+  const uint32_t k1 = n2 < 32u * E ? n2 : 32u * E;
+  // ---- phase 1: every k whose largest distance stays inside a warp's 32E elements
+  for (uint32_t b0 = 0; b0 < n2; b0 += per) {
+    const uint32_t base = b0 + t * E;
+    if (base < n2) {
+      float v[E];
+      uint32_t p[E];
+#pragma unroll
+      for (int r = 0; r < E; r++) {
+        v[r] = sv[base + r];
+        p[r] = sp[base + r];
+      }
+      for (uint32_t k = 2; k <= k1; k <<= 1) sort_reg_stages<E>(v, p, base, lane, k, k >> 1);
+#pragma unroll
+      for (int r = 0; r < E; r++) {
+        sv[base + r] = v[r];
+        sp[base + r] = (uint16_t)p[r];
+      }
+    }
+  }
+  g.sync();
+  // ---- phase 2: larger k: cross-warp distances in shared memory, the rest in registers
+  for (uint32_t k = 64u * E; k <= n2; k <<= 1) {
+    for (uint32_t j = k >> 1; j >= 32u * E; j >>= 1) {
+      for (uint32_t e = t; e < (n2 >> 1); e += g.n) {
+        const uint32_t i = 2 * e - (e & (j - 1)), b = i + j;
+        const float va = sv[i], vb = sv[b];
+        const uint32_t pa = sp[i], pb = sp[b];
+        const bool sw = ((i & k) == 0) ? (va > vb) : (va < vb);
+        sv[i] = sw ? vb : va;
+        sv[b] = sw ? va : vb;
+        sp[i] = (uint16_t)(sw ? pb : pa);
+        sp[b] = (uint16_t)(sw ? pa : pb);
+      }
+      g.sync();
+    }
+    for (uint32_t b0 = 0; b0 < n2; b0 += per) {
+      const uint32_t base = b0 + t * E;
+      if (base < n2) {
+        float v[E];
+        uint32_t p[E];
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+          v[r] = sv[base + r];
+          p[r] = sp[base + r];
+        }
+        sort_reg_stages<E>(v, p, base, lane, k, 16u * E);
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+          sv[base + r] = v[r];
+          sp[base + r] = (uint16_t)p[r];
+        }
+      }
+    }
+    g.sync();
+  }
+}
+
+// E = 4 elements per thread once there is enough work for the group; wider inputs take
+// several passes instead of more registers
+__device__ __forceinline__ void grp_sort_dispatch(const Grp& g, float* sv, uint16_t* sp, uint32_t n2) {
+  if (n2 <= g.n)
+    grp_sort_pairs<1>(g, sv, sp, n2);
+  else if (n2 <= 2 * g.n)
+    grp_sort_pairs<2>(g, sv, sp, n2);
   else
-    cta_sort_pairs<4>(sv, sp, n2);
+    grp_sort_pairs<4>(g, sv, sp, n2);
 }
 
 // Ranks the candidates of one query held in shared memory and writes the first k.
 //   s_val[a], s_id[a] for a < nv: ADC distance / vector id in candidate order
-//   s_pay: scratch [max_vec]; s_flag: one word.  blockDim.x == 1024.
-__device__ __forceinline__ void rank_and_emit(float* s_val, uint32_t* s_pay, const uint32_t* s_id,
-                                              uint32_t* s_flag, uint32_t nv, uint32_t max_vec,
-                                              uint32_t k, float* out_dist, uint32_t* out_idx,
-                                              unsigned long long* exact_counter) {
-  const uint32_t t = threadIdx.x;
+//   s_pay: scratch [max_vec]; s_flag: one word.  g.n >= 256 (max_vec <= 4096).
+__device__ __forceinline__ void rank_and_emit(const Grp& g, float* s_val, uint16_t* s_pay,
+                                              const uint32_t* s_id, uint32_t* s_flag, uint32_t nv,
+                                              uint32_t max_vec, uint32_t k, float* out_dist,
+                                              uint32_t* out_idx, unsigned long long* exact_counter) {
+  const uint32_t t = g.t;
   uint32_t n2 = pow2ceil(nv < 32 ? 32 : nv);
   if (n2 > max_vec) n2 = max_vec;  // max_vec < 32: tiny widths
   if (t == 0) *s_flag = 0;
-  __syncthreads();
+  g.sync();
   // payload = candidate position; pads (+inf) behind the real candidates
   bool bad = false;
-  for (uint32_t e = t; e < n2; e += blockDim.x) {
+  for (uint32_t e = t; e < n2; e += g.n) {
     if (e < nv) {
-      s_pay[e] = e;
+      s_pay[e] = (uint16_t)e;
       bad |= !(s_val[e] < kPadDist);  // >= 1e7, inf or NaN: pad order matters -> exact path
     } else {
       s_val[e] = __int_as_float(0x7f800000);
-      s_pay[e] = 0xFFFFFFFFu;
+      s_pay[e] = kPayPad;
     }
   }
   if (bad) atomicOr(s_flag, 1u);
-  __syncthreads();
-  if (n2 >= 32) cta_sort_dispatch(s_val, s_pay, n2);
+  g.sync();
+  if (n2 >= 32) grp_sort_dispatch(g, s_val, s_pay, n2);
   // ties between copies of the same vector are harmless (the same bin can be listed more
   // than once: the uint32 Horner hash keeps only idx_0 mod 4 of the first part); ties
   // between different ids expose the network's order -> exact path
-  for (uint32_t e = t + 1; e < nv; e += blockDim.x)
+  for (uint32_t e = t + 1; e < nv; e += g.n)
     if (s_val[e] == s_val[e - 1] && s_id[s_pay[e]] != s_id[s_pay[e - 1]]) atomicOr(s_flag, 1u);
-  __syncthreads();
+  g.sync();
   if (*s_flag || n2 < 32) {
     if (t == 0 && exact_counter) atomicAdd(exact_counter, 1ull);
     // ---- exact path: restore candidate order, pad to max_vec with 1e7, run the
     // reference's network (:5331-5340)
-    float rv[4];
-    uint32_t rp[4];
+    float rv[16];
+    uint32_t rp[16];
     int cnt = 0;
-    for (uint32_t e = t; e < n2; e += blockDim.x, cnt++) {
+    for (uint32_t e = t; e < n2 && cnt < 16; e += g.n, cnt++) {
       rv[cnt] = s_val[e];
       rp[cnt] = s_pay[e];
     }
-    __syncthreads();
+    g.sync();
     for (int c = 0; c < cnt; c++)
-      if (rp[c] != 0xFFFFFFFFu) s_val[rp[c]] = rv[c];
-    __syncthreads();
-    for (uint32_t e = t; e < max_vec; e += blockDim.x) {
+      if (rp[c] != kPayPad) s_val[rp[c]] = rv[c];
+    g.sync();
+    for (uint32_t e = t; e < max_vec; e += g.n) {
       if (e >= nv) s_val[e] = kPadDist;
-      s_pay[e] = e < nv ? e : 0xFFFFFFFFu;
+      s_pay[e] = e < nv ? (uint16_t)e : kPayPad;
     }
-    __syncthreads();
-    bitonic_smem(s_val, s_pay, max_vec, 1);
-    for (uint32_t e = t; e < k; e += blockDim.x) {
+    g.sync();
+    bitonic_smem_grp(g, s_val, s_pay, max_vec);
+    for (uint32_t e = t; e < k; e += g.n) {
       const uint32_t a = s_pay[e];
       out_dist[e] = s_val[e];
-      out_idx[e] = (a == 0xFFFFFFFFu) ? kPadIdx : s_id[a];
+      out_idx[e] = (a == kPayPad) ? kPadIdx : s_id[a];
     }
   } else {
-    for (uint32_t e = t; e < k; e += blockDim.x) {
+    for (uint32_t e = t; e < k; e += g.n) {
       if (e < nv) {
         out_dist[e] = s_val[e];
         out_idx[e] = s_id[s_pay[e]];
@@ -364,12 +533,14 @@ __device__ __forceinline__ void rank_and_emit(float* s_val, uint32_t* s_pay, con
       }
     }
   }
-  __syncthreads();
+  g.sync();
 }
 
 // ============================================================================
 // Fused Step E2: scan + rank + emit.  Same scan arithmetic and lane mapping as
 // adc_scan_kernel (see there); single-GPU only (all candidates are local).
+// One persistent CTA per SM = two groups of 512 threads, each walking its own queries:
+// shared cbd table, per-group LUT double buffer (TMA bulk copies) and candidate arrays.
 // ============================================================================
 struct RerankArgs {
   ScanArgs s;
@@ -379,56 +550,69 @@ struct RerankArgs {
   unsigned long long* exact_counter;  // queries ranked by the exact network (may be null)
 };
 
+constexpr int kRerankGroups = 2;
+constexpr int kRerankGroupThreads = kScanThreads / kRerankGroups;  // 512
+
 template <int LP>
 __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
   const ScanArgs& a = g.s;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t lut_floats = a.c1 * 32;
   const uint32_t cbd_floats = a.c1 * a.c1 * 32;
-  float* s_cbd = reinterpret_cast<float*>(smem_raw);
-  float* s_lut0 = s_cbd + cbd_floats;
-  float* s_lut1 = s_lut0 + lut_floats;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lut1 + lut_floats);  // 128-byte aligned
-  uint32_t* s_flag = reinterpret_cast<uint32_t*>(bars + 3);
-  float* s_val = reinterpret_cast<float*>(bars + 4);
-  uint32_t* s_pay = reinterpret_cast<uint32_t*>(s_val + a.max_vec);
-  uint32_t* s_id = s_pay + a.max_vec;
+  const uint32_t grp = threadIdx.x / kRerankGroupThreads;
+  Grp G{threadIdx.x - grp * kRerankGroupThreads, (uint32_t)kRerankGroupThreads, 1 + grp};
 
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  float* s_cbd = reinterpret_cast<float*>(smem_raw);
+  float* s_luts = s_cbd + cbd_floats;                                  // [groups][2][lut_floats]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_luts + kRerankGroups * 2 * lut_floats);  // [groups][2] + cbd
+  uint32_t* s_flags = reinterpret_cast<uint32_t*>(bars + 2 * kRerankGroups + 2);
+  float* s_arr = reinterpret_cast<float*>(s_flags + 4);                // [groups][3][max_vec]
+  float* s_lut0 = s_luts + grp * 2 * lut_floats;
+  float* s_lut1 = s_lut0 + lut_floats;
+  uint64_t* gbar = bars + 2 * grp;
+  uint64_t* cbar = bars + 2 * kRerankGroups;
+  uint32_t* s_flag = s_flags + grp;
+  // per group: val f32[max_vec] | id u32[max_vec] | pay u16[max_vec]  (= 2.5 words/slot)
+  float* s_val = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_arr) + (size_t)grp * (((size_t)10 * a.max_vec + 15) & ~(size_t)15));
+  uint32_t* s_id = reinterpret_cast<uint32_t*>(s_val + a.max_vec);
+  uint16_t* s_pay = reinterpret_cast<uint16_t*>(s_id + a.max_vec);
+
+  const uint32_t lane = G.t & 31, warp = G.t >> 5, nwarps = G.n >> 5;
   const uint32_t lp = lane & (LP - 1);
   const uint32_t grp_base = lane & ~(uint32_t)(LP - 1);
-  if (blockIdx.x >= a.QN) return;
+  const uint32_t worker = blockIdx.x * kRerankGroups + grp;
+  const uint32_t nworkers = gridDim.x * kRerankGroups;
 
   if (threadIdx.x == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_init(&bars[2], 1);
+    for (int i = 0; i < 2 * kRerankGroups + 1; i++) mbar_init(&bars[i], 1);
     mbar_fence_init();
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     const uint32_t cbd_bytes = cbd_floats * 4;
-    mbar_expect_tx(&bars[2], cbd_bytes);
+    mbar_expect_tx(cbar, cbd_bytes);
     for (uint32_t off = 0; off < cbd_bytes; off += 32768) {
       uint32_t n = cbd_bytes - off < 32768 ? cbd_bytes - off : 32768;
       tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_cbd) + off,
-                   reinterpret_cast<const unsigned char*>(a.cbd_dup) + off, n, &bars[2]);
+                   reinterpret_cast<const unsigned char*>(a.cbd_dup) + off, n, cbar);
     }
-    mbar_expect_tx(&bars[0], lut_floats * 4);
-    tma_bulk_g2s(s_lut0, a.lut_dup + (size_t)blockIdx.x * lut_floats, lut_floats * 4, &bars[0]);
   }
-  mbar_wait(&bars[2], 0);
+  if (G.t == 0 && worker < a.QN) {
+    mbar_expect_tx(&gbar[0], lut_floats * 4);
+    tma_bulk_g2s(s_lut0, a.lut_dup + (size_t)worker * lut_floats, lut_floats * 4, &gbar[0]);
+  }
+  mbar_wait(cbar, 0);
 
   uint32_t buf = 0, phase0 = 0, phase1 = 0;
-  for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
-    const uint32_t qn = qi + gridDim.x;
-    if (threadIdx.x == 0 && qn < a.QN) {
-      uint64_t* nb = &bars[buf ^ 1];
+  for (uint32_t qi = worker; qi < a.QN; qi += nworkers) {
+    const uint32_t qn = qi + nworkers;
+    if (G.t == 0 && qn < a.QN) {
+      uint64_t* nb = &gbar[buf ^ 1];
       mbar_expect_tx(nb, lut_floats * 4);
       tma_bulk_g2s(buf ? s_lut0 : s_lut1, a.lut_dup + (size_t)qn * lut_floats, lut_floats * 4, nb);
     }
     const float* s_lut = buf ? s_lut1 : s_lut0;
-    mbar_wait(&bars[buf], buf ? phase1 : phase0);
+    mbar_wait(&gbar[buf], buf ? phase1 : phase0);
     if (buf)
       phase1 ^= 1;
     else
@@ -471,8 +655,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
         s_id[ca] = myid;
       }
     }
-    __syncthreads();
-    rank_and_emit(s_val, s_pay, s_id, s_flag, nv, a.max_vec, g.k, g.out_dist + (size_t)qi * g.k,
+    G.sync();
+    rank_and_emit(G, s_val, s_pay, s_id, s_flag, nv, a.max_vec, g.k, g.out_dist + (size_t)qi * g.k,
                   g.out_idx + (size_t)qi * g.k, g.exact_counter);
     buf ^= 1;
   }
@@ -488,13 +672,14 @@ struct Rank2Args {
   unsigned long long* exact_counter;
 };
 
-__global__ void __launch_bounds__(kScanThreads) rank2_kernel(Rank2Args a) {
+__global__ void __launch_bounds__(kRerankGroupThreads) rank2_kernel(Rank2Args a) {
   extern __shared__ float smem_f[];
   float* s_val = smem_f;
-  uint32_t* s_pay = reinterpret_cast<uint32_t*>(s_val + a.max_vec);
-  uint32_t* s_id = s_pay + a.max_vec;
+  uint32_t* s_id = reinterpret_cast<uint32_t*>(s_val + a.max_vec);
   uint32_t* s_flag = s_id + a.max_vec;
   uint32_t* s_nv = s_flag + 1;
+  uint16_t* s_pay = reinterpret_cast<uint16_t*>(s_nv + 1);
+  const Grp G{threadIdx.x, blockDim.x, 0};
   for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
     __syncthreads();
     if (threadIdx.x == 0) *s_nv = 0;
@@ -512,7 +697,7 @@ __global__ void __launch_bounds__(kScanThreads) rank2_kernel(Rank2Args a) {
     __syncthreads();
     const uint32_t nv = *s_nv;
     __syncthreads();
-    rank_and_emit(s_val, s_pay, s_id, s_flag, nv, a.max_vec, a.k, a.out_dist + (size_t)qi * a.k,
+    rank_and_emit(G, s_val, s_pay, s_id, s_flag, nv, a.max_vec, a.k, a.out_dist + (size_t)qi * a.k,
                   a.out_idx + (size_t)qi * a.k, a.exact_counter);
   }
 }
