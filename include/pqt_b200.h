@@ -62,7 +62,11 @@ typedef struct pqt_params {
                                pow2ceil(k) (:6159).  Non-zero (power of two >= k): fixed
                                candidate budget, results = first k of that ranking
                                (extension; lets k be small without shrinking the scan)  */
-  uint32_t reserved[8];
+  /* literals of the 1-B variant queryBIGKNNRerank2 / getBIGBins2D */
+  uint32_t big_k1;          /* 16 (:8604)                                                 */
+  uint32_t big_max_bins;    /* 64 * 8192 (:8639)                                          */
+  uint32_t big_max_trials;  /* 2560 rounds of 1024 merged bins (:3727)                    */
+  uint32_t reserved[5];
 } pqt_params;
 
 /* cumulative device-side timings of the query kernels (CUDA events on the
@@ -132,6 +136,16 @@ int pqt_set_lines(pqt_index *h, const uint32_t *lines, uint32_t N, uint32_t line
 int pqt_query_knn(pqt_index *h, const float *Q, int q_on_device, uint32_t QN, uint32_t k,
                   uint32_t *idx, float *dist, int out_on_device);
 
+/* queryBIGKNNRerank2(resIdx, resDist, Q, QN, k, hLines), :8596-8701 -- the 1-B variant:
+ * k1 = big_k1, bins from the 2-D anisotropic merge of parts (0,1) and (2,3) (getBIGBins2D
+ * :3702-3778, needs p == 4), at most two vectors counted per bin while collecting, every
+ * listed bin contributes up to pow2ceil(k) candidates (:6525), same ADC + ranking.  The
+ * reference fetches the line codes from pinned host memory (hLines); here they are the
+ * resident codes of pqt_set_lines / pqt_line_dist.  prepare2DDistSequence(512)
+ * (pqt/ProTree.cu:50-126, test/test1B.cpp:1215) is done on first use. */
+int pqt_query_big_knn_rerank2(pqt_index *h, const float *Q, int q_on_device, uint32_t QN,
+                              uint32_t k, uint32_t *idx, float *dist, int out_on_device);
+
 /* ---- build side (creates the query path's inputs) ----------------------------- */
 
 /* buildKBestDB(A, N), :1231-1315 -- bins every vector (k1_build L1 cells), builds
@@ -187,7 +201,10 @@ typedef enum pqt_stage {
   PQT_STAGE_SELECT_IDX = 6, /* uint32 [QN][max_vec]      Step E1 */
   PQT_STAGE_NVEC = 7,       /* uint32 [QN]               Step E1 */
   PQT_STAGE_CB_DIST = 8,    /* float  [c1][c1][LP]       computeCBL1L1Dist :1902-1917 */
-  PQT_STAGE_DIST_SEQ = 9    /* uint32 [65536]            prepareDistSequence pqt/ProTree.cu:128-207 */
+  PQT_STAGE_DIST_SEQ = 9,   /* uint32 [65536]            prepareDistSequence pqt/ProTree.cu:128-207 */
+  PQT_STAGE_DIST_SEQ_2D = 10, /* uint32 [10][65536]      prepare2DDistSequence pqt/ProTree.cu:50-126 */
+  PQT_STAGE_BIG_BINS = 11,  /* uint32 [QN][candidate width] bins listed by getBIGBins2D (last BIG query) */
+  PQT_STAGE_BIG_NBINS = 12  /* uint32 [QN] */
 } pqt_stage;
 int pqt_debug_enable(pqt_index *h, int on);
 int pqt_debug_stage(const pqt_index *h, int stage, void *host_out, size_t bytes);

@@ -514,6 +514,207 @@ int pqto_query_knn(const pqto_params *prm, const float *cb1, const float *cb2,
 }
 
 /* ------------------------------------------------------------------------- */
+/* a11: queryBIGKNNRerank2                                                   */
+/* ------------------------------------------------------------------------- */
+
+/* pqt/ProTree.cu:50-126.  Host arithmetic of the reference: s = (float)pow(0.9 * 1.2f,
+ * slope - 5) in double; dist = powf(x, 0.8f) + s * powf(y, 0.8f) in float; pairs sorted
+ * lexicographically; the first min(maxCluster^2, 65536) codes of every slope are kept. */
+void pqto_dist_seq_2d(uint32_t max_cluster, uint32_t *seq) {
+  uint32_t n_vec = max_cluster * max_cluster;
+  uint32_t copy = n_vec < PQTO_NUM_DISTSEQ ? n_vec : PQTO_NUM_DISTSEQ;
+  seq_pair *d = (seq_pair *)malloc(sizeof(seq_pair) * n_vec);
+  for (int slope = 0; slope < PQTO_NUM_ANISO_DIR; slope++) {
+    float s = (float)pow(0.9 * (double)PQTO_ANISO_BASE, (double)(slope - (PQTO_NUM_ANISO_DIR / 2)));
+    for (uint32_t i = 0; i < n_vec; i++) {
+      float x = (float)(i % max_cluster);
+      float y = (float)(i / max_cluster);
+      float n = 0.8f;
+      volatile float py = s * powf(y, n);
+      d[i].d = powf(x, n) + py;
+      d[i].code = i;
+    }
+    qsort(d, n_vec, sizeof(seq_pair), seq_pair_cmp);
+    for (uint32_t i = 0; i < PQTO_NUM_DISTSEQ; i++) seq[(size_t)slope * PQTO_NUM_DISTSEQ + i] = 0;
+    for (uint32_t i = 0; i < copy; i++) seq[(size_t)slope * PQTO_NUM_DISTSEQ + i] = d[i].code;
+  }
+  free(d);
+}
+
+/* :2839-2862 (device code: sqrtf, IEEE division, logf, roundf; float -> int conversion
+ * saturates and maps NaN to 0) */
+uint32_t pqto_slope_idx(const float *val0, const float *val1, uint32_t N, int *ambiguous) {
+  uint32_t sample = (uint32_t)sqrtf(2.f * (float)N);
+  float num = (val1[sample] + val1[sample - 1]) - 2.f * val1[0];
+  float den = (val0[sample] + val0[sample - 1]) - 2.f * val0[0];
+  float slope = num / den;
+  float r = logf(slope) / logf(PQTO_ANISO_BASE);
+  float f = roundf(r) + (float)(PQTO_NUM_ANISO_DIR / 2);
+  int si;
+  if (f != f)
+    si = 0;
+  else if (f >= 2147483648.f)
+    si = 2147483647;
+  else if (f <= -2147483648.f)
+    si = -2147483647 - 1;
+  else
+    si = (int)f;
+  if (si >= PQTO_NUM_ANISO_DIR) si = PQTO_NUM_ANISO_DIR - 1;
+  if (si < 0) si = 0;
+  if (ambiguous && r == r) {
+    float frac = fabsf(r - floorf(r) - 0.5f);
+    if (frac < 1e-3f && r > -6.f && r < 5.f) *ambiguous = 1;
+  }
+  return (uint32_t)si;
+}
+
+uint32_t pqto_step_d_big(const pqto_params *prm, uint32_t k1, const uint32_t *seq2d,
+                         const float *assign_val, const uint32_t *assign_idx,
+                         const uint32_t *bin_counts, uint32_t k2, uint32_t *bins, int *ambiguous) {
+  const uint32_t n = k1 * prm->c2, K = prm->c1 * prm->c2;
+  const uint32_t kMax = PQTO_BIG_KMAX, nI = PQTO_BIG_NINTER, dc = PQTO_BIG_DISTCLUSTER;
+  const uint32_t T = prm->bin_threads; /* 1024 */
+  const uint32_t max_out = prm->max_bins;
+  float *ival = (float *)malloc(sizeof(float) * 2 * nI);
+  uint32_t *iidx = (uint32_t *)malloc(sizeof(uint32_t) * 2 * nI);
+  float *dist = (float *)malloc(sizeof(float) * T);
+  uint32_t *oidx = (uint32_t *)malloc(sizeof(uint32_t) * T);
+  uint32_t *nel = (uint32_t *)malloc(sizeof(uint32_t) * T);
+  memset(bins, 0, sizeof(uint32_t) * (size_t)max_out);
+
+  /* ---- selectBinKernel2D2Parts: parts (0,1) -> list 0, parts (2,3) -> list 1 */
+  for (uint32_t pi = 0; pi < prm->p / 2; pi++) {
+    const float *v0 = assign_val + (size_t)(2 * pi) * n, *v1 = assign_val + (size_t)(2 * pi + 1) * n;
+    const uint32_t *i0 = assign_idx + (size_t)(2 * pi) * n, *i1 = assign_idx + (size_t)(2 * pi + 1) * n;
+    uint32_t si = pqto_slope_idx(v0, v1, nI, ambiguous);
+    const uint32_t *seq = seq2d + (size_t)si * PQTO_NUM_DISTSEQ;
+    float *dv = ival + pi * nI;
+    uint32_t *di = iidx + pi * nI;
+    for (uint32_t t = 0; t < nI; t++) {
+      uint32_t s = seq[t], x = s % dc, y = s / dc;
+      if (x < kMax && y < kMax) {
+        dv[t] = v0[x] + v1[y];
+        di[t] = i0[x] * K + i1[y];
+      } else {
+        dv[t] = 99999999999.f;
+        di[t] = 0;
+      }
+    }
+    if (pi < 2) pqto_bitonic(dv, di, nI);
+  }
+  /* ---- selectBinKernel2DFinal */
+  uint32_t si = pqto_slope_idx(ival, ival + nI, 1024, ambiguous);
+  const size_t seq_total = (size_t)PQTO_NUM_ANISO_DIR * PQTO_NUM_DISTSEQ;
+  uint32_t n_out = 0, n_elements = 0, n_iter = 0;
+  const uint32_t factor = K * K; /* uint32 wrap, :3101 */
+  while (n_elements < k2 && n_iter < prm->max_trials && n_out < max_out) {
+    size_t off = (size_t)si * PQTO_NUM_DISTSEQ + (size_t)n_iter * T;
+    if (off + T > seq_total) break; /* the reference reads past d_distSeq from here on */
+    for (uint32_t t = 0; t < T; t++) {
+      uint32_t s = seq2d[off + t], x = s % dc, y = s / dc;
+      if (x < nI && y < nI) {
+        dist[t] = ival[x] + ival[nI + y];
+        oidx[t] = iidx[x] * factor + iidx[nI + y];
+      } else {
+        dist[t] = 99999999999.f;
+        oidx[t] = 0;
+      }
+      oidx[t] = oidx[t] % prm->hash_size;
+    }
+    pqto_bitonic(dist, oidx, T);
+    uint32_t run = 0, total = 0;
+    for (uint32_t t = 0; t < T; t++) {
+      uint32_t c = bin_counts[oidx[t]];
+      total += c < 2 ? c : 2; /* maxVecPB = 2, :3114 */
+    }
+    uint32_t kept_before = 0, kept_excl_last = 0;
+    for (uint32_t t = 0; t < T; t++) {
+      uint32_t c = bin_counts[oidx[t]];
+      uint32_t e = c < 2 ? c : 2;
+      uint32_t reg = e;
+      /* inclusive scan of the previous thread + nElements >= k -> dropped (:3126-3129) */
+      if (t > 0 && (run + n_elements) >= k2) reg = 0;
+      run += e;
+      if (reg) {
+        uint32_t pos = kept_before + n_out; /* exclusive scan: 0-based (:3146-3151) */
+        if (pos < max_out) bins[pos] = oidx[t];
+        kept_before++;
+      }
+      if (t == T - 2) kept_excl_last = kept_before;
+    }
+    if (T == 1) kept_excl_last = 0;
+    n_elements += total;
+    /* nOutBins += nElem[blockDim.x - 1] of the EXCLUSIVE scan: the last thread's own flag is
+     * not counted (:3163) */
+    n_out += kept_excl_last;
+    n_iter++;
+  }
+  free(ival);
+  free(iidx);
+  free(dist);
+  free(oidx);
+  free(nel);
+  return n_out > max_out ? max_out : n_out;
+}
+
+int pqto_query_big_knn_rerank2(const pqto_params *prm, const float *cb1, const float *cb2,
+                               const uint32_t *bin_prefix, const uint32_t *bin_counts,
+                               const uint32_t *db_idx, const uint32_t *lines, const float *Q,
+                               uint32_t QN, uint32_t k, float *out_dist, uint32_t *out_idx,
+                               uint32_t *n_bins_out, uint32_t *n_vec_out, int *ambiguous,
+                               int nthreads) {
+  if (!shapes_ok(prm) || prm->k1 > prm->c1 || k == 0 || prm->p != 4) return -1;
+  if (prm->k1 * prm->c2 < PQTO_BIG_KMAX) return -1; /* reads 64 sorted entries per part */
+  uint32_t p = prm->p, c1 = prm->c1, c2 = prm->c2, LP = prm->line_parts, k1 = prm->k1;
+  uint32_t n = k1 * c2;
+  uint32_t max_vec = pqto_pow2ceil(k);
+  uint32_t *seq2d = (uint32_t *)malloc(sizeof(uint32_t) * PQTO_NUM_ANISO_DIR * PQTO_NUM_DISTSEQ);
+  pqto_dist_seq_2d(PQTO_BIG_DISTCLUSTER, seq2d);
+  float *cb_dist = (float *)malloc(sizeof(float) * (size_t)c1 * c1 * LP);
+  pqto_cb_dist(prm, cb1, cb_dist);
+  pqto_params e1 = *prm;
+  e1.max_vec_per_bin = max_vec; /* :6525: maxNVecPerBin = nnn */
+#ifdef _OPENMP
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+  nthreads = 1;
+#endif
+#pragma omp parallel num_threads(nthreads)
+  {
+    uint32_t *assign = (uint32_t *)malloc(sizeof(uint32_t) * k1 * p);
+    float *lut = (float *)malloc(sizeof(float) * LP * c1);
+    float *aval = (float *)malloc(sizeof(float) * p * n);
+    uint32_t *aidx = (uint32_t *)malloc(sizeof(uint32_t) * p * n);
+    uint32_t *bins = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)prm->max_bins);
+    uint32_t *sel = (uint32_t *)malloc(sizeof(uint32_t) * max_vec);
+#pragma omp for schedule(dynamic, 1)
+    for (int64_t qi = 0; qi < (int64_t)QN; qi++) {
+      const float *q = Q + (size_t)qi * prm->dim;
+      int amb = 0;
+      pqto_step_a(prm, cb1, q, k1, assign);
+      pqto_step_b(prm, cb1, q, lut);
+      pqto_step_c(prm, cb2, q, k1, assign, aval, aidx);
+      uint32_t nb = pqto_step_d_big(prm, k1, seq2d, aval, aidx, bin_counts, k, bins, &amb);
+      uint32_t nv = pqto_step_e1(&e1, bins, nb, bin_prefix, bin_counts, db_idx, max_vec, sel);
+      pqto_step_e2(prm, lut, cb_dist, lines, sel, nv, max_vec, k, out_dist + (size_t)qi * k,
+                   out_idx + (size_t)qi * k);
+      if (n_bins_out) n_bins_out[qi] = nb;
+      if (n_vec_out) n_vec_out[qi] = nv;
+      if (ambiguous) ambiguous[qi] = amb;
+    }
+    free(assign);
+    free(lut);
+    free(aval);
+    free(aidx);
+    free(bins);
+    free(sel);
+  }
+  free(cb_dist);
+  free(seq2d);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------- */
 /* build side                                                                */
 /* ------------------------------------------------------------------------- */
 

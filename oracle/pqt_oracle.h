@@ -124,6 +124,34 @@ int pqto_query_knn(const pqto_params *prm, const float *cb1, const float *cb2,
                    uint32_t k, float *out_dist, uint32_t *out_idx, pqto_stages *stages,
                    int nthreads);
 
+/* ---- a11: the 1-B variant queryBIGKNNRerank2 (:8596-8701) ------------------------------ */
+#define PQTO_NUM_ANISO_DIR 10   /* pqt/ProTree.hh:12 */
+#define PQTO_ANISO_BASE 1.2f    /* pqt/ProTree.hh:13 */
+#define PQTO_BIG_KMAX 64        /* getBIGBins2D :3729 kMax           */
+#define PQTO_BIG_NINTER 256     /* :3735 nIntermediateBin            */
+#define PQTO_BIG_DISTCLUSTER 512 /* prepare2DDistSequence(512), test/test1B.cpp:1215 */
+
+/* prepare2DDistSequence, pqt/ProTree.cu:50-126: seq[NUM_ANISO_DIR * NUM_DISTSEQ] */
+void pqto_dist_seq_2d(uint32_t max_cluster, uint32_t *seq);
+/* computeSlopeIdx :2839-2862.  *ambiguous is set when logf(slope)/logf(1.2) lies so close
+ * to a rounding boundary that the device's logf may round the other way */
+uint32_t pqto_slope_idx(const float *val0, const float *val1, uint32_t N, int *ambiguous);
+/* getBIGBins2D :3702-3778 = selectBinKernel2D2Parts :2914-3006 + selectBinKernel2DFinal
+ * :3012-3188.  assign_val/assign_idx [p][k1*c2] from Step C (k1 = 16).  bins[max_bins]
+ * (zeroed by the callee); returns nBins.  k2 = the kVec of the query. */
+uint32_t pqto_step_d_big(const pqto_params *prm, uint32_t k1, const uint32_t *seq2d,
+                         const float *assign_val, const uint32_t *assign_idx,
+                         const uint32_t *bin_counts, uint32_t k2, uint32_t *bins, int *ambiguous);
+/* queryBIGKNNRerank2.  prm->k1 (16), prm->max_bins (524288), prm->max_trials (2560) are the
+ * literals of :8604-8639 / :3725-3727; candidates per bin are capped at pow2ceil(k) (:6525).
+ * ambiguous[QN] (may be NULL) flags queries whose slope index sits on a rounding boundary. */
+int pqto_query_big_knn_rerank2(const pqto_params *prm, const float *cb1, const float *cb2,
+                               const uint32_t *bin_prefix, const uint32_t *bin_counts,
+                               const uint32_t *db_idx, const uint32_t *lines, const float *Q,
+                               uint32_t QN, uint32_t k, float *out_dist, uint32_t *out_idx,
+                               uint32_t *n_bins_out, uint32_t *n_vec_out, int *ambiguous,
+                               int nthreads);
+
 /* ---- build side (creates the query path's inputs) ---------- */
 /* bin of each DB vector: buildKBestDB :1231-1315 + assignPerturbationBestBinKernel2 :830-942
  * (k1 = 16 there; passed explicitly) */

@@ -187,6 +187,49 @@ def query_knn(prm, cb1, cb2, prefix, counts, db_idx, lines, Q, k, stages=False, 
     return (out_d, out_i, bufs) if stages else (out_d, out_i)
 
 
+NUM_ANISO_DIR = 10
+
+
+def dist_seq_2d(max_cluster=512):
+    seq = np.zeros(NUM_ANISO_DIR * NUM_DISTSEQ, np.uint32)
+    lib().pqto_dist_seq_2d(C.c_uint32(max_cluster), _p(seq))
+    return seq.reshape(NUM_ANISO_DIR, NUM_DISTSEQ)
+
+
+def slope_idx(val0, val1, n):
+    val0, val1 = _f32(val0), _f32(val1)
+    amb = C.c_int(0)
+    lib().pqto_slope_idx.restype = C.c_uint32
+    si = lib().pqto_slope_idx(_p(val0), _p(val1), C.c_uint32(n), C.byref(amb))
+    return int(si), bool(amb.value)
+
+
+def big_params(dim, p, c1, c2, line_parts, **over):
+    """literals of queryBIGKNNRerank2 (:8604-8639) and getBIGBins2D (:3725-3727)"""
+    kw = dict(k1=16, max_bins=64 * 8192, max_trials=2560, bin_threads=1024)
+    kw.update(over)
+    return default_params(dim, p, c1, c2, line_parts, **kw)
+
+
+def query_big_knn_rerank2(prm, cb1, cb2, prefix, counts, db_idx, lines, Q, k, nthreads=0):
+    """Returns (dist, idx, info) with info = dict(n_bins, n_vec, ambiguous)."""
+    cb1, cb2, Q = _f32(cb1), _f32(cb2), _f32(Q)
+    prefix, counts, db_idx, lines = _u32(prefix), _u32(counts), _u32(db_idx), _u32(lines)
+    QN = Q.shape[0]
+    out_d = np.zeros((QN, k), np.float32)
+    out_i = np.zeros((QN, k), np.uint32)
+    nb = np.zeros(QN, np.uint32)
+    nv = np.zeros(QN, np.uint32)
+    amb = np.zeros(QN, np.int32)
+    rc = lib().pqto_query_big_knn_rerank2(
+        C.byref(prm), _p(cb1), _p(cb2), _p(prefix), _p(counts), _p(db_idx), _p(lines), _p(Q),
+        C.c_uint32(QN), C.c_uint32(k), _p(out_d), _p(out_i), _p(nb), _p(nv), _p(amb),
+        C.c_int(nthreads))
+    if rc != 0:
+        raise ValueError("pqto_query_big_knn_rerank2: unsupported shape (rc=%d)" % rc)
+    return out_d, out_i, dict(n_bins=nb, n_vec=nv, ambiguous=amb.astype(bool))
+
+
 def assign_bins(prm, cb1, cb2, X, k1=16, nthreads=0):
     cb1, cb2, X = _f32(cb1), _f32(cb2), _f32(X)
     out = np.zeros(X.shape[0], np.uint32)

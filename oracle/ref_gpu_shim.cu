@@ -15,6 +15,7 @@ class RefTree : public pqt::PerturbationProTree {
   RefTree(uint dim, uint p) : pqt::PerturbationProTree(dim, p, p) {}
   using pqt::PerturbationProTree::computeCBL1L1Dist;
   using pqt::PerturbationProTree::getBins;
+  using pqt::PerturbationProTree::getBIGBins2D;
   using pqt::PerturbationProTree::getKBestAssignment;
   using pqt::PerturbationProTree::getKBestAssignment2;
   using pqt::PerturbationProTree::getLineAssignment;
@@ -26,6 +27,7 @@ class RefTree : public pqt::PerturbationProTree {
   float* cb1() { return d_multiCodeBook; }
   float* cb2() { return d_multiCodeBook2; }
   float* cbDist() { return d_codeBookDistL1L2; }
+  uint* distSeq() { return d_distSeq; }
   void setLinesFromHost(const float* lines, uint N, uint LP) {
     prepareEmptyLambda(N, LP);  // sets d_lineParts, allocates d_lineLambda
     cudaMemcpy(getLine(), lines, (size_t)N * LP * sizeof(float), cudaMemcpyHostToDevice);
@@ -115,6 +117,43 @@ void refgpu_build(void* h, const float* X, unsigned N, unsigned hash_size, unsig
   cudaMemcpy(dbidx, t->getDBIdx(), (size_t)N * 4, cudaMemcpyDeviceToHost);
   cudaMemcpy(lines16, t->getLine(), (size_t)N * 16 * 4, cudaMemcpyDeviceToHost);
   cudaFree(dX);
+}
+
+// the 1-B variant: prepare2DDistSequence(512) + the steps of queryBIGKNNRerank2
+// (pqt/PerturbationProTree.cu:8596-8701) up to getBIGBins2D, bins copied out (first `cap`
+// slots per query), then the public queryBIGKNNRerank2 itself with the resident line codes
+void refgpu_big(void* h, const float* Q, unsigned QN, unsigned k, unsigned cap, unsigned* bins_out,
+                unsigned* nbins_out, unsigned* idx, float* dist, unsigned* seq2d_out) {
+  RefTree* t = static_cast<RefTree*>(h);
+  const unsigned p = t->P(), c1 = t->c1(), c2 = t->c2(), LP = t->lineParts(), dim = t->dim();
+  const unsigned k1 = 16, maxBins = 64 * 8192;
+  t->prepare2DDistSequence(512);
+  float *dQ, *dLut, *dAval;
+  unsigned *dAssign, *dAidx, *dBins, *dNbins;
+  cudaMalloc(&dQ, (size_t)QN * dim * 4);
+  cudaMemcpy(dQ, Q, (size_t)QN * dim * 4, cudaMemcpyHostToDevice);
+  cudaMalloc(&dAssign, (size_t)QN * k1 * p * 4);
+  cudaMalloc(&dLut, (size_t)QN * LP * c1 * 4);
+  cudaMalloc(&dAval, (size_t)QN * p * k1 * c2 * 4);
+  cudaMalloc(&dAidx, (size_t)QN * p * k1 * c2 * 4);
+  cudaMalloc(&dBins, (size_t)QN * maxBins * 4);
+  cudaMalloc(&dNbins, (size_t)QN * 4);
+  t->getKBestAssignment(dAssign, t->cb1(), dQ, c1, QN, k1);
+  t->getLineAssignment(dLut, dQ, QN);
+  t->getKBestAssignment2(dAval, dAidx, t->cb2(), dQ, c2, QN, dAssign, c1, k1);
+  t->getBIGBins2D(dBins, dNbins, dAval, dAidx, QN, k1, k, maxBins);
+  cudaDeviceSynchronize();
+  for (unsigned q = 0; q < QN; q++)
+    cudaMemcpy(bins_out + (size_t)q * cap, dBins + (size_t)q * maxBins, (size_t)cap * 4, cudaMemcpyDeviceToHost);
+  cudaMemcpy(nbins_out, dNbins, (size_t)QN * 4, cudaMemcpyDeviceToHost);
+  if (seq2d_out) cudaMemcpy(seq2d_out, t->distSeq(), (size_t)10 * 65536 * 4, cudaMemcpyDeviceToHost);
+  cudaFree(dAssign); cudaFree(dLut); cudaFree(dAval); cudaFree(dAidx); cudaFree(dBins); cudaFree(dNbins);
+  std::vector<unsigned> ri;
+  std::vector<float> rd;
+  t->queryBIGKNNRerank2(ri, rd, dQ, QN, k, t->getLine());
+  std::memcpy(idx, ri.data(), (size_t)QN * k * sizeof(unsigned));
+  std::memcpy(dist, rd.data(), (size_t)QN * k * sizeof(float));
+  cudaFree(dQ);
 }
 
 unsigned refgpu_hash_size(void) { return HASH_SIZE; }

@@ -19,6 +19,7 @@
 #include "index_kernels.cuh"
 #include "query_kernels.cuh"
 #include "rerank_kernels.cuh"
+#include "big_kernels.cuh"
 
 using namespace pqtb;
 
@@ -68,6 +69,11 @@ struct pqt_index {
   // traversal order (prepareDistSequence), cached per (m, p)
   DevBuf d_distseq;
   DevBuf d_seqnib;  // same codes with the rank of part j in nibble j
+  DevBuf d_seq2d;  // prepare2DDistSequence(512): [10][65536]
+  std::vector<uint32_t> h_seq2d;
+  DevBuf s_topv, s_topi;  // [QN][p][64] best Step-C entries (1-B variant)
+  DevBuf g_bigbins, g_bignbins;
+  uint32_t dbg_big_QN = 0, dbg_big_cap = 0;
   DevBuf d_seqsorted;  // per 4096-batch, sorted by the ranks of all parts but the last (bins3)
   std::vector<uint32_t> h_distseq;
   uint32_t seq_m = 0, seq_p = 0;
@@ -211,6 +217,32 @@ int ensure_dist_seq(pqt_index* h, uint32_t max_cluster) {
   return PQT_OK;
 }
 
+// ---- prepare2DDistSequence(512) (pqt/ProTree.cu:50-126) on the host, cached ----------
+int ensure_dist_seq_2d(pqt_index* h) {
+  if (h->d_seq2d.p) return PQT_OK;
+  const uint32_t mc = kBigDistCluster, nvec = mc * mc;
+  const uint32_t copy = std::min<uint32_t>(nvec, kNumDistSeq);
+  h->h_seq2d.assign((size_t)kNumAnisoDir * kNumDistSeq, 0u);
+  std::vector<std::pair<float, uint32_t>> d(nvec);
+  for (uint32_t slope = 0; slope < kNumAnisoDir; slope++) {
+    const float s = (float)std::pow(0.9 * (double)PQTB_ANISO_BASE, (double)((int)slope - (int)(kNumAnisoDir / 2)));
+    for (uint32_t i = 0; i < nvec; i++) {
+      const float x = (float)(i % mc), y = (float)(i / mc);
+      const float n = 0.8f;
+      const float px = std::pow(x, n);
+      volatile float py = s * std::pow(y, n);  // separate roundings, as compiled for the host
+      d[i] = std::make_pair(px + py, i);
+    }
+    std::sort(d.begin(), d.end());
+    for (uint32_t i = 0; i < copy; i++) h->h_seq2d[(size_t)slope * kNumDistSeq + i] = d[i].second;
+  }
+  CU_TRY(h, h->d_seq2d.ensure(h->h_seq2d.size() * sizeof(uint32_t)));
+  CU_TRY(h, cudaMemcpyAsync(h->d_seq2d.p, h->h_seq2d.data(), h->h_seq2d.size() * sizeof(uint32_t),
+                            cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return PQT_OK;
+}
+
 int upload_tree(pqt_index* h) {
   CU_TRY(h, h->d_cb1.ensure(h->h_cb1.size() * sizeof(float)));
   CU_TRY(h, h->d_cb2.ensure(h->h_cb2.size() * sizeof(float)));
@@ -319,9 +351,10 @@ struct QueryPlan {
 // kernel and d_val/d_idx are not touched.
 int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float* d_val,
                    uint32_t* d_idx, float* fused_out_dist = nullptr,
-                   uint32_t* fused_out_idx = nullptr) {
+                   uint32_t* fused_out_idx = nullptr, bool big = false) {
   const uint32_t max_vec = candidate_width(h, k);
-  const pqt_params& P = h->prm;
+  pqt_params P = h->prm;
+  if (big) P.k1 = P.big_k1;  // queryBIGKNNRerank2 :8604
   PQ_TRY(ensure_dist_seq(h, h->c2 * P.k1));  // :8191
   const uint32_t m = h->seq_m;
   const uint32_t n = P.k1 * h->c2;
@@ -358,6 +391,13 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
     a.m = m;
     a.lut_dup = h->s_lut.as<float>();
     a.idx16 = h->s_idx16.as<uint32_t>();
+    if (big) {
+      CU_TRY(h, h->s_topv.ensure((size_t)QN * h->p * kBigKMax * 4));
+      CU_TRY(h, h->s_topi.ensure((size_t)QN * h->p * kBigKMax * 4));
+      a.top_val = h->s_topv.as<float>();
+      a.top_idx = h->s_topi.as<uint32_t>();
+      a.top_n = kBigKMax;
+    }
     if (h->debug) {
       a.dbg_assign = h->g_assign.as<uint32_t>();
       a.dbg_lut = h->g_lut.as<float>();
@@ -391,7 +431,39 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
   }
   if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[1], h->stream));
   // ---- Steps D+E1
-  if (h->p <= 4) {
+  if (big) {
+    PQ_TRY(ensure_dist_seq_2d(h));
+    BinsBigArgs a{};
+    a.top_val = h->s_topv.as<float>();
+    a.top_idx = h->s_topi.as<uint32_t>();
+    a.seq2d = h->d_seq2d.as<uint32_t>();
+    a.dir.bitmap = h->d_bitmap.as<uint32_t>();
+    a.dir.rank_base = h->d_rank_base.as<uint32_t>();
+    a.dir.cprefix = h->d_cprefix.as<uint32_t>();
+    a.hash = make_magicmod(h->db_hash_size);
+    a.QN = QN; a.c1c2 = h->c1 * h->c2;
+    a.k2 = k;
+    a.max_trials = P.big_max_trials; a.max_bins = P.big_max_bins;
+    a.max_vec = max_vec; a.max_vec_per_bin = max_vec;  // maxNVecPerBin = pow2ceil(k) (:6525)
+    a.list_cap = std::max<uint32_t>(max_vec, 32);
+    a.cand_pos = h->s_cand.as<uint32_t>();
+    a.n_vec = h->s_nvec.as<uint32_t>();
+    if (h->debug) {
+      CU_TRY(h, h->g_bigbins.ensure((size_t)QN * a.list_cap * 4));
+      CU_TRY(h, h->g_bignbins.ensure((size_t)QN * 4));
+      a.dbg_bins = h->g_bigbins.as<uint32_t>();
+      a.dbg_nbins = h->g_bignbins.as<uint32_t>();
+      h->dbg_big_QN = QN;
+      h->dbg_big_cap = a.list_cap;
+    }
+    size_t smem = (size_t)(4 * kBigInter + 2 * kBigThreads + 4 * kBigKMax + a.list_cap + 32 + 4) * 4;
+    if (smem > 48 * 1024)
+      CU_TRY(h, cudaFuncSetAttribute(bins_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 2);
+    bins_big_kernel<<<grid, kBigThreads, smem, h->stream>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    h->stats.kernel_launches++;
+  } else if (h->p <= 4) {
     Bins3Args a{};
     a.idx16 = h->s_idx16.as<uint32_t>();
     a.seq_sorted = h->d_seqsorted.as<uint32_t>();
@@ -611,6 +683,9 @@ void pqt_default_params(pqt_params* prm) {
   prm->hash_size = 400000000u;
   prm->k1_build = 16;
   prm->max_vec = 0;
+  prm->big_k1 = 16;
+  prm->big_max_bins = 64 * 8192;
+  prm->big_max_trials = 2560;
 }
 
 int pqt_create(uint32_t dim, uint32_t p, uint32_t p2, int device, pqt_index** out) {
@@ -651,7 +726,7 @@ int pqt_destroy(pqt_index* h) {
   if (!h) return PQT_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  for (DevBuf* b : {&h->d_cb1, &h->d_cb2, &h->d_cb1T, &h->d_cb2T, &h->d_distseq, &h->d_seqnib, &h->d_seqsorted, &h->d_bitmap, &h->d_rank_base, &h->d_cprefix,
+  for (DevBuf* b : {&h->d_cb1, &h->d_cb2, &h->d_cb1T, &h->d_cb2T, &h->d_distseq, &h->d_seqnib, &h->d_seqsorted, &h->d_seq2d, &h->s_topv, &h->s_topi, &h->g_bigbins, &h->g_bignbins, &h->d_bitmap, &h->d_rank_base, &h->d_cprefix,
                     &h->d_dbidx, &h->d_codes, &h->d_cbd, &h->d_cbd_dup, &h->s_q, &h->s_lut, &h->s_idx16,
                     &h->s_cand, &h->s_nvec, &h->s_val, &h->s_idx, &h->s_outd, &h->s_outi, &h->g_assign,
                     &h->g_lut, &h->g_aval, &h->g_aidx, &h->g_bins, &h->g_nbins, &h->g_sel, &h->d_exact})
@@ -987,11 +1062,17 @@ int pqt_candidate_width(const pqt_index* h, uint32_t k, uint32_t* max_vec) {
   return PQT_OK;
 }
 
-int pqt_query_knn(pqt_index* h, const float* Q, int q_on_device, uint32_t QN, uint32_t k,
-                  uint32_t* idx, float* dist, int out_on_device) {
+static int query_common(pqt_index* h, const float* Q, int q_on_device, uint32_t QN, uint32_t k,
+                        uint32_t* idx, float* dist, int out_on_device, bool big) {
   if (!h || !Q || !idx || !dist) return PQT_ERR_INVALID;
   CU_TRY(h, cudaSetDevice(h->device));
   PQ_TRY(check_query_state(h, QN, k));
+  if (big) {
+    if (h->p != 4) return fail(h, PQT_ERR_INVALID, "queryBIGKNNRerank2 merges parts (0,1) and (2,3): p must be 4 (pqt/PerturbationProTree.cu:2952,3061-3070)");
+    if (h->prm.big_k1 > h->c1 || h->prm.big_k1 > 32) return fail(h, PQT_ERR_INVALID, "big_k1 %u > c1 %u", h->prm.big_k1, h->c1);
+    if (h->prm.big_k1 * h->c2 < kBigKMax) return fail(h, PQT_ERR_INVALID, "big_k1*c2 < 64: the 2-D merge reads 64 sorted entries per part (:3729)");
+    if (pow2ceil(h->prm.big_k1 * h->c2) > 1024) return fail(h, PQT_ERR_INVALID, "big_k1*c2 > 1024");
+  }
   if (h->world != 1) return fail(h, PQT_ERR_STATE, "sharded handle: use pqt_query_scan_shard + pqt_rank_candidates");
   const uint32_t max_vec = candidate_width(h, k);
   const float* dQ = Q;
@@ -1037,7 +1118,7 @@ int pqt_query_knn(pqt_index* h, const float* Q, int q_on_device, uint32_t QN, ui
     float* od = d_out_dist + (size_t)q0 * k;
     uint32_t* oi = d_out_idx + (size_t)q0 * k;
     if (fused) {
-      PQ_TRY(run_scan_chain(h, q, n, k, nullptr, nullptr, od, oi));
+      PQ_TRY(run_scan_chain(h, q, n, k, nullptr, nullptr, od, oi, big));
       if (h->profile) {
         CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
         CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
@@ -1045,7 +1126,7 @@ int pqt_query_knn(pqt_index* h, const float* Q, int q_on_device, uint32_t QN, ui
     } else {
       CU_TRY(h, h->s_val.ensure((size_t)n * max_vec * 4));
       CU_TRY(h, h->s_idx.ensure((size_t)n * max_vec * 4));
-      PQ_TRY(run_scan_chain(h, q, n, k, h->s_val.as<float>(), h->s_idx.as<uint32_t>()));
+      PQ_TRY(run_scan_chain(h, q, n, k, h->s_val.as<float>(), h->s_idx.as<uint32_t>(), nullptr, nullptr, big));
       if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
       PQ_TRY(run_rank(h, h->s_val.as<float>(), h->s_idx.as<uint32_t>(), n, max_vec, k, od, oi));
       if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
@@ -1064,6 +1145,16 @@ int pqt_query_knn(pqt_index* h, const float* Q, int q_on_device, uint32_t QN, ui
   }
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   return PQT_OK;
+}
+
+int pqt_query_knn(pqt_index* h, const float* Q, int q_on_device, uint32_t QN, uint32_t k,
+                  uint32_t* idx, float* dist, int out_on_device) {
+  return query_common(h, Q, q_on_device, QN, k, idx, dist, out_on_device, false);
+}
+
+int pqt_query_big_knn_rerank2(pqt_index* h, const float* Q, int q_on_device, uint32_t QN,
+                              uint32_t k, uint32_t* idx, float* dist, int out_on_device) {
+  return query_common(h, Q, q_on_device, QN, k, idx, dist, out_on_device, true);
 }
 
 int pqt_query_scan_shard(pqt_index* h, const float* Q, int q_on_device, uint32_t QN, uint32_t k,
@@ -1166,8 +1257,17 @@ int pqt_debug_stage(const pqt_index* hc, int stage, void* host_out, size_t bytes
       if (bytes != kNumDistSeq * 4) return fail(h, PQT_ERR_INVALID, "size mismatch");
       std::memcpy(host_out, h->h_distseq.data(), bytes);
       return PQT_OK;
+    case PQT_STAGE_DIST_SEQ_2D:
+      if (h->h_seq2d.empty()) return fail(h, PQT_ERR_STATE, "no BIG query has run yet");
+      if (bytes != h->h_seq2d.size() * 4) return fail(h, PQT_ERR_INVALID, "size mismatch");
+      std::memcpy(host_out, h->h_seq2d.data(), bytes);
+      return PQT_OK;
+    case PQT_STAGE_BIG_BINS: src = h->g_bigbins.p; need = (size_t)h->dbg_big_QN * h->dbg_big_cap * 4; break;
+    case PQT_STAGE_BIG_NBINS: src = h->g_bignbins.p; need = (size_t)h->dbg_big_QN * 4; break;
     default: return fail(h, PQT_ERR_INVALID, "unknown stage %d", stage);
   }
+  if ((stage == PQT_STAGE_BIG_BINS || stage == PQT_STAGE_BIG_NBINS) && (!h->debug || !h->dbg_big_QN))
+    return fail(h, PQT_ERR_STATE, "debug recording is off or no BIG query has run");
   if (stage <= PQT_STAGE_NVEC && (!h->debug || !QN)) return fail(h, PQT_ERR_STATE, "debug recording is off or no query has run");
   if (bytes != need) return fail(h, PQT_ERR_INVALID, "stage %d holds %zu bytes, caller passed %zu", stage, need, bytes);
   CU_TRY(h, cudaMemcpy(host_out, src, need, cudaMemcpyDeviceToHost));

@@ -61,6 +61,10 @@ struct TablesArgs {
   float* dbg_lut;        // [QN][LP][c1]
   float* dbg_aval;       // [QN][p][k1*c2]
   uint32_t* dbg_aidx;    // [QN][p][k1*c2]
+  // optional: first top_n entries of every sorted Step-C list (1-B variant), may be null
+  float* top_val;     // [QN][p][top_n]
+  uint32_t* top_idx;  // [QN][p][top_n]
+  uint32_t top_n;
 };
 
 // dynamic smem: q[dim] | val[p*npMax] | idx[p*npMax] | assign[k1*p]
@@ -138,6 +142,13 @@ __global__ void __launch_bounds__(128) tables_kernel(TablesArgs a) {
         uint32_t part = e / n, i = e - part * n;
         a.dbg_aval[(size_t)qi * a.p * n + e] = sval[part * a.npC + i];
         a.dbg_aidx[(size_t)qi * a.p * n + e] = sidx[part * a.npC + i];
+      }
+    }
+    if (a.top_val) {
+      for (uint32_t e = threadIdx.x; e < a.p * a.top_n; e += blockDim.x) {
+        uint32_t part = e / a.top_n, i = e - part * a.top_n;
+        a.top_val[(size_t)qi * a.p * a.top_n + e] = sval[part * a.npC + i];
+        a.top_idx[(size_t)qi * a.p * a.top_n + e] = sidx[part * a.npC + i];
       }
     }
   }
@@ -737,6 +748,12 @@ __global__ void __launch_bounds__(kTablesWarps * 32) tables_warp_kernel(TablesWa
       __syncwarp();
       bitonic_warp_smem(sv, si, a.npC, lane);
       if (lane < 16) a.idx16[((size_t)qi * a.p + part) * 16 + lane] = (lane < a.m) ? si[lane] : 0u;
+      if (a.top_val) {
+        for (uint32_t e = lane; e < a.top_n; e += 32) {
+          a.top_val[((size_t)qi * a.p + part) * a.top_n + e] = sv[e];
+          a.top_idx[((size_t)qi * a.p + part) * a.top_n + e] = si[e];
+        }
+      }
       if (a.dbg_aval) {
         for (uint32_t e = lane; e < n; e += 32) {
           a.dbg_aval[((size_t)qi * a.p + part) * n + e] = sv[e];

@@ -19,20 +19,21 @@ EXPORTS = [
     "pqt_abi_version", "pqt_create", "pqt_destroy", "pqt_last_error", "pqt_default_params",
     "pqt_set_params", "pqt_get_params", "pqt_set_stream", "pqt_read_tree", "pqt_write_tree",
     "pqt_set_tree", "pqt_get_tree_shape", "pqt_get_tree", "pqt_set_db", "pqt_set_lines",
-    "pqt_query_knn", "pqt_build_kbest_db", "pqt_line_dist", "pqt_get_db", "pqt_get_lines",
+    "pqt_query_knn", "pqt_query_big_knn_rerank2", "pqt_build_kbest_db", "pqt_line_dist", "pqt_get_db", "pqt_get_lines",
     "pqt_get_db_size", "pqt_set_shard", "pqt_query_scan_shard", "pqt_rank_candidates",
     "pqt_candidate_width", "pqt_profile_enable", "pqt_get_stats", "pqt_reset_stats",
     "pqt_debug_enable", "pqt_debug_stage",
 ]
 
 STAGES = dict(assign=0, lut=1, assign_val=2, assign_idx=3, bins=4, n_bins=5, select_idx=6,
-              n_vec=7, cb_dist=8, dist_seq=9)
+              n_vec=7, cb_dist=8, dist_seq=9, dist_seq_2d=10, big_bins=11, big_n_bins=12)
 
 
 class Params(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in (
         "k1", "max_bins", "max_trials", "bin_threads", "max_vec_per_bin", "hash_size",
-        "k1_build", "max_vec")] + [("reserved", C.c_uint32 * 8)]
+        "k1_build", "max_vec", "big_k1", "big_max_bins", "big_max_trials")] + \
+        [("reserved", C.c_uint32 * 5)]
 
 
 class Stats(C.Structure):
@@ -89,6 +90,7 @@ def lib():
         L.pqt_set_lines.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
         L.pqt_query_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32,
                                     C.c_void_p, C.c_void_p, C.c_int]
+        L.pqt_query_big_knn_rerank2.argtypes = L.pqt_query_knn.argtypes
         L.pqt_build_kbest_db.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]
         L.pqt_line_dist.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32]
         L.pqt_get_db.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -250,6 +252,21 @@ class PerturbationProTree:
         dp, ddev = _ptr(out_dist)
         assert idev == ddev
         self._chk(self._L.pqt_query_knn(self._h, qp, qdev, QN, k, ip, dp, idev))
+        return out_idx, out_dist
+
+    def queryBIGKNNRerank2(self, Q, QN, k, out_idx=None, out_dist=None):
+        """queryBIGKNNRerank2 (pqt/PerturbationProTree.hh:80): the 1-B variant; the line
+        codes are the resident ones instead of the reference's pinned-host hLines."""
+        if isinstance(Q, np.ndarray):
+            Q = np.ascontiguousarray(Q, np.float32)
+        qp, qdev = _ptr(Q)
+        if out_idx is None:
+            out_idx = np.zeros((QN, k), np.uint32)
+            out_dist = np.zeros((QN, k), np.float32)
+        ip, idev = _ptr(out_idx)
+        dp, ddev = _ptr(out_dist)
+        assert idev == ddev
+        self._chk(self._L.pqt_query_big_knn_rerank2(self._h, qp, qdev, QN, k, ip, dp, idev))
         return out_idx, out_dist
 
     def queryScanShard(self, Q, QN, k, val, idx):

@@ -70,6 +70,20 @@ def main(case_path, out_path, ppqt):
     L.refgpu_query_knn(h, vp(Q.ctypes.data), QN, k, vp(idx.ctypes.data), vp(dist.ctypes.data))
     out.update(idx=idx, dist=dist)
     np.savez(out_path, **out)
+    # ---- the 1-B variant (queryBIGKNNRerank2) with a small k so that the bin walk ends
+    # long before the reference would read past its d_distSeq allocation
+    kb = int(c["k_big"]) if "k_big" in c else 0
+    if kb:
+        cap = max(kb, 32)
+        bb = np.zeros((QN, cap), np.uint32)
+        nb = np.zeros(QN, np.uint32)
+        bi = np.zeros((QN, kb), np.uint32)
+        bd = np.zeros((QN, kb), np.float32)
+        seq2d = np.zeros((10, 65536), np.uint32)
+        L.refgpu_big(h, vp(Q.ctypes.data), QN, kb, cap, vp(bb.ctypes.data), vp(nb.ctypes.data),
+                     vp(bi.ctypes.data), vp(bd.ctypes.data), vp(seq2d.ctypes.data))
+        np.savez(out_path + ".big.npz", big_bins=bb, big_n_bins=nb, big_idx=bi, big_dist=bd,
+                 seq2d=seq2d)
 
 
 if __name__ == "__main__":

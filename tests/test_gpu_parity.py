@@ -252,3 +252,47 @@ def test_sharded_scan_assembles_the_single_gpu_result(case_small):
     assert np.array_equal(oi.cpu().numpy().view(np.uint32), i0)
     assert np.array_equal(od.cpu().numpy(), d0)
     t.close()
+
+
+# ---- a11: the 1-B variant queryBIGKNNRerank2 ---------------------------------------------
+
+def _big_check(c, hash_size, ks):
+    prm = c["prm"]
+    QN = c["Q"].shape[0]
+    bp = po.big_params(prm.dim, prm.p, prm.c1, prm.c2, prm.line_parts, hash_size=hash_size)
+    t = make_gpu_index(c)
+    t.debug(True)
+    for k in ks:
+        d0, i0, info = po.query_big_knn_rerank2(bp, c["cb1"], c["cb2"], c["prefix"], c["counts"],
+                                                c["db_idx"], c["lines"], c["Q"], k)
+        i1, d1 = t.queryBIGKNNRerank2(c["Q"], QN, k)
+        assert np.array_equal(t.stage("dist_seq_2d", (10, 65536), np.uint32), po.dist_seq_2d(512))
+        ok = ~info["ambiguous"]  # slope index on a logf rounding boundary: host/device may differ
+        assert ok.sum() >= QN - 2
+        assert np.array_equal(t.stage("n_vec", (QN,), np.uint32)[ok], info["n_vec"][ok])
+        assert np.array_equal(t.stage("big_n_bins", (QN,), np.uint32)[ok], info["n_bins"][ok])
+        assert np.array_equal(d1[ok], d0[ok])
+        assert np.array_equal(i1[ok], i0[ok])
+    t.close()
+
+
+def test_big_variant_dense_index():
+    import conftest
+    c = conftest.make_case(N=30000, QN=24, c1=16, c2=8, LP=16, hash_size=20011, seed=21)
+    _big_check(c, 20011, (16, 256, 1024, 4096))
+
+
+def test_big_variant_sparse_index(case_small):
+    # almost all hash bins empty: hundreds of merge rounds per query, up to the point where
+    # the reference would leave its d_distSeq allocation
+    c = dict(case_small)
+    c["Q"] = case_small["Q"][:12]
+    _big_check(c, case_small["prm"].hash_size, (64, 512))
+
+
+def test_big_variant_rejects_unsupported_shapes(case_small):
+    import pqt_b200
+    t = make_gpu_index(case_small, big_k1=4)  # 4 * c2 = 32 < 64 sorted entries per part
+    with pytest.raises(pqt_b200.PqtError):
+        t.queryBIGKNNRerank2(case_small["Q"], 4, 16)
+    t.close()

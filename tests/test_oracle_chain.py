@@ -184,3 +184,64 @@ def test_builder_properties(case_small):
     d, i = oracle_query(c2, 64)
     hit = [q in i[q] for q in range(32)]
     assert np.mean(hit) > 0.9
+
+
+# ---- a11: the 1-B variant (queryBIGKNNRerank2) -------------------------------------------
+
+def test_dist_seq_2d_properties():
+    seq = po.dist_seq_2d(512)
+    assert seq.shape == (10, 65536)
+    for s in range(10):
+        assert seq[s, 0] == 0                      # origin first
+        assert len(np.unique(seq[s])) == 65536     # distinct codes of the 512 x 512 grid
+        x, y = seq[s] % 512, seq[s] // 512
+        sl = np.float32(pow(0.9 * float(np.float32(1.2)), s - 5))
+        key = (np.power(x.astype(np.float32), np.float32(0.8)) +
+               sl * np.power(y.astype(np.float32), np.float32(0.8)))
+        assert np.all(np.diff(key.astype(np.float64)) >= -1e-3)   # sorted by the anisotropic cost
+    # flatter slopes walk further along x before stepping in y
+    first_y = [int(np.argmax(seq[s] // 512 > 0)) for s in range(10)]
+    assert first_y == sorted(first_y)
+
+
+def test_slope_idx_cases():
+    v = np.arange(64, dtype=np.float32)
+    assert po.slope_idx(v, v, 256)[0] == 5                        # equal growth -> middle slope
+    assert po.slope_idx(v, 1.2 ** 3 * v, 256)[0] == 8
+    assert po.slope_idx(v, 100 * v, 256)[0] == 9                  # clamped
+    assert po.slope_idx(100 * v, v, 256)[0] == 0
+    assert po.slope_idx(np.zeros(64, np.float32), v, 256)[0] == 9   # division by zero -> +inf
+    assert po.slope_idx(np.zeros(64, np.float32), np.zeros(64, np.float32), 256)[0] == 0  # NaN
+
+
+def _dense_case():
+    """c1 = c2 = 8, tiny hash: most hash bins are occupied, the regime of the 1-B path"""
+    import conftest
+    return conftest.make_case(N=30000, QN=24, c1=16, c2=8, LP=16, hash_size=20011, seed=21)
+
+
+def test_big_path_properties():
+    c = _dense_case()
+    prm = po.big_params(128, 4, 16, 8, 16, hash_size=20011)
+    k = 256
+    d, i, info = po.query_big_knn_rerank2(prm, c["cb1"], c["cb2"], c["prefix"], c["counts"],
+                                          c["db_idx"], c["lines"], c["Q"], k)
+    assert np.all(np.diff(d, axis=1) >= 0)          # test/test1B.cpp:1256-1265
+    assert np.all(info["n_vec"] <= k) and np.all(info["n_bins"] <= prm.max_bins)
+    assert info["n_vec"].min() > 0
+    cbd = c["cb_dist"]
+    d0, i0, st = oracle_query(c, k, stages=True)    # same LUT (Step B does not depend on k1)
+    for q in range(c["Q"].shape[0]):
+        nv = int(info["n_vec"][q])
+        assert np.all(i[q, nv:] == po.PAD_IDX)
+        real = i[q, :nv]
+        assert np.all(real < c["X"].shape[0])
+        # reported distances are the ADC distances of the reported ids
+        for j in (0, nv // 2, nv - 1):
+            assert d[q, j] == po.line_adc(c["prm"], st["lut"][q], cbd, c["lines"][real[j]])
+    # a DB vector used as query finds itself
+    c2 = dict(c)
+    c2["Q"] = c["X"][:16]
+    d, i, info = po.query_big_knn_rerank2(prm, c["cb1"], c["cb2"], c["prefix"], c["counts"],
+                                          c["db_idx"], c["lines"], c2["Q"], k)
+    assert np.mean([q in i[q] for q in range(16)]) > 0.8

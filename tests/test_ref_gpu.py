@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
 
 REF_LIB = os.path.join(conftest.ROOT, "oracle", "_ref", "libpqt_ref_gpu.so")
 HASH = 400000000  # compiled into the reference (pqt/PerturbationProTree.hh:12)
+K_BIG = 16        # kVec of the queryBIGKNNRerank2 cross-check
 
 
 def _run_case(tmp, N, QN, seed):
@@ -32,7 +33,7 @@ def _run_case(tmp, N, QN, seed):
     index = po.build_index(prm, cb1, cb2, X, k1_build=16)
     nz = np.nonzero(index["counts"])[0].astype(np.uint32)
     case = str(tmp / ("case%d.npz" % seed))
-    np.savez(case, X=X, Q=Q, dim=dim, p=p, c1=c1, c2=c2, LP=LP, k1=k1, k=k, hash_size=HASH,
+    np.savez(case, X=X, Q=Q, dim=dim, p=p, c1=c1, c2=c2, LP=LP, k1=k1, k=k, hash_size=HASH, k_big=K_BIG,
              nz_bins=nz, nz_counts=index["counts"][nz], db_idx=index["db_idx"], lines=index["lines"])
     out = str(tmp / ("out%d.npz" % seed))
     runner = os.path.join(conftest.ROOT, "tests", "ref_gpu_runner.py")
@@ -43,13 +44,14 @@ def _run_case(tmp, N, QN, seed):
         r = None
     stages = dict(np.load(out + ".stages.npz")) if os.path.exists(out + ".stages.npz") else None
     full = dict(np.load(out)) if os.path.exists(out) else None
+    big = dict(np.load(out + ".big.npz")) if os.path.exists(out + ".big.npz") else None
     if stages is None:
         pytest.fail("the reference kernels did not produce the stage outputs: %s"
                     % (r.stderr[-2000:] if r else "timeout"))
     d0, i0, st0 = po.query_knn(prm, cb1, cb2, index["prefix"], index["counts"], index["db_idx"],
                                index["lines"], Q, k, stages=True)
-    return dict(prm=prm, index=index, stages=stages, full=full, oracle=(d0, i0, st0), X=X, Q=Q,
-                cb1=cb1, cb2=cb2, k=k)
+    return dict(prm=prm, index=index, stages=stages, full=full, big=big, oracle=(d0, i0, st0),
+                X=X, Q=Q, cb1=cb1, cb2=cb2, k=k, shape=(dim, p, c1, c2, LP))
 
 
 @pytest.fixture(scope="module")
@@ -137,3 +139,38 @@ def test_reference_query_knn_end_to_end_race_free_regime(ref_run_sparse):
 
 def test_reference_kernels_steps_a_to_d_sparse(ref_run_sparse):
     test_reference_kernels_steps_a_to_d(ref_run_sparse)
+
+
+def _check_big(run):
+    """queryBIGKNNRerank2 on the reference's own kernels: prepare2DDistSequence, the bins of
+    getBIGBins2D (bit-exact, in order), and the result ids / race-free distances."""
+    if run["big"] is None:
+        pytest.xfail("the reference's queryBIGKNNRerank2 did not complete on this GPU")
+    big, index = run["big"], run["index"]
+    dim, p, c1, c2, LP = run["shape"]
+    assert np.array_equal(big["seq2d"], po.dist_seq_2d(512))
+    prm = po.big_params(dim, p, c1, c2, LP, hash_size=HASH)
+    d0, i0, info = po.query_big_knn_rerank2(prm, run["cb1"], run["cb2"], index["prefix"],
+                                            index["counts"], index["db_idx"], index["lines"],
+                                            run["Q"], K_BIG)
+    # bins: re-run the oracle's step to get the list itself
+    compared = 0
+    for q in range(run["Q"].shape[0]):
+        if info["ambiguous"][q]:
+            continue  # slope index on a rounding boundary of logf: host/device may differ
+        assert big["big_n_bins"][q] == info["n_bins"][q]
+        n = int(info["n_vec"][q])
+        assert sorted(big["big_idx"][q, :n]) == sorted(i0[q, :n])
+        if n <= RACE_FREE:
+            assert np.array_equal(big["big_dist"][q], d0[q])
+            assert np.array_equal(big["big_idx"][q, :n], i0[q, :n])
+        compared += 1
+    assert compared >= run["Q"].shape[0] // 2
+
+
+def test_reference_big_variant(ref_run):
+    _check_big(ref_run)
+
+
+def test_reference_big_variant_sparse(ref_run_sparse):
+    _check_big(ref_run_sparse)
