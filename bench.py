@@ -40,7 +40,8 @@ def parse():
     ap.add_argument("--dim", type=int, default=128)
     ap.add_argument("--lineparts", type=int, default=16)
     ap.add_argument("--hashsize", type=int, default=400000000)
-    ap.add_argument("--clusters", type=int, default=4096)
+    ap.add_argument("--clusters", type=int, default=0,
+                    help="cluster centres of the synthetic data (0 = max(4096, n // 256))")
     ap.add_argument("--train", type=int, default=300000)
     ap.add_argument("--mode", default="shard", choices=["shard", "replica"],
                     help="N>1: bin-range shards + NCCL exchange (north_star) or index replicas")
@@ -387,6 +388,8 @@ def run_b200(a, rank, world, local_rank):
 
 def main():
     a = parse()
+    if a.clusters <= 0:
+        a.clusters = max(4096, a.n // 256)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

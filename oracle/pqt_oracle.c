@@ -563,7 +563,7 @@ uint32_t pqto_slope_idx(const float *val0, const float *val1, uint32_t N, int *a
   if (si < 0) si = 0;
   if (ambiguous && r == r) {
     float frac = fabsf(r - floorf(r) - 0.5f);
-    if (frac < 1e-3f && r > -6.f && r < 5.f) *ambiguous = 1;
+    if (frac < 1e-3f && r > -6.f && r < 5.f) *ambiguous |= 1;
   }
   return (uint32_t)si;
 }
@@ -609,7 +609,10 @@ uint32_t pqto_step_d_big(const pqto_params *prm, uint32_t k1, const uint32_t *se
   const uint32_t factor = K * K; /* uint32 wrap, :3101 */
   while (n_elements < k2 && n_iter < prm->max_trials && n_out < max_out) {
     size_t off = (size_t)si * PQTO_NUM_DISTSEQ + (size_t)n_iter * T;
-    if (off + T > seq_total) break; /* the reference reads past d_distSeq from here on */
+    if (off + T > seq_total) { /* the reference reads past d_distSeq from here on */
+      if (ambiguous) *ambiguous |= 2;
+      break;
+    }
     for (uint32_t t = 0; t < T; t++) {
       uint32_t s = seq2d[off + t], x = s % dc, y = s / dc;
       if (x < nI && y < nI) {

@@ -144,7 +144,9 @@ uint32_t pqto_step_d_big(const pqto_params *prm, uint32_t k1, const uint32_t *se
                          const uint32_t *bin_counts, uint32_t k2, uint32_t *bins, int *ambiguous);
 /* queryBIGKNNRerank2.  prm->k1 (16), prm->max_bins (524288), prm->max_trials (2560) are the
  * literals of :8604-8639 / :3725-3727; candidates per bin are capped at pow2ceil(k) (:6525).
- * ambiguous[QN] (may be NULL) flags queries whose slope index sits on a rounding boundary. */
+ * ambiguous[QN] (may be NULL): bit 0 = a slope index sits on a logf rounding boundary,
+ * bit 1 = the bin walk ran into the end of d_distSeq (the reference reads past its
+ * allocation from there on: undefined, not comparable). */
 int pqto_query_big_knn_rerank2(const pqto_params *prm, const float *cb1, const float *cb2,
                                const uint32_t *bin_prefix, const uint32_t *bin_counts,
                                const uint32_t *db_idx, const uint32_t *lines, const float *Q,

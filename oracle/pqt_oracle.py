@@ -227,7 +227,8 @@ def query_big_knn_rerank2(prm, cb1, cb2, prefix, counts, db_idx, lines, Q, k, nt
         C.c_int(nthreads))
     if rc != 0:
         raise ValueError("pqto_query_big_knn_rerank2: unsupported shape (rc=%d)" % rc)
-    return out_d, out_i, dict(n_bins=nb, n_vec=nv, ambiguous=amb.astype(bool))
+    return out_d, out_i, dict(n_bins=nb, n_vec=nv, ambiguous=(amb & 1).astype(bool),
+                              ran_off_table=(amb & 2).astype(bool))
 
 
 def assign_bins(prm, cb1, cb2, X, k1=16, nthreads=0):

@@ -8,14 +8,14 @@
 //                   touch HBM
 //   rank2_kernel    ranking only (multi-GPU path: after the shards are assembled)
 //
-// Ranking.  The reference ranks with a bitonic network (pqt/bitonicSort.cuh:16-78),
-// whose output is a plain ascending sort whenever all keys are distinct; only ties
-// make the network's own (unstable) order observable.  So the kernels sort the nVec
-// real candidates with a register/shuffle bitonic sort of pow2ceil(nVec) elements,
-// then check (a) every real distance < 1e7 (the pad value) and (b) no two adjacent
-// sorted distances are equal unless they belong to the same vector id.  If either check fails the query is re-ranked with the
-// exact max_vec-wide network in shared memory, candidate order restored first.  Both
-// paths therefore return exactly what the reference's network returns.
+// Ranking.  The reference ranks with a bitonic network over max_vec slots
+// (pqt/bitonicSort.cuh:16-78).  grp_sort_pairs executes the same compare-exchanges (same
+// pairs, same direction rule, strict compares) in registers / shuffles / shared memory, so
+// at full width with the reference's 1e7 padding it returns the reference's order including
+// ties.  For sparse candidate lists the kernels first sort only pow2ceil(nVec) slots; that
+// is the same result unless a distance is >= 1e7 or two different ids have bit-equal
+// distances, which is checked, and then the full-width network runs on the restored
+// candidate order.  Both paths therefore return exactly what the reference's network returns.
 #pragma once
 #include "common.cuh"
 #include "query_kernels.cuh"
@@ -467,6 +467,13 @@ __device__ __forceinline__ void grp_sort_dispatch(const Grp& g, float* sv, uint1
 // Ranks the candidates of one query held in shared memory and writes the first k.
 //   s_val[a], s_id[a] for a < nv: ADC distance / vector id in candidate order
 //   s_pay: scratch [max_vec]; s_flag: one word.  g.n >= 256 (max_vec <= 4096).
+//
+// grp_sort_pairs executes exactly the compare-exchanges of the reference's network
+// (pqt/bitonicSort.cuh:16-78: pairs (i, i^j), ascending iff (i & k) == 0, strict compare), so
+// run over all max_vec slots with the reference's padding (1e7) it returns the reference's
+// order INCLUDING ties.  Sparse candidate lists are first sorted at pow2ceil(nVec) width
+// (pads +inf); that shortcut is valid unless a distance is >= 1e7 or two different ids tie,
+// in which case the candidate order is restored and the full-width network runs.
 __device__ __forceinline__ void rank_and_emit(const Grp& g, float* s_val, uint16_t* s_pay,
                                               const uint32_t* s_id, uint32_t* s_flag, uint32_t nv,
                                               uint32_t max_vec, uint32_t k, float* out_dist,
@@ -474,49 +481,66 @@ __device__ __forceinline__ void rank_and_emit(const Grp& g, float* s_val, uint16
   const uint32_t t = g.t;
   uint32_t n2 = pow2ceil(nv < 32 ? 32 : nv);
   if (n2 > max_vec) n2 = max_vec;  // max_vec < 32: tiny widths
+  const bool full = (n2 == max_vec);
   if (t == 0) *s_flag = 0;
   g.sync();
-  // payload = candidate position; pads (+inf) behind the real candidates
-  bool bad = false;
+  // payload = candidate position
+  uint32_t bad = 0;
   for (uint32_t e = t; e < n2; e += g.n) {
     if (e < nv) {
       s_pay[e] = (uint16_t)e;
-      bad |= !(s_val[e] < kPadDist);  // >= 1e7, inf or NaN: pad order matters -> exact path
+      const float v = s_val[e];
+      if (!(fabsf(v) < __int_as_float(0x7f800000))) bad |= 2u;  // NaN / inf: min/max compare-exchange
+      if (!(v < kPadDist)) bad |= 1u;                          // pad order matters
     } else {
-      s_val[e] = __int_as_float(0x7f800000);
+      s_val[e] = full ? kPadDist : __int_as_float(0x7f800000);
       s_pay[e] = kPayPad;
     }
   }
-  if (bad) atomicOr(s_flag, 1u);
+  if (bad) atomicOr(s_flag, bad);
   g.sync();
-  if (n2 >= 32) grp_sort_dispatch(g, s_val, s_pay, n2);
-  // ties between copies of the same vector are harmless (the same bin can be listed more
-  // than once: the uint32 Horner hash keeps only idx_0 mod 4 of the first part); ties
-  // between different ids expose the network's order -> exact path
-  for (uint32_t e = t + 1; e < nv; e += g.n)
-    if (s_val[e] == s_val[e - 1] && s_id[s_pay[e]] != s_id[s_pay[e - 1]]) atomicOr(s_flag, 1u);
+  const bool nonfinite = (*s_flag & 2u) != 0;
+  if (n2 >= 32 && !nonfinite) grp_sort_dispatch(g, s_val, s_pay, n2);
+  if (!full && !nonfinite) {
+    // ties between copies of the same vector are harmless (the same bin can be listed more
+    // than once: the uint32 Horner hash keeps only idx_0 mod 4 of the first part); ties
+    // between different ids expose the network's order
+    for (uint32_t e = t + 1; e < nv; e += g.n)
+      if (s_val[e] == s_val[e - 1] && s_id[s_pay[e]] != s_id[s_pay[e - 1]]) atomicOr(s_flag, 1u);
+  }
   g.sync();
-  if (*s_flag || n2 < 32) {
+  const uint32_t flag = *s_flag;
+  if (n2 < 32 || nonfinite || (!full && flag)) {
     if (t == 0 && exact_counter) atomicAdd(exact_counter, 1ull);
-    // ---- exact path: restore candidate order, pad to max_vec with 1e7, run the
-    // reference's network (:5331-5340)
-    float rv[16];
-    uint32_t rp[16];
-    int cnt = 0;
-    for (uint32_t e = t; e < n2 && cnt < 16; e += g.n, cnt++) {
-      rv[cnt] = s_val[e];
-      rp[cnt] = s_pay[e];
+    // restore candidate order, pad to max_vec with 1e7, run the full-width network (:5331-5340)
+    if (!nonfinite && n2 >= 32) {
+      float rv[16];
+      uint32_t rp[16];
+      int cnt = 0;
+      for (uint32_t e = t; e < n2 && cnt < 16; e += g.n, cnt++) {
+        rv[cnt] = s_val[e];
+        rp[cnt] = s_pay[e];
+      }
+      g.sync();
+      for (int c = 0; c < cnt; c++)
+        if (rp[c] != kPayPad) s_val[rp[c]] = rv[c];
+      g.sync();
     }
-    g.sync();
-    for (int c = 0; c < cnt; c++)
-      if (rp[c] != kPayPad) s_val[rp[c]] = rv[c];
-    g.sync();
     for (uint32_t e = t; e < max_vec; e += g.n) {
       if (e >= nv) s_val[e] = kPadDist;
       s_pay[e] = e < nv ? (uint16_t)e : kPayPad;
     }
     g.sync();
-    bitonic_smem_grp(g, s_val, s_pay, max_vec);
+    if (nonfinite || max_vec < 32)
+      bitonic_smem_grp(g, s_val, s_pay, max_vec);  // literal strict-compare network
+    else
+      grp_sort_dispatch(g, s_val, s_pay, max_vec);
+    for (uint32_t e = t; e < k; e += g.n) {
+      const uint32_t a = s_pay[e];
+      out_dist[e] = s_val[e];
+      out_idx[e] = (a == kPayPad) ? kPadIdx : s_id[a];
+    }
+  } else if (full) {
     for (uint32_t e = t; e < k; e += g.n) {
       const uint32_t a = s_pay[e];
       out_dist[e] = s_val[e];
