@@ -250,27 +250,39 @@ def run_b200(a, rank, world, local_rank):
     pin_i = torch.empty((nq_out, k), dtype=torch.int32).pin_memory()
     pin_d = torch.empty((nq_out, k), dtype=torch.float32).pin_memory()
     if sharded:
-        val = torch.empty((QN, mv), dtype=torch.float32, device=device)
-        idx = torch.empty((QN, mv), dtype=torch.int32, device=device)
-        val_s = torch.empty((nq_out, mv), dtype=torch.float32, device=device)
-        idx_s = torch.empty((nq_out, mv), dtype=torch.int32, device=device)
+        # fused scan + exchange: candidate arrays of the own queries are owned by the handle
+        # and mapped by the peers through CUDA IPC
+        t.shardExchangeAlloc(nq_out, mv)
+        handles = [None] * world
+        dist.all_gather_object(handles, t.shardExchangeHandle())
+        t.shardExchangeOpen(handles)
+        cand = torch.zeros((QN, mv), dtype=torch.int32, device=device)
+        nvec = torch.zeros((QN,), dtype=torch.int32, device=device)
+        token = torch.zeros(1, dtype=torch.int32, device=device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
+
+    def shard_step(Qdev, oi, od):
+        # 1. Steps A-E1 for the own queries (+ the LUT of every query)
+        t.shardCandidates(Qdev, QN, k, q_lo, q_hi, cand, nvec)
+        # 2. everyone learns every query's candidate positions
+        dist.all_gather_into_tensor(cand, cand[q_lo:q_hi])
+        dist.all_gather_into_tensor(nvec, nvec[q_lo:q_hi])
+        # 3. scan the own shard's candidates of all queries, results stored into the owners'
+        #    arrays over NVLink; 4. stream-ordered cross-rank barrier; 5. rank the own queries
+        t.shardScanP2P(QN, k, cand, nvec)
+        dist.all_reduce(token)
+        t.shardRank(nvec[q_lo:q_hi], nq_out, k, oi, od)
 
     def step_device():
         if sharded:
-            t.queryScanShard(Qd, QN, k, val, idx)
-            sharding.exchange(val, idx, val_s, idx_s, rank, world)
-            t.rankCandidates(val_s, idx_s, nq_out, mv, k, out_i, out_d)
+            shard_step(Qd, out_i, out_d)
         else:
             t.queryKNN(Qd[q_lo:q_hi], nq_out, k, out_i, out_d)
 
     def step_e2e():
         # host buffers in, host buffers out, through the public call
         if sharded:
-            Qdev = Qh.to(device, non_blocking=True)
-            t.queryScanShard(Qdev, QN, k, val, idx)
-            sharding.exchange(val, idx, val_s, idx_s, rank, world)
-            t.rankCandidates(val_s, idx_s, nq_out, mv, k, pin_i, pin_d)
+            shard_step(Qh.to(device, non_blocking=True), pin_i, pin_d)
         else:
             t.queryKNN(Qh[q_lo:q_hi], nq_out, k, pin_i, pin_d)
 
@@ -369,7 +381,7 @@ def run_b200(a, rank, world, local_rank):
         "scaling": "strong" if sharded else "weak" if world > 1 else "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "l2": "flushed between steps (256 MiB write)",
-                   "parallelism": ("bin-range shards x%d + NCCL reduce-scatter" % world) if sharded
+                   "parallelism": ("bin-range shards x%d, scan fused with peer-memory exchange (NVLink), NCCL all-gather of candidate lists" % world) if sharded
                    else ("replicas x%d" % world) if replica else "single GPU",
                    "index_build_s": build_s},
         "roofline": roofline,

@@ -180,6 +180,38 @@ int pqt_query_scan_shard(pqt_index *h, const float *Q, int q_on_device, uint32_t
  * emit the first k per query, exactly like the tail of rerankKernelFast :5331-5346 */
 int pqt_rank_candidates(pqt_index *h, float *val, uint32_t *idx, uint32_t QN, uint32_t max_vec,
                         uint32_t k, uint32_t *out_idx, float *out_dist, int out_on_device);
+/* ---- multi-GPU, fused scan + exchange over peer memory ----------------------------------
+ * Rank r owns queries [r*q_per_rank, (r+1)*q_per_rank) (Steps A, C, D, E1 and the ranking)
+ * and a slice of the bin-ordered codes (pqt_set_shard).  Per batch:
+ *   1. pqt_shard_candidates   Steps A-E1 for the own queries -> rows of cand_pos / n_vec;
+ *                             Step B (the LUT) for ALL queries (cheaper than shipping it)
+ *   2. all-gather of cand_pos / n_vec (NCCL, caller)
+ *   3. pqt_shard_scan_p2p     ADC scan of the own shard's candidates of ALL queries; every
+ *                             result is stored directly into the candidate arrays of the
+ *                             rank that owns the query (peer memory over NVLink)
+ *   4. a cross-rank barrier on the stream (caller: any tiny NCCL collective)
+ *   5. pqt_shard_rank         bitonic ranking of the own queries
+ * The exchange buffers (val/idx [q_per_rank][max_vec]) are owned by the handle; peers map
+ * them through CUDA IPC handles (or raw pointers inside one process). */
+int pqt_shard_exchange_alloc(pqt_index *h, uint32_t q_per_rank, uint32_t max_vec);
+/* 128 bytes: cudaIpcMemHandle_t of the val buffer, then of the idx buffer */
+int pqt_shard_exchange_handle(pqt_index *h, void *handle128);
+/* handles: world * 128 bytes, entry r from rank r (the own entry is ignored) */
+int pqt_shard_exchange_open(pqt_index *h, uint32_t world, const void *handles);
+/* same-process alternative (tests): raw device pointers of every rank's buffers */
+int pqt_shard_exchange_set_peers(pqt_index *h, uint32_t world, void *const *val_ptrs,
+                                 void *const *idx_ptrs);
+int pqt_shard_exchange_ptrs(pqt_index *h, void **val_ptr, void **idx_ptr);
+/* Q: all QN queries (device or host); cand_pos [QN][max_vec] / n_vec [QN]: DEVICE arrays,
+ * rows [q_lo, q_hi) are written */
+int pqt_shard_candidates(pqt_index *h, const float *Q, int q_on_device, uint32_t QN, uint32_t k,
+                         uint32_t q_lo, uint32_t q_hi, uint32_t *cand_pos, uint32_t *n_vec);
+int pqt_shard_scan_p2p(pqt_index *h, uint32_t QN, uint32_t k, const uint32_t *cand_pos,
+                       const uint32_t *n_vec);
+/* n_vec_own: DEVICE [q_per_rank] (the own rows of n_vec); idx/dist: [q_per_rank][k] */
+int pqt_shard_rank(pqt_index *h, const uint32_t *n_vec_own, uint32_t q_own, uint32_t k,
+                   uint32_t *idx, float *dist, int out_on_device);
+
 /* pow2ceil(k) or params.max_vec: row length of the candidate arrays */
 int pqt_candidate_width(const pqt_index *h, uint32_t k, uint32_t *max_vec);
 

@@ -99,6 +99,12 @@ struct pqt_index {
   bool debug = false;
   uint32_t dbg_QN = 0, dbg_k = 0, dbg_maxvec = 0;
   DevBuf g_assign, g_lut, g_aval, g_aidx, g_bins, g_nbins, g_sel;
+  // multi-GPU exchange (fused scan + peer stores)
+  DevBuf x_val, x_idx;  // own [q_per_rank][max_vec] candidate arrays, written by peers
+  uint32_t x_q_per_rank = 0, x_max_vec = 0, x_world = 0;
+  float* x_peer_val[8] = {nullptr};
+  uint32_t* x_peer_idx[8] = {nullptr};
+  bool x_ipc_opened[8] = {false};
   DevBuf d_exact;  // one uint64: queries ranked by the exact-network fallback
 
   // profiling
@@ -729,10 +735,15 @@ int pqt_destroy(pqt_index* h) {
   for (DevBuf* b : {&h->d_cb1, &h->d_cb2, &h->d_cb1T, &h->d_cb2T, &h->d_distseq, &h->d_seqnib, &h->d_seqsorted, &h->d_seq2d, &h->s_topv, &h->s_topi, &h->g_bigbins, &h->g_bignbins, &h->d_bitmap, &h->d_rank_base, &h->d_cprefix,
                     &h->d_dbidx, &h->d_codes, &h->d_cbd, &h->d_cbd_dup, &h->s_q, &h->s_lut, &h->s_idx16,
                     &h->s_cand, &h->s_nvec, &h->s_val, &h->s_idx, &h->s_outd, &h->s_outi, &h->g_assign,
-                    &h->g_lut, &h->g_aval, &h->g_aidx, &h->g_bins, &h->g_nbins, &h->g_sel, &h->d_exact})
+                    &h->g_lut, &h->g_aval, &h->g_aidx, &h->g_bins, &h->g_nbins, &h->g_sel, &h->d_exact, &h->x_val, &h->x_idx})
     b->release();
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
+  for (uint32_t r = 0; r < 8; r++)
+    if (h->x_ipc_opened[r]) {
+      cudaIpcCloseMemHandle(h->x_peer_val[r]);
+      cudaIpcCloseMemHandle(h->x_peer_idx[r]);
+    }
   for (auto& e : h->slab_ev) cudaEventDestroy(e);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1171,6 +1182,285 @@ int pqt_query_scan_shard(pqt_index* h, const float* Q, int q_on_device, uint32_t
   PQ_TRY(run_scan_chain(h, dQ, QN, k, val, idx));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   if (h->profile) accumulate_profile(h, QN, false);
+  return PQT_OK;
+}
+
+// ---- multi-GPU: fused scan + exchange over peer memory ---------------------------------
+int pqt_shard_exchange_alloc(pqt_index* h, uint32_t q_per_rank, uint32_t max_vec) {
+  if (!h || !q_per_rank || !max_vec) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  // cudaIpcGetMemHandle needs a plain cudaMalloc allocation
+  h->x_val.release();
+  h->x_idx.release();
+  CU_TRY(h, h->x_val.ensure((size_t)q_per_rank * max_vec * 4));
+  CU_TRY(h, h->x_idx.ensure((size_t)q_per_rank * max_vec * 4));
+  h->x_q_per_rank = q_per_rank;
+  h->x_max_vec = max_vec;
+  return PQT_OK;
+}
+
+int pqt_shard_exchange_handle(pqt_index* h, void* handle128) {
+  if (!h || !handle128) return PQT_ERR_INVALID;
+  if (!h->x_val.p) return fail(h, PQT_ERR_STATE, "pqt_shard_exchange_alloc first");
+  CU_TRY(h, cudaSetDevice(h->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaIpcMemHandle_t hv, hi;
+  CU_TRY(h, cudaIpcGetMemHandle(&hv, h->x_val.p));
+  CU_TRY(h, cudaIpcGetMemHandle(&hi, h->x_idx.p));
+  std::memcpy(handle128, &hv, 64);
+  std::memcpy(static_cast<char*>(handle128) + 64, &hi, 64);
+  return PQT_OK;
+}
+
+int pqt_shard_exchange_open(pqt_index* h, uint32_t world, const void* handles) {
+  if (!h || !handles || world == 0 || world > 8) return PQT_ERR_INVALID;
+  if (world != h->world) return fail(h, PQT_ERR_STATE, "world differs from pqt_set_shard");
+  if (!h->x_val.p) return fail(h, PQT_ERR_STATE, "pqt_shard_exchange_alloc first");
+  CU_TRY(h, cudaSetDevice(h->device));
+  for (uint32_t r = 0; r < world; r++) {
+    if (r == h->rank) {
+      h->x_peer_val[r] = h->x_val.as<float>();
+      h->x_peer_idx[r] = h->x_idx.as<uint32_t>();
+      continue;
+    }
+    cudaIpcMemHandle_t hv, hi;
+    std::memcpy(&hv, static_cast<const char*>(handles) + (size_t)r * 128, 64);
+    std::memcpy(&hi, static_cast<const char*>(handles) + (size_t)r * 128 + 64, 64);
+    void *pv = nullptr, *pi = nullptr;
+    CU_TRY(h, cudaIpcOpenMemHandle(&pv, hv, cudaIpcMemLazyEnablePeerAccess));
+    CU_TRY(h, cudaIpcOpenMemHandle(&pi, hi, cudaIpcMemLazyEnablePeerAccess));
+    h->x_peer_val[r] = static_cast<float*>(pv);
+    h->x_peer_idx[r] = static_cast<uint32_t*>(pi);
+    h->x_ipc_opened[r] = true;
+  }
+  h->x_world = world;
+  return PQT_OK;
+}
+
+int pqt_shard_exchange_set_peers(pqt_index* h, uint32_t world, void* const* val_ptrs,
+                                 void* const* idx_ptrs) {
+  if (!h || !val_ptrs || !idx_ptrs || world == 0 || world > 8) return PQT_ERR_INVALID;
+  if (world != h->world) return fail(h, PQT_ERR_STATE, "world differs from pqt_set_shard");
+  for (uint32_t r = 0; r < world; r++) {
+    h->x_peer_val[r] = static_cast<float*>(val_ptrs[r]);
+    h->x_peer_idx[r] = static_cast<uint32_t*>(idx_ptrs[r]);
+  }
+  h->x_world = world;
+  return PQT_OK;
+}
+
+int pqt_shard_exchange_ptrs(pqt_index* h, void** val_ptr, void** idx_ptr) {
+  if (!h || !val_ptr || !idx_ptr) return PQT_ERR_INVALID;
+  if (!h->x_val.p) return fail(h, PQT_ERR_STATE, "pqt_shard_exchange_alloc first");
+  *val_ptr = h->x_val.p;
+  *idx_ptr = h->x_idx.p;
+  return PQT_OK;
+}
+
+int pqt_shard_candidates(pqt_index* h, const float* Q, int q_on_device, uint32_t QN, uint32_t k,
+                         uint32_t q_lo, uint32_t q_hi, uint32_t* cand_pos, uint32_t* n_vec) {
+  if (!h || !Q || !cand_pos || !n_vec || q_lo >= q_hi || q_hi > QN) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  PQ_TRY(check_query_state(h, QN, k));
+  const pqt_params& P = h->prm;
+  const uint32_t max_vec = candidate_width(h, k);
+  const uint32_t n = P.k1 * h->c2, npC = pow2ceil(n);
+  const bool warp_path = h->c1 <= 32 && P.k1 <= 32 && (h->LP % h->p) == 0 &&
+                         (h->vl == 8 || h->vl == 16 || h->vl == 32) && (h->dim % 4) == 0;
+  if (!warp_path || h->p > 4)
+    return fail(h, PQT_ERR_INVALID, "the peer-store multi-GPU path supports c1 <= 32, p <= 4, dim/p in {8,16,32}");
+  const float* dQ = Q;
+  if (!q_on_device) {
+    CU_TRY(h, h->s_q.ensure((size_t)QN * h->dim * 4));
+    CU_TRY(h, cudaMemcpyAsync(h->s_q.p, Q, (size_t)QN * h->dim * 4, cudaMemcpyHostToDevice, h->stream));
+    dQ = h->s_q.as<float>();
+  }
+  PQ_TRY(ensure_dist_seq(h, h->c2 * P.k1));
+  const uint32_t nq = q_hi - q_lo;
+  CU_TRY(h, h->s_lut.ensure((size_t)QN * h->c1 * 32 * sizeof(float)));
+  CU_TRY(h, h->s_idx16.ensure((size_t)nq * h->p * 16 * sizeof(uint32_t)));
+  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[0], h->stream));
+  {
+    TablesWarpArgs w{};
+    TablesArgs& a = w.t;
+    a.Q = dQ + (size_t)q_lo * h->dim;
+    a.cb1 = h->d_cb1.as<float>();
+    a.cb2 = h->d_cb2.as<float>();
+    a.QN = nq; a.dim = h->dim; a.p = h->p; a.c1 = h->c1; a.c2 = h->c2; a.LP = h->LP;
+    a.k1 = P.k1; a.vl = h->vl; a.sl = h->sl;
+    a.npA = pow2ceil(h->c1);
+    a.npC = npC;
+    a.m = h->seq_m;
+    a.lut_dup = h->s_lut.as<float>() + (size_t)q_lo * h->c1 * 32;
+    a.idx16 = h->s_idx16.as<uint32_t>();
+    w.cb1T = h->d_cb1T.as<float>();
+    w.cb2T = h->d_cb2T.as<float>();
+    size_t smem = (size_t)(h->dim + h->c1 * 32 + 2 * kTablesWarps * a.npC) * 4;
+    uint32_t grid = std::min<uint32_t>(nq, (uint32_t)h->num_sms * 12);
+    switch (h->vl) {
+      case 8: tables_warp_kernel<8><<<grid, kTablesWarps * 32, smem, h->stream>>>(w); break;
+      case 16: tables_warp_kernel<16><<<grid, kTablesWarps * 32, smem, h->stream>>>(w); break;
+      default: tables_warp_kernel<32><<<grid, kTablesWarps * 32, smem, h->stream>>>(w); break;
+    }
+    CU_TRY(h, cudaGetLastError());
+    h->stats.kernel_launches++;
+    // Step B for the queries owned by other ranks
+    const size_t lsmem = (size_t)(h->dim + h->c1 * 32) * 4;
+    if (q_lo > 0) {
+      lut_kernel<<<std::min<uint32_t>(q_lo, (uint32_t)h->num_sms * 8), 128, lsmem, h->stream>>>(
+          dQ, h->d_cb1T.as<float>(), 0, q_lo, h->dim, h->c1, h->LP, h->sl, h->s_lut.as<float>());
+      h->stats.kernel_launches++;
+    }
+    if (q_hi < QN) {
+      lut_kernel<<<std::min<uint32_t>(QN - q_hi, (uint32_t)h->num_sms * 8), 128, lsmem, h->stream>>>(
+          dQ, h->d_cb1T.as<float>(), q_hi, QN, h->dim, h->c1, h->LP, h->sl, h->s_lut.as<float>());
+      h->stats.kernel_launches++;
+    }
+    CU_TRY(h, cudaGetLastError());
+  }
+  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[1], h->stream));
+  {
+    Bins3Args a{};
+    a.idx16 = h->s_idx16.as<uint32_t>();
+    a.seq_sorted = h->d_seqsorted.as<uint32_t>();
+    a.dir.bitmap = h->d_bitmap.as<uint32_t>();
+    a.dir.rank_base = h->d_rank_base.as<uint32_t>();
+    a.dir.cprefix = h->d_cprefix.as<uint32_t>();
+    a.hash = make_magicmod(h->db_hash_size);
+    a.QN = nq; a.p = h->p; a.c1c2 = h->c1 * h->c2;
+    a.n_probes = P.max_trials * P.bin_threads;
+    a.max_bins = P.max_bins; a.max_vec_per_bin = P.max_vec_per_bin; a.max_vec = max_vec;
+    a.cand_pos = cand_pos + (size_t)q_lo * max_vec;
+    a.n_vec = n_vec + q_lo;
+    size_t smem = (size_t)(P.max_bins + kBins3Batch + 2 * 256 + kBins3Batch / 32 + 32) * 4;
+    uint32_t grid = std::min<uint32_t>(nq, (uint32_t)h->num_sms * 6);
+    if (h->p <= 2) {
+      if (smem > 48 * 1024)
+        CU_TRY(h, cudaFuncSetAttribute(bins3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      bins3_kernel<1><<<grid, kBins2Threads, smem, h->stream>>>(a);
+    } else {
+      if (smem > 48 * 1024)
+        CU_TRY(h, cudaFuncSetAttribute(bins3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      bins3_kernel<2><<<grid, kBins2Threads, smem, h->stream>>>(a);
+    }
+    CU_TRY(h, cudaGetLastError());
+    h->stats.kernel_launches++;
+  }
+  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  if (h->profile) {
+    float t = 0;
+    cudaEventElapsedTime(&t, h->ev[0], h->ev[1]);
+    h->stats.ms_tables += t;
+    cudaEventElapsedTime(&t, h->ev[1], h->ev[2]);
+    h->stats.ms_bins += t;
+    h->stats.queries += nq;
+    h->stats.calls++;
+  }
+  return PQT_OK;
+}
+
+int pqt_shard_scan_p2p(pqt_index* h, uint32_t QN, uint32_t k, const uint32_t* cand_pos,
+                       const uint32_t* n_vec) {
+  if (!h || !cand_pos || !n_vec) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  PQ_TRY(check_query_state(h, QN, k));
+  const uint32_t max_vec = candidate_width(h, k);
+  if (!h->x_world || h->x_world != h->world) return fail(h, PQT_ERR_STATE, "exchange buffers are not connected (pqt_shard_exchange_open / _set_peers)");
+  if (max_vec != h->x_max_vec) return fail(h, PQT_ERR_INVALID, "candidate width %u differs from the exchange buffers' %u", max_vec, h->x_max_vec);
+  if ((uint64_t)h->x_q_per_rank * h->world < QN) return fail(h, PQT_ERR_INVALID, "QN exceeds q_per_rank * world");
+  ScanArgs a{};
+  a.codes = h->d_codes.as<uint32_t>();
+  a.ids = h->d_dbidx.as<uint32_t>() + h->pos_lo;
+  a.cand_pos = cand_pos;
+  a.n_vec = n_vec;
+  a.lut_dup = h->s_lut.as<float>();
+  a.cbd_dup = h->d_cbd_dup.as<float>();
+  a.QN = QN; a.c1 = h->c1; a.max_vec = max_vec;
+  a.pos_lo = h->pos_lo; a.pos_hi = h->pos_hi;
+  a.p2p = 1;
+  a.q_per_rank = h->x_q_per_rank;
+  for (uint32_t r = 0; r < h->world; r++) {
+    a.peer_val[r] = h->x_peer_val[r];
+    a.peer_idx[r] = h->x_peer_idx[r];
+  }
+  size_t smem = ((size_t)h->c1 * h->c1 * 32 + 2 * (size_t)h->c1 * 32) * 4 + 64;
+  if (smem > 220 * 1024) return fail(h, PQT_ERR_INVALID, "c1 = %u > 32 is not supported by the ADC scan yet", h->c1);
+  uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms);
+  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+#define LAUNCH_SCAN_P2P(LPV)                                                                     \
+  do {                                                                                           \
+    CU_TRY(h, cudaFuncSetAttribute(adc_scan_kernel<LPV>,                                         \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    adc_scan_kernel<LPV><<<grid, kScanThreads, smem, h->stream>>>(a);                            \
+  } while (0)
+  switch (h->LP) {
+    case 1: LAUNCH_SCAN_P2P(1); break;
+    case 2: LAUNCH_SCAN_P2P(2); break;
+    case 4: LAUNCH_SCAN_P2P(4); break;
+    case 8: LAUNCH_SCAN_P2P(8); break;
+    case 16: LAUNCH_SCAN_P2P(16); break;
+    default: LAUNCH_SCAN_P2P(32); break;
+  }
+#undef LAUNCH_SCAN_P2P
+  CU_TRY(h, cudaGetLastError());
+  h->stats.kernel_launches++;
+  h->stats.scan_launches++;
+  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  if (h->profile) {
+    float t = 0;
+    cudaEventElapsedTime(&t, h->ev[2], h->ev[3]);
+    h->stats.ms_scan += t;
+    std::vector<uint32_t> nv(QN);
+    cudaMemcpy(nv.data(), n_vec, (size_t)QN * 4, cudaMemcpyDeviceToHost);
+    uint64_t sum = 0;
+    for (uint32_t v : nv) sum += v;
+    h->stats.candidates += sum;
+  }
+  return PQT_OK;
+}
+
+int pqt_shard_rank(pqt_index* h, const uint32_t* n_vec_own, uint32_t q_own, uint32_t k, uint32_t* idx,
+                   float* dist, int out_on_device) {
+  if (!h || !n_vec_own || !idx || !dist || !q_own || !k) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (!h->x_val.p) return fail(h, PQT_ERR_STATE, "pqt_shard_exchange_alloc first");
+  if (q_own > h->x_q_per_rank) return fail(h, PQT_ERR_INVALID, "q_own exceeds the exchange buffers");
+  const uint32_t max_vec = h->x_max_vec;
+  if (!is_pow2(max_vec) || max_vec > 4096 || k > max_vec) return fail(h, PQT_ERR_INVALID, "bad candidate width / k");
+  float* d_out_dist = dist;
+  uint32_t* d_out_idx = idx;
+  if (!out_on_device) {
+    CU_TRY(h, h->s_outd.ensure((size_t)q_own * k * 4));
+    CU_TRY(h, h->s_outi.ensure((size_t)q_own * k * 4));
+    d_out_dist = h->s_outd.as<float>();
+    d_out_idx = h->s_outi.as<uint32_t>();
+  }
+  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
+  Rank2Args a{};
+  a.val = h->x_val.as<float>(); a.idx = h->x_idx.as<uint32_t>();
+  a.QN = q_own; a.max_vec = max_vec; a.k = k;
+  a.out_dist = d_out_dist; a.out_idx = d_out_idx;
+  a.exact_counter = h->d_exact.as<unsigned long long>();
+  a.n_vec = n_vec_own;
+  size_t smem = (size_t)max_vec * 10 + 16;
+  if (smem > 48 * 1024)
+    CU_TRY(h, cudaFuncSetAttribute(rank2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rank2_kernel<<<std::min<uint32_t>(q_own, (uint32_t)h->num_sms * 4), kRerankGroupThreads, smem, h->stream>>>(a);
+  CU_TRY(h, cudaGetLastError());
+  h->stats.kernel_launches++;
+  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+  if (!out_on_device) {
+    CU_TRY(h, cudaMemcpyAsync(idx, d_out_idx, (size_t)q_own * k * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(dist, d_out_dist, (size_t)q_own * k * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  if (h->profile) {
+    float t = 0;
+    cudaEventElapsedTime(&t, h->ev[4], h->ev[5]);
+    h->stats.ms_sort += t;
+  }
   return PQT_OK;
 }
 

@@ -155,6 +155,61 @@ __global__ void __launch_bounds__(128) tables_kernel(TablesArgs a) {
 }
 
 // ============================================================================
+// Step B alone (lineAssignmentKernel :7739-7799) for a range of queries: in the multi-GPU
+// path Steps A/C/D of a query run on one rank only, but every shard needs the query's LUT
+// to scan its own candidates; recomputing it (c1*LP short segment distances) is cheaper
+// than shipping it.  Same arithmetic and output layout as the Step-B part of the tables
+// kernels.  blockDim = 128, one CTA per query, cb1T = cb1 transposed [dim][c1].
+// ============================================================================
+__global__ void __launch_bounds__(128) lut_kernel(const float* Q, const float* cb1T, uint32_t q_begin,
+                                                  uint32_t q_end, uint32_t dim, uint32_t c1,
+                                                  uint32_t LP, uint32_t sl, float* lut_dup) {
+  extern __shared__ float smem_f[];
+  float* sq = smem_f;          // [dim]
+  float* s_lut = sq + dim;     // [c1*32]
+  const uint32_t R = 32 / LP;
+  for (uint32_t qi = q_begin + blockIdx.x; qi < q_end; qi += gridDim.x) {
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < dim; t += blockDim.x) sq[t] = Q[(size_t)qi * dim + t];
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < LP * c1; e += blockDim.x) {
+      const uint32_t lp = e / c1, c = e - lp * c1;  // c fastest: coalesced cb1T reads
+      float s[128];
+      const float* cb = cb1T + (size_t)(lp * sl) * c1 + c;
+      float v;
+      switch (sl) {
+#define PQTB_LUT_CASE(L)                                                         \
+  case L: {                                                                      \
+    _Pragma("unroll") for (int t = 0; t < L; t++) {                              \
+      float d = __fsub_rn(sq[lp * L + t], __ldg(cb + (size_t)t * c1));           \
+      s[t] = __fmul_rn(d, d);                                                    \
+    }                                                                            \
+    _Pragma("unroll") for (int stride = L / 2; stride > 0; stride >>= 1) {       \
+      _Pragma("unroll") for (int j = 0; j < stride; j++) s[j] = __fadd_rn(s[j], s[j + stride]); \
+    }                                                                            \
+    v = s[0];                                                                    \
+  } break;
+        PQTB_LUT_CASE(1)
+        PQTB_LUT_CASE(2)
+        PQTB_LUT_CASE(4)
+        PQTB_LUT_CASE(8)
+        PQTB_LUT_CASE(16)
+        PQTB_LUT_CASE(32)
+        PQTB_LUT_CASE(64)
+        default:
+          PQTB_LUT_CASE(128)
+#undef PQTB_LUT_CASE
+      }
+      for (uint32_t j = 0; j < R; j++) s_lut[c * 32 + j * LP + lp] = v;
+    }
+    __syncthreads();
+    float4* dst = reinterpret_cast<float4*>(lut_dup + (size_t)qi * c1 * 32);
+    const float4* src = reinterpret_cast<const float4*>(s_lut);
+    for (uint32_t e = threadIdx.x; e < c1 * 8; e += blockDim.x) dst[e] = src[e];
+  }
+}
+
+// ============================================================================
 // Bin directory: occupancy bitmap + rank.  Replaces probing the dense
 // binCounts[hash_size] (1.6 GB) by one 32-byte sector of a hash_size/8-byte
 // bitmap (50 MB, L2 resident), and the dense binPrefix by a compact array
@@ -353,6 +408,13 @@ struct ScanArgs {
   uint32_t sharded;         // 1: slots of other shards get (+inf, 0)
   float* out_val;           // [QN][max_vec]
   uint32_t* out_idx;        // [QN][max_vec]
+  // peer-store mode (multi-GPU, fused scan + all-to-all): results of this shard's candidates
+  // are stored straight into the candidate arrays of the rank that owns the query
+  // (peer memory over NVLink); nothing is written for other shards' candidates or pads.
+  uint32_t p2p;             // 1: use peer_val / peer_idx
+  uint32_t q_per_rank;      // queries [r*q_per_rank, (r+1)*q_per_rank) are ranked by rank r
+  float* peer_val[8];       // [world] each [q_per_rank][max_vec], mapped peer (or local) memory
+  uint32_t* peer_idx[8];
 };
 
 constexpr int kScanThreads = 1024;
@@ -413,10 +475,19 @@ __global__ void __launch_bounds__(kScanThreads, 1) adc_scan_kernel(ScanArgs a) {
 
     const uint32_t nv = min(__ldg(a.n_vec + qi), a.max_vec);
     const uint32_t* cand = a.cand_pos + (size_t)qi * a.max_vec;
-    float* oval = a.out_val + (size_t)qi * a.max_vec;
-    uint32_t* oidx = a.out_idx + (size_t)qi * a.max_vec;
+    float* oval;
+    uint32_t* oidx;
+    if (a.p2p) {
+      const uint32_t owner = qi / a.q_per_rank, ql = qi - owner * a.q_per_rank;
+      oval = a.peer_val[owner] + (size_t)ql * a.max_vec;
+      oidx = a.peer_idx[owner] + (size_t)ql * a.max_vec;
+    } else {
+      oval = a.out_val + (size_t)qi * a.max_vec;
+      oidx = a.out_idx + (size_t)qi * a.max_vec;
+    }
+    const uint32_t scan_end = a.p2p ? nv : a.max_vec;  // peer-store mode: real candidates only
 
-    for (uint32_t base = warp * 32; base < a.max_vec; base += nwarps * 32) {
+    for (uint32_t base = warp * 32; base < scan_end; base += nwarps * 32) {
       const uint32_t ca = base + lane;
       const bool valid = ca < nv;
       uint32_t pos = 0;
@@ -470,7 +541,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) adc_scan_kernel(ScanArgs a) {
         v = __int_as_float(0x7f800000);
         id = kNotMineIdx;
       }
-      if (ca < a.max_vec) {  // candidate widths below 32 leave the upper lanes idle
+      if (a.p2p) {
+        if (mine) {
+          oval[ca] = v;
+          oidx[ca] = id;
+        }
+      } else if (ca < a.max_vec) {  // candidate widths below 32 leave the upper lanes idle
         oval[ca] = v;
         oidx[ca] = id;
       }

@@ -694,6 +694,8 @@ struct Rank2Args {
   float* out_dist;
   uint32_t* out_idx;
   unsigned long long* exact_counter;
+  const uint32_t* n_vec;  // optional [QN]: number of real candidates; slots beyond are padding
+                          // and are NOT read (peer-store mode leaves them unwritten)
 };
 
 __global__ void __launch_bounds__(kRerankGroupThreads) rank2_kernel(Rank2Args a) {
@@ -708,19 +710,29 @@ __global__ void __launch_bounds__(kRerankGroupThreads) rank2_kernel(Rank2Args a)
     __syncthreads();
     if (threadIdx.x == 0) *s_nv = 0;
     __syncthreads();
-    // real candidates form a prefix: slots >= nVec hold (1e7, PAD)
-    uint32_t local = 0;
-    for (uint32_t e = threadIdx.x; e < a.max_vec; e += blockDim.x) {
-      const float v = a.val[(size_t)qi * a.max_vec + e];
-      const uint32_t id = a.idx[(size_t)qi * a.max_vec + e];
-      s_val[e] = v;
-      s_id[e] = id;
-      if (!(id == kPadIdx && v == kPadDist)) local = e + 1;
+    uint32_t nv;
+    if (a.n_vec) {
+      nv = min(a.n_vec[qi], a.max_vec);
+      for (uint32_t e = threadIdx.x; e < nv; e += blockDim.x) {
+        s_val[e] = a.val[(size_t)qi * a.max_vec + e];
+        s_id[e] = a.idx[(size_t)qi * a.max_vec + e];
+      }
+      __syncthreads();
+    } else {
+      // real candidates form a prefix: slots >= nVec hold (1e7, PAD)
+      uint32_t local = 0;
+      for (uint32_t e = threadIdx.x; e < a.max_vec; e += blockDim.x) {
+        const float v = a.val[(size_t)qi * a.max_vec + e];
+        const uint32_t id = a.idx[(size_t)qi * a.max_vec + e];
+        s_val[e] = v;
+        s_id[e] = id;
+        if (!(id == kPadIdx && v == kPadDist)) local = e + 1;
+      }
+      atomicMax(s_nv, local);
+      __syncthreads();
+      nv = *s_nv;
+      __syncthreads();
     }
-    atomicMax(s_nv, local);
-    __syncthreads();
-    const uint32_t nv = *s_nv;
-    __syncthreads();
     rank_and_emit(G, s_val, s_pay, s_id, s_flag, nv, a.max_vec, a.k, a.out_dist + (size_t)qi * a.k,
                   a.out_idx + (size_t)qi * a.k, a.exact_counter);
   }

@@ -21,7 +21,9 @@ EXPORTS = [
     "pqt_set_tree", "pqt_get_tree_shape", "pqt_get_tree", "pqt_set_db", "pqt_set_lines",
     "pqt_query_knn", "pqt_query_big_knn_rerank2", "pqt_build_kbest_db", "pqt_line_dist", "pqt_get_db", "pqt_get_lines",
     "pqt_get_db_size", "pqt_set_shard", "pqt_query_scan_shard", "pqt_rank_candidates",
-    "pqt_candidate_width", "pqt_profile_enable", "pqt_get_stats", "pqt_reset_stats",
+    "pqt_candidate_width", "pqt_shard_exchange_alloc", "pqt_shard_exchange_handle",
+    "pqt_shard_exchange_open", "pqt_shard_exchange_set_peers", "pqt_shard_exchange_ptrs",
+    "pqt_shard_candidates", "pqt_shard_scan_p2p", "pqt_shard_rank", "pqt_profile_enable", "pqt_get_stats", "pqt_reset_stats",
     "pqt_debug_enable", "pqt_debug_stage",
 ]
 
@@ -101,6 +103,16 @@ def lib():
                                            C.c_uint32, C.c_void_p, C.c_void_p]
         L.pqt_rank_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                           C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        L.pqt_shard_exchange_alloc.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        L.pqt_shard_exchange_handle.argtypes = [C.c_void_p, C.c_void_p]
+        L.pqt_shard_exchange_open.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.pqt_shard_exchange_set_peers.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.pqt_shard_exchange_ptrs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.pqt_shard_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32,
+                                           C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.pqt_shard_scan_p2p.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.pqt_shard_rank.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
+                                     C.c_void_p, C.c_int]
         L.pqt_candidate_width.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
         L.pqt_profile_enable.argtypes = [C.c_void_p, C.c_int]
         L.pqt_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
@@ -279,6 +291,44 @@ class PerturbationProTree:
         dp, _ = _ptr(out_dist)
         self._chk(self._L.pqt_rank_candidates(self._h, _ptr(val)[0], _ptr(idx)[0], QN, max_vec,
                                               k, ip, dp, idev))
+
+    # ---- multi-GPU: fused scan + exchange over peer memory (include/pqt_b200.h)
+    def shardExchangeAlloc(self, q_per_rank, max_vec):
+        self._chk(self._L.pqt_shard_exchange_alloc(self._h, q_per_rank, max_vec))
+
+    def shardExchangeHandle(self):
+        buf = C.create_string_buffer(128)
+        self._chk(self._L.pqt_shard_exchange_handle(self._h, buf))
+        return buf.raw
+
+    def shardExchangeOpen(self, handles):
+        """handles: list of 128-byte IPC handles, entry r from rank r"""
+        blob = b"".join(handles)
+        self._chk(self._L.pqt_shard_exchange_open(self._h, len(handles), blob))
+
+    def shardExchangePtrs(self):
+        v, i = C.c_void_p(), C.c_void_p()
+        self._chk(self._L.pqt_shard_exchange_ptrs(self._h, C.byref(v), C.byref(i)))
+        return v.value, i.value
+
+    def shardExchangeSetPeers(self, val_ptrs, idx_ptrs):
+        n = len(val_ptrs)
+        va = (C.c_void_p * n)(*val_ptrs)
+        ia = (C.c_void_p * n)(*idx_ptrs)
+        self._chk(self._L.pqt_shard_exchange_set_peers(self._h, n, va, ia))
+
+    def shardCandidates(self, Q, QN, k, q_lo, q_hi, cand_pos, n_vec):
+        qp, qdev = _ptr(Q)
+        self._chk(self._L.pqt_shard_candidates(self._h, qp, qdev, QN, k, q_lo, q_hi,
+                                               _ptr(cand_pos)[0], _ptr(n_vec)[0]))
+
+    def shardScanP2P(self, QN, k, cand_pos, n_vec):
+        self._chk(self._L.pqt_shard_scan_p2p(self._h, QN, k, _ptr(cand_pos)[0], _ptr(n_vec)[0]))
+
+    def shardRank(self, n_vec_own, q_own, k, out_idx, out_dist):
+        ip, idev = _ptr(out_idx)
+        dp, _ = _ptr(out_dist)
+        self._chk(self._L.pqt_shard_rank(self._h, _ptr(n_vec_own)[0], q_own, k, ip, dp, idev))
 
     # ---- measurement / introspection
     def profile(self, on=True):

@@ -254,6 +254,42 @@ def test_sharded_scan_assembles_the_single_gpu_result(case_small):
     t.close()
 
 
+def test_peer_store_shards_in_one_process(case_small):
+    """The fused scan + exchange path with three shard handles on one device: every shard
+    stores the distances of its own candidates straight into the owner's candidate arrays
+    (here: plain device pointers instead of IPC-mapped peer memory)."""
+    import torch
+    c = case_small
+    QN, k, world = 48, 256, 3
+    c = dict(c)
+    c["Q"] = case_small["Q"][:QN]
+    d0, i0 = oracle_query(c, k)
+    Qd = torch.from_numpy(c["Q"]).cuda()
+    ts = [make_gpu_index(c, shard=(r, world)) for r in range(world)]
+    mv = ts[0].candidateWidth(k)
+    per = QN // world
+    for t in ts:
+        t.shardExchangeAlloc(per, mv)
+    ptrs = [t.shardExchangePtrs() for t in ts]
+    for t in ts:
+        t.shardExchangeSetPeers([p[0] for p in ptrs], [p[1] for p in ptrs])
+    cand = torch.zeros((QN, mv), dtype=torch.int32, device="cuda")
+    nvec = torch.zeros((QN,), dtype=torch.int32, device="cuda")
+    for r, t in enumerate(ts):   # every rank fills the rows of its own queries (+ "all-gather")
+        t.shardCandidates(Qd, QN, k, r * per, (r + 1) * per, cand, nvec)
+    for t in ts:
+        t.shardScanP2P(QN, k, cand, nvec)
+    torch.cuda.synchronize()
+    for r, t in enumerate(ts):
+        oi = torch.zeros((per, k), dtype=torch.int32, device="cuda")
+        od = torch.zeros((per, k), dtype=torch.float32, device="cuda")
+        t.shardRank(nvec[r * per:(r + 1) * per].contiguous(), per, k, oi, od)
+        assert np.array_equal(oi.cpu().numpy().view(np.uint32), i0[r * per:(r + 1) * per])
+        assert np.array_equal(od.cpu().numpy(), d0[r * per:(r + 1) * per])
+    for t in ts:
+        t.close()
+
+
 # ---- a11: the 1-B variant queryBIGKNNRerank2 ---------------------------------------------
 
 def _big_check(c, hash_size, ks):
