@@ -1384,15 +1384,16 @@ int pqt_shard_scan_p2p(pqt_index* h, uint32_t QN, uint32_t k, const uint32_t* ca
     a.peer_val[r] = h->x_peer_val[r];
     a.peer_idx[r] = h->x_peer_idx[r];
   }
-  size_t smem = ((size_t)h->c1 * h->c1 * 32 + 2 * (size_t)h->c1 * 32) * 4 + 64;
-  if (smem > 220 * 1024) return fail(h, PQT_ERR_INVALID, "c1 = %u > 32 is not supported by the ADC scan yet", h->c1);
-  uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms);
+  size_t smem = ((size_t)h->c1 * h->c1 * 32 + kP2PGroups * 2 * (size_t)h->c1 * 32 +
+                 kP2PGroups * 2 * (size_t)max_vec) * 4 + 128;
+  if (smem > 227 * 1024) return fail(h, PQT_ERR_INVALID, "c1 = %u > 32 is not supported by the ADC scan yet", h->c1);
+  uint32_t grid = std::min<uint32_t>((QN + kP2PGroups - 1) / kP2PGroups, (uint32_t)h->num_sms);
   if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
 #define LAUNCH_SCAN_P2P(LPV)                                                                     \
   do {                                                                                           \
-    CU_TRY(h, cudaFuncSetAttribute(adc_scan_kernel<LPV>,                                         \
+    CU_TRY(h, cudaFuncSetAttribute(adc_scan_p2p_kernel<LPV>,                                     \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    adc_scan_kernel<LPV><<<grid, kScanThreads, smem, h->stream>>>(a);                            \
+    adc_scan_p2p_kernel<LPV><<<grid, kScanThreads, smem, h->stream>>>(a);                        \
   } while (0)
   switch (h->LP) {
     case 1: LAUNCH_SCAN_P2P(1); break;
@@ -1438,22 +1439,51 @@ int pqt_shard_rank(pqt_index* h, const uint32_t* n_vec_own, uint32_t q_own, uint
     d_out_idx = h->s_outi.as<uint32_t>();
   }
   if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
-  Rank2Args a{};
-  a.val = h->x_val.as<float>(); a.idx = h->x_idx.as<uint32_t>();
-  a.QN = q_own; a.max_vec = max_vec; a.k = k;
-  a.out_dist = d_out_dist; a.out_idx = d_out_idx;
-  a.exact_counter = h->d_exact.as<unsigned long long>();
-  a.n_vec = n_vec_own;
   size_t smem = (size_t)max_vec * 10 + 16;
   if (smem > 48 * 1024)
     CU_TRY(h, cudaFuncSetAttribute(rank2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  rank2_kernel<<<std::min<uint32_t>(q_own, (uint32_t)h->num_sms * 4), kRerankGroupThreads, smem, h->stream>>>(a);
-  CU_TRY(h, cudaGetLastError());
-  h->stats.kernel_launches++;
+  // host outputs: rank in slabs so that the device->host copy of one slab overlaps the
+  // ranking of the next (same scheme as pqt_query_knn)
+  const uint32_t slab = out_on_device ? q_own : std::min<uint32_t>(q_own, kSlabQueries);
+  const uint32_t nslabs = (q_own + slab - 1) / slab;
+  if (!out_on_device) {
+    while (h->slab_ev.size() < nslabs) {
+      cudaEvent_t e;
+      CU_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->slab_ev.push_back(e);
+    }
+  }
+  auto issue_copy = [&](uint32_t sidx) -> int {
+    const uint32_t q0 = sidx * slab, n = std::min(slab, q_own - q0);
+    CU_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->slab_ev[sidx], 0));
+    CU_TRY(h, cudaMemcpyAsync(idx + (size_t)q0 * k, d_out_idx + (size_t)q0 * k, (size_t)n * k * 4,
+                              cudaMemcpyDeviceToHost, h->copy_stream));
+    CU_TRY(h, cudaMemcpyAsync(dist + (size_t)q0 * k, d_out_dist + (size_t)q0 * k, (size_t)n * k * 4,
+                              cudaMemcpyDeviceToHost, h->copy_stream));
+    return PQT_OK;
+  };
+  for (uint32_t sidx = 0; sidx < nslabs; sidx++) {
+    const uint32_t q0 = sidx * slab, n = std::min(slab, q_own - q0);
+    Rank2Args a{};
+    a.val = h->x_val.as<float>() + (size_t)q0 * max_vec;
+    a.idx = h->x_idx.as<uint32_t>() + (size_t)q0 * max_vec;
+    a.QN = n; a.max_vec = max_vec; a.k = k;
+    a.out_dist = d_out_dist + (size_t)q0 * k;
+    a.out_idx = d_out_idx + (size_t)q0 * k;
+    a.exact_counter = h->d_exact.as<unsigned long long>();
+    a.n_vec = n_vec_own + q0;
+    rank2_kernel<<<std::min<uint32_t>(n, (uint32_t)h->num_sms * 4), kRerankGroupThreads, smem, h->stream>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    h->stats.kernel_launches++;
+    if (!out_on_device) {
+      CU_TRY(h, cudaEventRecord(h->slab_ev[sidx], h->stream));
+      if (sidx > 0) PQ_TRY(issue_copy(sidx - 1));
+    }
+  }
   if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
   if (!out_on_device) {
-    CU_TRY(h, cudaMemcpyAsync(idx, d_out_idx, (size_t)q_own * k * 4, cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(dist, d_out_dist, (size_t)q_own * k * 4, cudaMemcpyDeviceToHost, h->stream));
+    PQ_TRY(issue_copy(nslabs - 1));
+    CU_TRY(h, cudaStreamSynchronize(h->copy_stream));
   }
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   if (h->profile) {

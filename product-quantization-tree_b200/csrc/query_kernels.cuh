@@ -556,6 +556,154 @@ __global__ void __launch_bounds__(kScanThreads, 1) adc_scan_kernel(ScanArgs a) {
   }
 }
 
+// ============================================================================
+// Peer-store variant of the ADC scan (multi-GPU): per query the CTA first compacts the
+// candidates that live in THIS shard's slice into a dense list in shared memory, then
+// evaluates the list 32 candidates per warp step (same lane mapping and arithmetic as
+// above) and stores each result into the candidate arrays of the rank that owns the
+// query -- peer memory mapped over NVLink (or local memory for the own queries).  The
+// work of a shard is therefore proportional to its own candidates, and the all-to-all of
+// results happens inside the scan kernel's epilogue instead of in a separate collective.
+// ============================================================================
+constexpr int kP2PGroups = 2;  // thread groups per CTA, each walking its own queries
+constexpr int kP2PGroupThreads = kScanThreads / kP2PGroups;
+
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int LP>
+__global__ void __launch_bounds__(kScanThreads, 1) adc_scan_p2p_kernel(ScanArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t lut_floats = a.c1 * 32;
+  const uint32_t cbd_floats = a.c1 * a.c1 * 32;
+  const uint32_t grp = threadIdx.x / kP2PGroupThreads;
+  const uint32_t gt = threadIdx.x - grp * kP2PGroupThreads;  // thread inside the group
+  const uint32_t gbar_id = 1 + grp;
+  float* s_cbd = reinterpret_cast<float*>(smem_raw);
+  float* s_luts = s_cbd + cbd_floats;                                  // [groups][2][lut_floats]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_luts + kP2PGroups * 2 * lut_floats);
+  uint32_t* s_cnts = reinterpret_cast<uint32_t*>(bars + 2 * kP2PGroups + 2);
+  uint32_t* s_lists = s_cnts + 4;                                      // [groups][2][max_vec]
+  float* s_lut0 = s_luts + grp * 2 * lut_floats;
+  float* s_lut1 = s_lut0 + lut_floats;
+  uint64_t* gbar = bars + 2 * grp;
+  uint64_t* cbar = bars + 2 * kP2PGroups;
+  uint32_t* s_cnt = s_cnts + grp;
+  uint32_t* s_lpos = s_lists + (size_t)grp * 2 * a.max_vec;  // position inside this shard's slice
+  uint32_t* s_ca = s_lpos + a.max_vec;                       // candidate slot
+
+  const uint32_t lane = gt & 31, warp = gt >> 5, nwarps = kP2PGroupThreads >> 5;
+  const uint32_t lp = lane & (LP - 1);
+  const uint32_t grp_base = lane & ~(uint32_t)(LP - 1);
+  const uint32_t worker = blockIdx.x * kP2PGroups + grp;
+  const uint32_t nworkers = gridDim.x * kP2PGroups;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2 * kP2PGroups + 1; i++) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t cbd_bytes = cbd_floats * 4;
+    mbar_expect_tx(cbar, cbd_bytes);
+    for (uint32_t off = 0; off < cbd_bytes; off += 32768) {
+      uint32_t n = cbd_bytes - off < 32768 ? cbd_bytes - off : 32768;
+      tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_cbd) + off,
+                   reinterpret_cast<const unsigned char*>(a.cbd_dup) + off, n, cbar);
+    }
+  }
+  if (gt == 0 && worker < a.QN) {
+    mbar_expect_tx(&gbar[0], lut_floats * 4);
+    tma_bulk_g2s(s_lut0, a.lut_dup + (size_t)worker * lut_floats, lut_floats * 4, &gbar[0]);
+  }
+  mbar_wait(cbar, 0);
+
+  uint32_t buf = 0, phase0 = 0, phase1 = 0;
+  for (uint32_t qi = worker; qi < a.QN; qi += nworkers) {
+    const uint32_t qn = qi + nworkers;
+    if (gt == 0) {
+      *s_cnt = 0;
+      if (qn < a.QN) {
+        uint64_t* nb = &gbar[buf ^ 1];
+        mbar_expect_tx(nb, lut_floats * 4);
+        tma_bulk_g2s(buf ? s_lut0 : s_lut1, a.lut_dup + (size_t)qn * lut_floats, lut_floats * 4, nb);
+      }
+    }
+    named_bar_sync(gbar_id, kP2PGroupThreads);
+    const uint32_t nv = min(__ldg(a.n_vec + qi), a.max_vec);
+    const uint32_t* cand = a.cand_pos + (size_t)qi * a.max_vec;
+    // ---- phase 1: compact the candidates of this shard's slice
+    for (uint32_t base = warp * 32; base < nv; base += nwarps * 32) {
+      const uint32_t ca = base + lane;
+      uint32_t pos = 0;
+      bool mine = false;
+      if (ca < nv) {
+        pos = __ldg(cand + ca);
+        mine = (pos >= a.pos_lo) && (pos < a.pos_hi);
+      }
+      const uint32_t mask = __ballot_sync(0xffffffffu, mine);
+      if (mask) {
+        uint32_t off = 0;
+        if (lane == 0) off = atomicAdd(s_cnt, __popc(mask));
+        off = __shfl_sync(0xffffffffu, off, 0) + __popc(mask & ((1u << lane) - 1u));
+        if (mine) {
+          s_lpos[off] = pos - a.pos_lo;
+          s_ca[off] = ca;
+        }
+      }
+    }
+    named_bar_sync(gbar_id, kP2PGroupThreads);
+    const uint32_t M = *s_cnt;
+    const float* s_lut = buf ? s_lut1 : s_lut0;
+    mbar_wait(&gbar[buf], buf ? phase1 : phase0);
+    if (buf)
+      phase1 ^= 1;
+    else
+      phase0 ^= 1;
+    const uint32_t owner = qi / a.q_per_rank, ql = qi - owner * a.q_per_rank;
+    float* oval = a.peer_val[owner] + (size_t)ql * a.max_vec;
+    uint32_t* oidx = a.peer_idx[owner] + (size_t)ql * a.max_vec;
+    // ---- phase 2: dense chunks of 32 own candidates
+    for (uint32_t base = warp * 32; base < M; base += nwarps * 32) {
+      const uint32_t e = base + lane;
+      const bool valid = e < M;
+      const uint32_t lpos = valid ? s_lpos[e] : 0u;
+      const uint32_t ca = valid ? s_ca[e] : 0u;
+      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+      const uint32_t myid = valid ? __ldg(a.ids + lpos) : 0u;
+      uint32_t w[LP];
+#pragma unroll
+      for (int s = 0; s < LP; s++) {
+        const uint32_t src = grp_base + s;
+        const uint32_t cpos = __shfl_sync(0xffffffffu, lpos, src);
+        w[s] = ((vmask >> src) & 1u) ? __ldg(a.codes + (size_t)cpos * LP + lp) : 0u;
+      }
+      float myval = 0.f;
+#pragma unroll
+      for (int s = 0; s < LP; s++) {
+        const uint32_t p1 = w[s] & 0xFFu;
+        const uint32_t p2 = (w[s] >> 8) & 0xFFu;
+        const float lam = lambda_of(w[s]);
+        const float a2 = s_lut[p1 * 32 + lane];
+        const float b2 = s_lut[p2 * 32 + lane];
+        const float c2 = s_cbd[(p2 * a.c1 + p1) * 32 + lane];
+        float d = tri_dist(a2, b2, c2, lam);
+#pragma unroll
+        for (int st = LP >> 1; st > 0; st >>= 1)
+          d = __fadd_rn(d, __shfl_xor_sync(0xffffffffu, d, st));
+        if (lp == (uint32_t)s) myval = d;
+      }
+      if (valid) {
+        oval[ca] = myval;  // peer store (NVLink) when the query is ranked by another GPU
+        oidx[ca] = myid;
+      }
+    }
+    named_bar_sync(gbar_id, kP2PGroupThreads);  // list and LUT buffer are reused by the next query
+    buf ^= 1;
+  }
+}
+
 // Fallback for shapes whose cbd table does not fit in shared memory (c1 > 32):
 // same arithmetic, tables read through L1/L2 in their canonical layouts.
 struct ScanGenericArgs {
