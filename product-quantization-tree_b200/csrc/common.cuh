@@ -112,6 +112,54 @@ __device__ __forceinline__ uint32_t fastmod(uint32_t a, const FastMod& f) {
   return (uint32_t)__umul64hi(low, (uint64_t)f.d);
 }
 
+// ---- register / shuffle stages of the bitonic network ----------------------------------
+// A thread holds E consecutive elements (global indices base .. base+E-1, base = E * thread
+// index inside a 32-thread warp block).  Runs the compare-exchange distances jstart, jstart/2,
+// ..., 1 of merge size k: E <= j on shuffles, j < E in registers.  Same pairs, direction rule
+// and strict compares as pqt/bitonicSort.cuh:16-44.
+template <int E>
+__device__ __forceinline__ void sort_reg_stages(float (&v)[E], uint32_t (&p)[E], uint32_t base,
+                                                uint32_t lane, uint32_t k, uint32_t jstart) {
+  uint32_t j = jstart;
+  // ascending block for all elements of this thread once k >= E (base & k ignores r)
+  const bool desc_t = (base & k) != 0;
+  // distances inside a warp: shuffles.  The lane holding the lower index of a pair keeps
+  // the minimum when ascending; `nv != v` is exactly "the pair swaps" (ties keep their
+  // own bits and payload, like the network's strict compare).
+  for (; j >= (uint32_t)E; j >>= 1) {
+    const uint32_t lj = j / E;  // lane distance
+    const bool want_min = ((lane & lj) == 0) != desc_t;
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v[r], lj);
+      const uint32_t op = __shfl_xor_sync(0xffffffffu, p[r], lj);
+      const float nv = want_min ? fminf(v[r], ov) : fmaxf(v[r], ov);
+      const bool sw = nv != v[r];
+      v[r] = sw ? ov : v[r];
+      p[r] = sw ? op : p[r];
+    }
+  }
+  // distances inside a thread: registers
+#pragma unroll
+  for (int jj = E >> 1; jj > 0; jj >>= 1) {
+    if ((uint32_t)jj <= j) {
+#pragma unroll
+      for (int r = 0; r < E; r++) {
+        if ((r & jj) == 0) {
+          const bool desc = ((base + r) & k) != 0;
+          const float lo = v[r], hi = v[r + jj];
+          const uint32_t plo = p[r], phi = p[r + jj];
+          const bool sw = desc ? (lo < hi) : (lo > hi);
+          v[r] = sw ? hi : lo;
+          v[r + jj] = sw ? lo : hi;
+          p[r] = sw ? phi : plo;
+          p[r + jj] = sw ? plo : phi;
+        }
+      }
+    }
+  }
+}
+
 // ---- mbarrier / TMA bulk copy (cp.async.bulk, SASS: UBLKCP) ----------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);

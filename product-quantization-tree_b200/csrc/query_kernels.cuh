@@ -861,6 +861,28 @@ __device__ __forceinline__ void bitonic_warp_smem(float* val, uint32_t* idx, uin
   }
 }
 
+// whole network over n = 32 * E elements of a warp-private shared-memory array, run in
+// registers and shuffles (E consecutive elements per lane)
+template <int E>
+__device__ __forceinline__ void warp_sort_regs(float* sv, uint32_t* si, uint32_t lane) {
+  float v[E];
+  uint32_t p[E];
+  const uint32_t base = lane * E;
+#pragma unroll
+  for (int r = 0; r < E; r++) {
+    v[r] = sv[base + r];
+    p[r] = si[base + r];
+  }
+  for (uint32_t k = 2; k <= 32u * E; k <<= 1) sort_reg_stages<E>(v, p, base, lane, k, k >> 1);
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < E; r++) {
+    sv[base + r] = v[r];
+    si[base + r] = p[r];
+  }
+  __syncwarp();
+}
+
 template <int VL>
 __global__ void __launch_bounds__(kTablesWarps * 32) tables_warp_kernel(TablesWarpArgs w) {
   const TablesArgs& a = w.t;
@@ -970,7 +992,13 @@ __global__ void __launch_bounds__(kTablesWarps * 32) tables_warp_kernel(TablesWa
         }
       }
       __syncwarp();
-      bitonic_warp_smem(sv, si, a.npC, lane);
+      switch (a.npC) {  // :1639 bitonic3(shm, shmIdx, _NP2)
+        case 32: warp_sort_regs<1>(sv, si, lane); break;
+        case 64: warp_sort_regs<2>(sv, si, lane); break;
+        case 128: warp_sort_regs<4>(sv, si, lane); break;
+        case 256: warp_sort_regs<8>(sv, si, lane); break;
+        default: bitonic_warp_smem(sv, si, a.npC, lane); break;
+      }
       if (lane < 16) a.idx16[((size_t)qi * a.p + part) * 16 + lane] = (lane < a.m) ? si[lane] : 0u;
       if (a.top_val) {
         for (uint32_t e = lane; e < a.top_n; e += 32) {

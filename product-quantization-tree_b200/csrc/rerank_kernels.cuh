@@ -349,49 +349,6 @@ __device__ __forceinline__ void bitonic_smem_grp(const Grp& g, float* val, uint1
 // Every thread of the group must call.
 // ============================================================================
 template <int E>
-__device__ __forceinline__ void sort_reg_stages(float (&v)[E], uint32_t (&p)[E], uint32_t base,
-                                                uint32_t lane, uint32_t k, uint32_t jstart) {
-  uint32_t j = jstart;
-  // ascending block for all elements of this thread once k >= E (base & k ignores r)
-  const bool desc_t = (base & k) != 0;
-  // distances inside a warp: shuffles.  The lane holding the lower index of a pair keeps
-  // the minimum when ascending; `nv != v` is exactly "the pair swaps" (ties keep their
-  // own bits and payload, like the network's strict compare).
-  for (; j >= (uint32_t)E; j >>= 1) {
-    const uint32_t lj = j / E;  // lane distance
-    const bool want_min = ((lane & lj) == 0) != desc_t;
-#pragma unroll
-    for (int r = 0; r < E; r++) {
-      const float ov = __shfl_xor_sync(0xffffffffu, v[r], lj);
-      const uint32_t op = __shfl_xor_sync(0xffffffffu, p[r], lj);
-      const float nv = want_min ? fminf(v[r], ov) : fmaxf(v[r], ov);
-      const bool sw = nv != v[r];
-      v[r] = sw ? ov : v[r];
-      p[r] = sw ? op : p[r];
-    }
-  }
-  // distances inside a thread: registers
-#pragma unroll
-  for (int jj = E >> 1; jj > 0; jj >>= 1) {
-    if ((uint32_t)jj <= j) {
-#pragma unroll
-      for (int r = 0; r < E; r++) {
-        if ((r & jj) == 0) {
-          const bool desc = ((base + r) & k) != 0;
-          const float lo = v[r], hi = v[r + jj];
-          const uint32_t plo = p[r], phi = p[r + jj];
-          const bool sw = desc ? (lo < hi) : (lo > hi);
-          v[r] = sw ? hi : lo;
-          v[r + jj] = sw ? lo : hi;
-          p[r] = sw ? phi : plo;
-          p[r + jj] = sw ? plo : phi;
-        }
-      }
-    }
-  }
-}
-
-template <int E>
 __device__ __forceinline__ void grp_sort_pairs(const Grp& g, float* sv, uint16_t* sp, uint32_t n2) {
   const uint32_t t = g.t, lane = t & 31;
   const uint32_t per = E * g.n;  // elements one pass of the group covers
