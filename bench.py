@@ -349,8 +349,15 @@ def run_b200(a, rank, world, local_rank):
     if sharded:
         cand_per_launch /= world  # each rank scans its slice of the candidates
     achieved = cand_per_launch * bytes_per_cand / (scan_ms * 1e-3) / 1e9
+    traffic = None
+    try:  # DRAM bytes per launch from the committed ncu --set full capture of this workload
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if not sharded:
+            traffic = tj["rerank_kernel"].get(str(a.n), {}).get("bytes")
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": traffic,
                 "kernel": "adc_scan_kernel" if sharded else "rerank_kernel (ADC scan + ranking fused)",
                 "peak_source": peak_src,
                 "ms_per_launch": scan_ms, "candidates_per_launch": cand_per_launch,

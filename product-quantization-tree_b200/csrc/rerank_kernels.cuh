@@ -207,7 +207,7 @@ constexpr int kBins3Batch = kBins2Threads * kProbesPerThread;  // 4096
 
 // dynamic smem: list[max_bins] | binbuf[4096] | pairs[2][256] | bits[128] | warp_sums[32]
 template <int NPAIRS>
-__global__ void __launch_bounds__(kBins2Threads) bins3_kernel(Bins3Args a) {
+__global__ void __launch_bounds__(kBins2Threads, 6) bins3_kernel(Bins3Args a) {
   extern __shared__ uint32_t smem_u[];
   uint32_t* list = smem_u;
   uint32_t* binbuf = list + a.max_bins;
@@ -239,23 +239,31 @@ __global__ void __launch_bounds__(kBins2Threads) bins3_kernel(Bins3Args a) {
     for (uint32_t b0 = 0; b0 < n_probes && n_out < max_bins; b0 += kBins3Batch) {
       if (threadIdx.x < kBins3Batch / 32) bits[threadIdx.x] = 0;
       __syncthreads();
-      uint32_t bins[kProbesPerThread], words[kProbesPerThread], us[kProbesPerThread];
+      // only the loaded bitmap words (and the bit position inside them, 5 bits each) stay in
+      // registers while the 16 probes are in flight; bins of the few kept probes are
+      // recomputed -- keeps the kernel at 6 CTAs per SM
+      uint32_t words[kProbesPerThread];
+      uint32_t sh[kProbesPerThread / 4];
+#pragma unroll
+      for (int r = 0; r < kProbesPerThread / 4; r++) sh[r] = 0;
 #pragma unroll
       for (int r = 0; r < kProbesPerThread; r++) {
         const uint32_t ent = __ldg(a.seq_sorted + b0 + r * kBins2Threads + threadIdx.x);
-        const uint32_t u = ent >> 16;
         uint32_t o = pairs[ent & 0xFF];
         if (NPAIRS == 2) o = o * mul1 + pairs[256 + ((ent >> 8) & 0xFF)];
         const uint32_t bin = magicmod(o, hash);
-        us[r] = u;
-        bins[r] = bin;
-        words[r] = (b0 + u < n_probes) ? __ldg(bitmap + (bin >> 5)) : 0u;
+        sh[r >> 2] |= (bin & 31u) << (8 * (r & 3));
+        words[r] = (b0 + (ent >> 16) < n_probes) ? __ldg(bitmap + (bin >> 5)) : 0u;
       }
 #pragma unroll
       for (int r = 0; r < kProbesPerThread; r++) {
-        if ((words[r] >> (bins[r] & 31)) & 1u) {
-          atomicOr(&bits[us[r] >> 5], 1u << (us[r] & 31));
-          binbuf[us[r]] = bins[r];
+        if ((words[r] >> ((sh[r >> 2] >> (8 * (r & 3))) & 31u)) & 1u) {
+          const uint32_t ent = __ldg(a.seq_sorted + b0 + r * kBins2Threads + threadIdx.x);
+          const uint32_t u = ent >> 16;
+          uint32_t o = pairs[ent & 0xFF];
+          if (NPAIRS == 2) o = o * mul1 + pairs[256 + ((ent >> 8) & 0xFF)];
+          atomicOr(&bits[u >> 5], 1u << (u & 31));
+          binbuf[u] = magicmod(o, hash);
         }
       }
       __syncthreads();
