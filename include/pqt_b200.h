@@ -66,7 +66,11 @@ typedef struct pqt_params {
   uint32_t big_k1;          /* 16 (:8604)                                                 */
   uint32_t big_max_bins;    /* 64 * 8192 (:8639)                                          */
   uint32_t big_max_trials;  /* 2560 rounds of 1024 merged bins (:3727)                    */
-  uint32_t reserved[5];
+  uint32_t rank_mode;       /* 0 (default): composite-key sort, groups of bit-equal distances
+                               of different vectors re-ordered as the reference's network
+                               orders them (same output as 1, faster); 1: the reference's
+                               bitonic network on every query (pqt/bitonicSort.cuh:16-78)  */
+  uint32_t reserved[4];
 } pqt_params;
 
 /* cumulative device-side timings of the query kernels (CUDA events on the
@@ -236,7 +240,10 @@ typedef enum pqt_stage {
   PQT_STAGE_DIST_SEQ = 9,   /* uint32 [65536]            prepareDistSequence pqt/ProTree.cu:128-207 */
   PQT_STAGE_DIST_SEQ_2D = 10, /* uint32 [10][65536]      prepare2DDistSequence pqt/ProTree.cu:50-126 */
   PQT_STAGE_BIG_BINS = 11,  /* uint32 [QN][candidate width] bins listed by getBIGBins2D (last BIG query) */
-  PQT_STAGE_BIG_NBINS = 12  /* uint32 [QN] */
+  PQT_STAGE_BIG_NBINS = 12, /* uint32 [QN] */
+  PQT_STAGE_RERANK_PHASES = 13 /* uint64 [QN][8] clock64 stamps of the fused scan+rank kernel per
+                                  query: start, LUT ready, scan done, sort done, emit pass 1,
+                                  fast path done, query done, (SM << 32 | nVec << 1 | fast) */
 } pqt_stage;
 int pqt_debug_enable(pqt_index *h, int on);
 int pqt_debug_stage(const pqt_index *h, int stage, void *host_out, size_t bytes);

@@ -160,6 +160,17 @@ __device__ __forceinline__ void sort_reg_stages(float (&v)[E], uint32_t (&p)[E],
   }
 }
 
+// ---- thread group: a contiguous set of warps of a CTA that works on one query and
+// synchronises on its own named barrier (bar.sync id, n)
+struct Grp {
+  uint32_t t;    // thread index inside the group
+  uint32_t n;    // threads in the group (multiple of 32)
+  uint32_t bar;  // hardware barrier id (0 = the CTA-wide barrier of __syncthreads)
+  __device__ __forceinline__ void sync() const {
+    asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(n) : "memory");
+  }
+};
+
 // ---- mbarrier / TMA bulk copy (cp.async.bulk, SASS: UBLKCP) ----------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);

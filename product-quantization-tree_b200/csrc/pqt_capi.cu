@@ -72,7 +72,7 @@ struct pqt_index {
   DevBuf d_seq2d;  // prepare2DDistSequence(512): [10][65536]
   std::vector<uint32_t> h_seq2d;
   DevBuf s_topv, s_topi;  // [QN][p][64] best Step-C entries (1-B variant)
-  DevBuf g_bigbins, g_bignbins;
+  DevBuf g_bigbins, g_bignbins, g_phases;
   uint32_t dbg_big_QN = 0, dbg_big_cap = 0;
   DevBuf d_seqsorted;  // per 4096-batch, sorted by the ranks of all parts but the last (bins3)
   std::vector<uint32_t> h_distseq;
@@ -105,6 +105,7 @@ struct pqt_index {
   float* x_peer_val[8] = {nullptr};
   uint32_t* x_peer_idx[8] = {nullptr};
   bool x_ipc_opened[8] = {false};
+  DevBuf d_sched;  // one uint32: work counter of the fused scan+rank kernel
   DevBuf d_exact;  // one uint64: queries ranked by the exact-network fallback
 
   // profiling
@@ -543,7 +544,7 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
     size_t smem = ((size_t)h->c1 * h->c1 * 32 + 2 * (size_t)h->c1 * 32) * 4 + 64;
     // cbd + per group (2 LUT buffers + 3 candidate arrays) + barriers/flags
     const size_t smem_fused = ((size_t)h->c1 * h->c1 * 32 + kRerankGroups * 2 * (size_t)h->c1 * 32 +
-                               0) * 4 + kRerankGroups * (((size_t)10 * max_vec + 15) & ~(size_t)15) + 128;
+                               0) * 4 + kRerankGroups * ((size_t)8 * max_vec + 512) + 128;
     if (fused_out_dist && smem_fused <= 227 * 1024) {
       RerankArgs g{};
       g.s = a;
@@ -551,6 +552,14 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
       g.out_dist = fused_out_dist;
       g.out_idx = fused_out_idx;
       g.exact_counter = h->d_exact.as<unsigned long long>();
+      g.fast_rank = (P.rank_mode == 0) ? 1u : 0u;
+      CU_TRY(h, h->d_sched.ensure(4));
+      CU_TRY(h, cudaMemsetAsync(h->d_sched.p, 0, 4, h->stream));
+      g.next_query = h->d_sched.as<uint32_t>();
+      if (h->debug) {
+        CU_TRY(h, h->g_phases.ensure((size_t)QN * 8 * 8));
+        g.phase_dbg = h->g_phases.as<unsigned long long>();
+      }
       uint32_t grid = std::min<uint32_t>((QN + kRerankGroups - 1) / kRerankGroups, (uint32_t)h->num_sms);
 #define LAUNCH_RERANK(LPV)                                                                       \
   do {                                                                                           \
@@ -759,6 +768,7 @@ int pqt_set_params(pqt_index* h, const pqt_params* prm) {
       !prm->k1_build)
     return fail(h, PQT_ERR_INVALID, "zero parameter");
   if (prm->max_vec && !is_pow2(prm->max_vec)) return fail(h, PQT_ERR_INVALID, "max_vec must be a power of two");
+  if (prm->rank_mode > 1) return fail(h, PQT_ERR_INVALID, "rank_mode must be 0 or 1");
   h->prm = *prm;
   return PQT_OK;
 }
@@ -1584,6 +1594,9 @@ int pqt_debug_stage(const pqt_index* hc, int stage, void* host_out, size_t bytes
       return PQT_OK;
     case PQT_STAGE_BIG_BINS: src = h->g_bigbins.p; need = (size_t)h->dbg_big_QN * h->dbg_big_cap * 4; break;
     case PQT_STAGE_BIG_NBINS: src = h->g_bignbins.p; need = (size_t)h->dbg_big_QN * 4; break;
+    case PQT_STAGE_RERANK_PHASES:
+      if (!h->debug || !QN || !h->g_phases.p) return fail(h, PQT_ERR_STATE, "debug recording is off or no query has run");
+      src = h->g_phases.p; need = (size_t)QN * 64; break;
     default: return fail(h, PQT_ERR_INVALID, "unknown stage %d", stage);
   }
   if ((stage == PQT_STAGE_BIG_BINS || stage == PQT_STAGE_BIG_NBINS) && (!h->debug || !h->dbg_big_QN))

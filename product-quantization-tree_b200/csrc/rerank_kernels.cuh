@@ -19,6 +19,7 @@
 #pragma once
 #include "common.cuh"
 #include "query_kernels.cuh"
+#include "fast_rank.cuh"
 
 namespace pqtb {
 
@@ -317,15 +318,6 @@ __global__ void __launch_bounds__(kBins2Threads, 6) bins3_kernel(Bins3Args a) {
 // ============================================================================
 constexpr uint32_t kPayPad = 0xFFFFu;  // payload of a padded sort slot (candidate positions < 4096)
 
-struct Grp {
-  uint32_t t;    // thread index inside the group
-  uint32_t n;    // threads in the group (multiple of 32)
-  uint32_t bar;  // hardware barrier id (0 = the CTA-wide barrier of __syncthreads)
-  __device__ __forceinline__ void sync() const {
-    asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(n) : "memory");
-  }
-};
-
 // the reference's network (pqt/bitonicSort.cuh:16-78) over n elements, run by a group
 __device__ __forceinline__ void bitonic_smem_grp(const Grp& g, float* val, uint16_t* idx, uint32_t n) {
   const uint32_t half = n >> 1;
@@ -439,8 +431,9 @@ __device__ __forceinline__ void grp_sort_dispatch(const Grp& g, float* sv, uint1
 // order INCLUDING ties.  Sparse candidate lists are first sorted at pow2ceil(nVec) width
 // (pads +inf); that shortcut is valid unless a distance is >= 1e7 or two different ids tie,
 // in which case the candidate order is restored and the full-width network runs.
+template <class IdOf>
 __device__ __forceinline__ void rank_and_emit(const Grp& g, float* s_val, uint16_t* s_pay,
-                                              const uint32_t* s_id, uint32_t* s_flag, uint32_t nv,
+                                              IdOf id_of, uint32_t* s_flag, uint32_t nv,
                                               uint32_t max_vec, uint32_t k, float* out_dist,
                                               uint32_t* out_idx, unsigned long long* exact_counter) {
   const uint32_t t = g.t;
@@ -471,7 +464,7 @@ __device__ __forceinline__ void rank_and_emit(const Grp& g, float* s_val, uint16
     // than once: the uint32 Horner hash keeps only idx_0 mod 4 of the first part); ties
     // between different ids expose the network's order
     for (uint32_t e = t + 1; e < nv; e += g.n)
-      if (s_val[e] == s_val[e - 1] && s_id[s_pay[e]] != s_id[s_pay[e - 1]]) atomicOr(s_flag, 1u);
+      if (s_val[e] == s_val[e - 1] && id_of(s_pay[e]) != id_of(s_pay[e - 1])) atomicOr(s_flag, 1u);
   }
   g.sync();
   const uint32_t flag = *s_flag;
@@ -503,19 +496,19 @@ __device__ __forceinline__ void rank_and_emit(const Grp& g, float* s_val, uint16
     for (uint32_t e = t; e < k; e += g.n) {
       const uint32_t a = s_pay[e];
       out_dist[e] = s_val[e];
-      out_idx[e] = (a == kPayPad) ? kPadIdx : s_id[a];
+      out_idx[e] = (a == kPayPad) ? kPadIdx : id_of(a);
     }
   } else if (full) {
     for (uint32_t e = t; e < k; e += g.n) {
       const uint32_t a = s_pay[e];
       out_dist[e] = s_val[e];
-      out_idx[e] = (a == kPayPad) ? kPadIdx : s_id[a];
+      out_idx[e] = (a == kPayPad) ? kPadIdx : id_of(a);
     }
   } else {
     for (uint32_t e = t; e < k; e += g.n) {
       if (e < nv) {
         out_dist[e] = s_val[e];
-        out_idx[e] = s_id[s_pay[e]];
+        out_idx[e] = id_of(s_pay[e]);
       } else {
         out_dist[e] = kPadDist;
         out_idx[e] = kPadIdx;
@@ -537,6 +530,11 @@ struct RerankArgs {
   float* out_dist;    // [QN][k]
   uint32_t* out_idx;  // [QN][k]
   unsigned long long* exact_counter;  // queries ranked by the exact network (may be null)
+  uint32_t fast_rank;                 // 1: composite-key sort first (fast_rank.cuh); 0: network only
+  unsigned long long* phase_dbg;      // optional [QN][8] clock64 stamps per query (debug)
+  uint32_t* next_query;               // work counter (zeroed before the launch): the thread groups
+                                      // draw queries from it, so a slow query does not hold up a
+                                      // statically assigned tail
 };
 
 constexpr int kRerankGroups = 2;
@@ -555,16 +553,25 @@ __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
   float* s_luts = s_cbd + cbd_floats;                                  // [groups][2][lut_floats]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_luts + kRerankGroups * 2 * lut_floats);  // [groups][2] + cbd
   uint32_t* s_flags = reinterpret_cast<uint32_t*>(bars + 2 * kRerankGroups + 2);
-  float* s_arr = reinterpret_cast<float*>(s_flags + 4);                // [groups][3][max_vec]
+  uint32_t* s_red = s_flags + 4;                                       // [groups][4]: umin, umax, bad
+  uint32_t* s_fixes = s_red + 4 * kRerankGroups;                       // [groups][128]: emit bitmap
+  float* s_arr = reinterpret_cast<float*>(s_fixes + 128 * kRerankGroups);  // [groups][2][max_vec]
   float* s_lut0 = s_luts + grp * 2 * lut_floats;
   float* s_lut1 = s_lut0 + lut_floats;
   uint64_t* gbar = bars + 2 * grp;
   uint64_t* cbar = bars + 2 * kRerankGroups;
   uint32_t* s_flag = s_flags + grp;
-  // per group: val f32[max_vec] | id u32[max_vec] | pay u16[max_vec]  (= 2.5 words/slot)
-  float* s_val = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_arr) + (size_t)grp * (((size_t)10 * a.max_vec + 15) & ~(size_t)15));
-  uint32_t* s_id = reinterpret_cast<uint32_t*>(s_val + a.max_vec);
-  uint16_t* s_pay = reinterpret_cast<uint16_t*>(s_id + a.max_vec);
+  uint32_t* s_min = s_red + 4 * grp;
+  uint32_t* s_max = s_min + 1;
+  uint32_t* s_bad = s_min + 2;
+  uint32_t* s_fix = s_fixes + 128 * grp;
+  uint32_t* s_q = s_min + 3;  // next query of this group
+  // per group: val f32[max_vec] | scratch u32[max_vec] (composite sort words; the (u16) payload
+  // array of the exact network aliases it).  Vector ids are not staged: they are read once,
+  // when a result is emitted.
+  float* s_val = s_arr + (size_t)grp * 2 * a.max_vec;
+  uint32_t* s_cmp = reinterpret_cast<uint32_t*>(s_val + a.max_vec);
+  uint16_t* s_pay = reinterpret_cast<uint16_t*>(s_cmp);
 
   const uint32_t lane = G.t & 31, warp = G.t >> 5, nwarps = G.n >> 5;
   const uint32_t lp = lane & (LP - 1);
@@ -586,21 +593,38 @@ __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
                    reinterpret_cast<const unsigned char*>(a.cbd_dup) + off, n, cbar);
     }
   }
-  if (G.t == 0 && worker < a.QN) {
-    mbar_expect_tx(&gbar[0], lut_floats * 4);
-    tma_bulk_g2s(s_lut0, a.lut_dup + (size_t)worker * lut_floats, lut_floats * 4, &gbar[0]);
+  // first query of this group
+  if (G.t == 0) {
+    const uint32_t q0 = atomicAdd(g.next_query, 1u);
+    *s_q = q0;
+    if (q0 < a.QN) {
+      mbar_expect_tx(&gbar[0], lut_floats * 4);
+      tma_bulk_g2s(s_lut0, a.lut_dup + (size_t)q0 * lut_floats, lut_floats * 4, &gbar[0]);
+    }
   }
   mbar_wait(cbar, 0);
+  G.sync();
+  uint32_t qi = *s_q;
 
   uint32_t buf = 0, phase0 = 0, phase1 = 0;
-  for (uint32_t qi = worker; qi < a.QN; qi += nworkers) {
-    const uint32_t qn = qi + nworkers;
-    if (G.t == 0 && qn < a.QN) {
-      uint64_t* nb = &gbar[buf ^ 1];
-      mbar_expect_tx(nb, lut_floats * 4);
-      tma_bulk_g2s(buf ? s_lut0 : s_lut1, a.lut_dup + (size_t)qn * lut_floats, lut_floats * 4, nb);
+  while (qi < a.QN) {
+    G.sync();  // everyone has read *s_q
+    if (G.t == 0) {
+      // draw the next query and start the copy of its LUT into the other buffer
+      const uint32_t qn = atomicAdd(g.next_query, 1u);
+      *s_q = qn;
+      if (qn < a.QN) {
+        uint64_t* nb = &gbar[buf ^ 1];
+        mbar_expect_tx(nb, lut_floats * 4);
+        tma_bulk_g2s(buf ? s_lut0 : s_lut1, a.lut_dup + (size_t)qn * lut_floats, lut_floats * 4, nb);
+      }
+      *s_min = 0xFFFFFFFFu;
+      *s_max = 0u;
+      *s_bad = 0u;
     }
     const float* s_lut = buf ? s_lut1 : s_lut0;
+    unsigned long long* ph = g.phase_dbg ? g.phase_dbg + (size_t)qi * 8 : nullptr;
+    if (ph && G.t == 0) ph[0] = clock64();
     mbar_wait(&gbar[buf], buf ? phase1 : phase0);
     if (buf)
       phase1 ^= 1;
@@ -609,44 +633,97 @@ __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
 
     const uint32_t nv = min(__ldg(a.n_vec + qi), a.max_vec);
     const uint32_t* cand = a.cand_pos + (size_t)qi * a.max_vec;
-
+    if (ph && G.t == 0) ph[1] = clock64();
+    G.sync();
+    const uint32_t q_next = *s_q;
     // ---- scan: only chunks that hold real candidates
+    uint32_t umin = 0xFFFFFFFFu, umax = 0u, bad = 0u;
+    uint32_t pos_next = (warp * 32 + lane < nv) ? __ldg(cand + warp * 32 + lane) : 0u;
     for (uint32_t base = warp * 32; base < nv; base += nwarps * 32) {
       const uint32_t ca = base + lane;
       const bool valid = ca < nv;
-      const uint32_t pos = valid ? __ldg(cand + ca) : 0u;
-      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-      const uint32_t myid = valid ? __ldg(a.ids + pos) : 0u;
-      uint32_t w[LP];
-#pragma unroll
-      for (int s = 0; s < LP; s++) {
-        const uint32_t src = grp_base + s;
-        const uint32_t cpos = __shfl_sync(0xffffffffu, pos, src);
-        w[s] = ((vmask >> src) & 1u) ? __ldg(a.codes + (size_t)cpos * LP + lp) : 0u;
+      const uint32_t pos = pos_next;  // 0 for lanes past the end: a valid code row, result unused
+      {
+        const uint32_t cn = ca + nwarps * 32;
+        pos_next = cn < nv ? __ldg(cand + cn) : 0u;
       }
-      float myval = 0.f;
+      float d[LP];
+      {
+        uint32_t w[LP];
 #pragma unroll
-      for (int s = 0; s < LP; s++) {
-        const uint32_t p1 = w[s] & 0xFFu;
-        const uint32_t p2 = (w[s] >> 8) & 0xFFu;
-        const float lam = lambda_of(w[s]);
-        const float a2 = s_lut[p1 * 32 + lane];
-        const float b2 = s_lut[p2 * 32 + lane];
-        const float c2 = s_cbd[(p2 * a.c1 + p1) * 32 + lane];
-        float d = tri_dist(a2, b2, c2, lam);
+        for (int s = 0; s < LP; s++) {
+          const uint32_t cpos = __shfl_sync(0xffffffffu, pos, grp_base + s);
+          w[s] = __ldg(a.codes + (size_t)cpos * LP + lp);
+        }
 #pragma unroll
-        for (int st = LP >> 1; st > 0; st >>= 1)
-          d = __fadd_rn(d, __shfl_xor_sync(0xffffffffu, d, st));
-        if (lp == (uint32_t)s) myval = d;
+        for (int s = 0; s < LP; s++) {
+          const uint32_t p1 = w[s] & 0xFFu;
+          const uint32_t p2 = (w[s] >> 8) & 0xFFu;
+          const float lam = lambda_of(w[s]);
+          const float a2 = s_lut[p1 * 32 + lane];
+          const float b2 = s_lut[p2 * 32 + lane];
+          const float c2 = s_cbd[(p2 * a.c1 + p1) * 32 + lane];
+          d[s] = tri_dist(a2, b2, c2, lam);
+        }
       }
+      // Sum over the LP lanes of a candidate with the reference's pairwise tree
+      // (warpReduceSum, :5183-5187: v += shfl_down(v, st), st = LP/2 .. 1), for all LP
+      // candidates of the lane group at once: at distance st a lane keeps the half of its
+      // partial sums whose candidate index has bit st equal to its own lane bit and hands
+      // the other half to its partner, so every step adds exactly the two operands the
+      // reference adds (fp32 addition is commutative) and lane lp ends with candidate lp.
+#pragma unroll
+      for (int st = LP >> 1; st > 0; st >>= 1) {
+        const bool up = (lp & (uint32_t)st) != 0u;
+#pragma unroll
+        for (int s = 0; s < st; s++) {
+          const float send = up ? d[s] : d[s + st];
+          const float keep = up ? d[s + st] : d[s];
+          d[s] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, st));
+        }
+      }
+      const float myval = d[0];
       if (valid) {
         s_val[ca] = myval;
-        s_id[ca] = myid;
+        const uint32_t u = sortable_key(myval);
+        umin = min(umin, u);
+        umax = max(umax, u);
+        // the fast path needs finite distances below the pad value
+        if (!(myval < kPadDist) || !(myval > -__int_as_float(0x7f800000))) bad = 1u;
       }
     }
+    umin = __reduce_min_sync(0xffffffffu, umin);
+    umax = __reduce_max_sync(0xffffffffu, umax);
+    bad = __any_sync(0xffffffffu, bad) ? 1u : 0u;
+    if (lane == 0 && nv > 0) {
+      atomicMin(s_min, umin);
+      atomicMax(s_max, umax);
+      if (bad) atomicOr(s_bad, 1u);
+    }
     G.sync();
-    rank_and_emit(G, s_val, s_pay, s_id, s_flag, nv, a.max_vec, g.k, g.out_dist + (size_t)qi * g.k,
-                  g.out_idx + (size_t)qi * g.k, g.exact_counter);
+    if (ph && G.t == 0) {
+      ph[2] = clock64();
+      ph[3] = ph[4] = ph[5] = 0;
+    }
+    float* od = g.out_dist + (size_t)qi * g.k;
+    uint32_t* oi = g.out_idx + (size_t)qi * g.k;
+    auto id_of = [&](uint32_t slot) { return __ldg(a.ids + __ldg(cand + slot)); };
+    const uint32_t n2 = nv ? pow2ceil(nv) : 0u;
+    bool done = false;
+    if (g.fast_rank && n2 >= kFastMinN2 && *s_bad == 0u) {
+      FastRankState st{*s_min, *s_max};
+      const uint32_t f = fast_rank_emit(G, 3 + grp, s_val, s_cmp, s_fix, s_flag, nv, n2, g.k, st,
+                                                od, oi, cand, a.ids, ph);
+      done = (f == 0u);
+      if (ph && G.t == 0) ph[5] = clock64();
+    }
+    if (!done)
+      rank_and_emit(G, s_val, s_pay, id_of, s_flag, nv, a.max_vec, g.k, od, oi, g.exact_counter);
+    if (ph && G.t == 0) {
+      ph[6] = clock64();
+      ph[7] = ((unsigned long long)blockIdx.x << 32) | (nv << 1) | (done ? 1u : 0u);
+    }
+    qi = q_next;
     buf ^= 1;
   }
 }
@@ -698,7 +775,8 @@ __global__ void __launch_bounds__(kRerankGroupThreads) rank2_kernel(Rank2Args a)
       nv = *s_nv;
       __syncthreads();
     }
-    rank_and_emit(G, s_val, s_pay, s_id, s_flag, nv, a.max_vec, a.k, a.out_dist + (size_t)qi * a.k,
+    auto id_of = [&](uint32_t slot) { return s_id[slot]; };
+    rank_and_emit(G, s_val, s_pay, id_of, s_flag, nv, a.max_vec, a.k, a.out_dist + (size_t)qi * a.k,
                   a.out_idx + (size_t)qi * a.k, a.exact_counter);
   }
 }

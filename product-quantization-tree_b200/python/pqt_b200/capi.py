@@ -28,14 +28,14 @@ EXPORTS = [
 ]
 
 STAGES = dict(assign=0, lut=1, assign_val=2, assign_idx=3, bins=4, n_bins=5, select_idx=6,
-              n_vec=7, cb_dist=8, dist_seq=9, dist_seq_2d=10, big_bins=11, big_n_bins=12)
+              n_vec=7, cb_dist=8, dist_seq=9, dist_seq_2d=10, big_bins=11, big_n_bins=12, rerank_phases=13)
 
 
 class Params(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in (
         "k1", "max_bins", "max_trials", "bin_threads", "max_vec_per_bin", "hash_size",
-        "k1_build", "max_vec", "big_k1", "big_max_bins", "big_max_trials")] + \
-        [("reserved", C.c_uint32 * 5)]
+        "k1_build", "max_vec", "big_k1", "big_max_bins", "big_max_trials", "rank_mode")] + \
+        [("reserved", C.c_uint32 * 4)]
 
 
 class Stats(C.Structure):

@@ -102,6 +102,39 @@ def test_tied_distances_follow_the_network_order():
         t.close()
 
 
+@pytest.fixture(scope="module")
+def case_dense():
+    """Every query fills its 4096-candidate budget (small hash => no empty bins): the regime
+    of the 100M / 1B indexes.  About half of the queries hold bit-equal distances of
+    different vectors, a third of the candidates are duplicates of a vector listed twice."""
+    import conftest
+    return conftest.make_case(N=200000, QN=256, c1=32, c2=32, LP=16, hash_size=20011,
+                              n_clusters=1024, seed=5)
+
+
+@pytest.mark.parametrize("k", [4096, 1000, 37])
+def test_dense_candidate_lists_fast_ranking(case_dense, k):
+    """rank_mode 0 (composite-key sort + tie handling) and rank_mode 1 (the reference's
+    network on every query) both return the oracle's ids and distances."""
+    c = case_dense
+    QN = c["Q"].shape[0]
+    d0, i0 = oracle_query(c, k)
+    if k == 4096:
+        ties = sum(int(np.any((d0[q][1:] == d0[q][:-1]) & (i0[q][1:] != i0[q][:-1]))) for q in range(QN))
+        assert ties > QN // 8  # ties between different vectors are common here
+    for mode in (0, 1):
+        t = make_gpu_index(c, rank_mode=mode)
+        t.profile(True)
+        t.reset_stats()
+        i1, d1 = t.queryKNN(c["Q"], QN, k)
+        st = t.stats()
+        assert np.array_equal(d1, d0), "rank_mode %d" % mode
+        assert np.array_equal(i1, i0), "rank_mode %d" % mode
+        if mode == 0:
+            assert st.exact_rank_queries < QN  # the network is the exception, not the rule
+        t.close()
+
+
 def test_distances_at_or_above_the_pad_value(case_small):
     """Distances >= 1e7 sort behind / among the 1e7 padding in the reference's network."""
     c = dict(case_small)
