@@ -3,9 +3,9 @@
 // The reference ranks with a key/value bitonic network and strict float compares
 // (pqt/bitonicSort.cuh:16-78).  Its result is "ascending by distance"; only the order
 // inside a group of bit-equal distances depends on the network.  The fast path sorts
-// 32-bit composite words  (20-bit order-preserving key | 12-bit candidate slot)  with
+// 32-bit composite words  (order-preserving key in the high bits | candidate slot)  with
 // unsigned min/max compare-exchanges (2 ALU instructions instead of 5, one shuffle
-// instead of two, 4 bytes per element), then repairs the few neighbours whose 20-bit
+// instead of two, 4 bytes per element), then repairs the few neighbours whose truncated
 // keys collide by comparing their full 32-bit keys while the results are emitted.
 // Equal distances of the SAME vector (a bin listed twice) are interchangeable; equal
 // distances of DIFFERENT vectors are reported to the caller, which resolves the group
@@ -106,14 +106,32 @@ __device__ __forceinline__ void block_sort_u32(uint32_t (&c)[E], uint32_t t, uin
   }
 }
 
-constexpr uint32_t kFastRunMax = 16;  // slots on either side of one that a run of colliding 20-bit
+constexpr uint32_t kFastRunMax = 16;  // slots on either side of one that a run of colliding truncated
                                       // keys may reach and still be repaired in place
 constexpr uint32_t kFastMinN2 = 128;  // shortest list the composite sort takes (32 threads x 4)
-constexpr int kEmitW = 8;              // consecutive result slots per thread in the emit pass
 
 struct FastRankState {
   uint32_t umin, umax;  // sortable keys of the real candidates
 };
+
+// composite words of the nv real candidates, sorted ascending into s_cmp[0 .. n2)
+template <int E>
+__device__ __forceinline__ void fast_sort_composites(uint32_t t, uint32_t sub_bar, const float* s_val,
+                                                     uint32_t* s_cmp, uint32_t nv, uint32_t n2,
+                                                     uint32_t umin, uint32_t shift, uint32_t sb) {
+  const uint32_t T = n2 / E;
+  if (t < T) {
+    uint32_t c[E];
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+      const uint32_t e = r * T + t;  // any assignment of slots to threads will do
+      c[r] = e < nv ? ((((sortable_key(s_val[e]) - umin) >> shift) << sb) | e) : 0xFFFFFFFFu;
+    }
+    block_sort_u32<E>(c, t, T, s_cmp, sub_bar);
+#pragma unroll
+    for (int r = 0; r < E; r++) s_cmp[t * E + r] = c[r];
+  }
+}
 
 // Fast ranking of the nv real candidates of one query (all < 1e7, finite).
 //   s_val[a]: distance of candidate slot a (candidate order, untouched)
@@ -123,26 +141,9 @@ struct FastRankState {
 // Writes the first k results (pads after nv).  Returns (to every thread of the group) a
 // flag word: bit 0 = some bit-equal distances belong to different vectors (their order in
 // the output is by candidate slot, not yet the network's), bit 1 = a run of colliding keys
-// was too long to repair (output incomplete).  g.n * kEmitW >= max_vec.
-// composite words of the nv real candidates, sorted ascending into s_cmp[0 .. n2)
-template <int E>
-__device__ __forceinline__ void fast_sort_composites(uint32_t t, uint32_t sub_bar, const float* s_val,
-                                                     uint32_t* s_cmp, uint32_t nv, uint32_t n2,
-                                                     uint32_t umin, uint32_t shift) {
-  const uint32_t T = n2 / E;
-  if (t < T) {
-    uint32_t c[E];
-#pragma unroll
-    for (int r = 0; r < E; r++) {
-      const uint32_t e = r * T + t;  // any assignment of slots to threads will do
-      c[r] = e < nv ? ((((sortable_key(s_val[e]) - umin) >> shift) << 12) | e) : 0xFFFFFFFFu;
-    }
-    block_sort_u32<E>(c, t, T, s_cmp, sub_bar);
-#pragma unroll
-    for (int r = 0; r < E; r++) s_cmp[t * E + r] = c[r];
-  }
-}
-
+// was too long to repair (output incomplete).  kEmitW = consecutive result slots per
+// thread in the emit pass (a multiple of 4; g.n * kEmitW >= max_vec).
+template <int kEmitW>
 __device__ __forceinline__ uint32_t fast_rank_emit(const Grp& g, uint32_t sub_bar, const float* s_val,
                                                    uint32_t* s_cmp, uint32_t* s_fix, uint32_t* s_flag,
                                                    uint32_t nv, uint32_t n2, uint32_t k,
@@ -152,20 +153,23 @@ __device__ __forceinline__ uint32_t fast_rank_emit(const Grp& g, uint32_t sub_ba
                                                    unsigned long long* ph) {
   const uint32_t t = g.t;
   const uint32_t range = st.umax - st.umin;
+  // composite word = key << sb | slot: sb = log2(n2) slot bits, the other 32 - sb bits hold
+  // the order-preserving key (shorter lists get longer keys, hence fewer collisions)
+  const uint32_t sb = 31u - (uint32_t)__clz((int)n2);
+  const uint32_t smask = n2 - 1u;
   const uint32_t bits = 32u - (uint32_t)__clz((int)range);
-  const uint32_t shift = bits > 20u ? bits - 20u : 0u;
+  const uint32_t shift = bits > 32u - sb ? bits - (32u - sb) : 0u;
   if (t == 0) *s_flag = 0;
   if (t < 128u) s_fix[t] = 0;  // one bit per result slot (<= 4096)
-  // elements per thread: fewer for short lists, so that the sort keeps 4-8 warps busy
-  if (n2 >= 4096u)
-    fast_sort_composites<16>(t, sub_bar, s_val, s_cmp, nv, n2, st.umin, shift);
-  else if (n2 >= 2048u)
-    fast_sort_composites<8>(t, sub_bar, s_val, s_cmp, nv, n2, st.umin, shift);
+  // 16 elements per thread cost the fewest instructions (the kernel is issue-bound; other
+  // thread groups of the CTA cover the latency); short lists take 4 so that a warp is filled
+  if (n2 >= 512u)
+    fast_sort_composites<16>(t, sub_bar, s_val, s_cmp, nv, n2, st.umin, shift, sb);
   else
-    fast_sort_composites<4>(t, sub_bar, s_val, s_cmp, nv, n2, st.umin, shift);
+    fast_sort_composites<4>(t, sub_bar, s_val, s_cmp, nv, n2, st.umin, shift, sb);
   g.sync();
   if (ph && t == 0) ph[3] = clock64();
-  // ---- emit.  Sorted slot e holds composite s_cmp[e]; neighbours whose 20-bit keys collide
+  // ---- emit.  Sorted slot e holds composite s_cmp[e]; neighbours whose truncated keys collide
   // are in candidate-slot order and may have to be re-ordered by their full keys.  A thread
   // looks at kEmitW consecutive slots plus one neighbour on each side, with all loads of a
   // level issued together (slot -> distance and position, position -> id).
@@ -177,7 +181,7 @@ __device__ __forceinline__ uint32_t fast_rank_emit(const Grp& g, uint32_t sub_ba
   float v[kEmitW + 2];
   const bool active = e0 < e_end;
   if (active) {
-    uint32_t eq20 = 0;  // bit b: slots e0-1+b and e0+b are real and share their 20-bit key
+    uint32_t eq20 = 0;  // bit b: slots e0-1+b and e0+b are real and share their truncated key
     {
       uint32_t c[kEmitW + 2];
 #pragma unroll
@@ -188,13 +192,13 @@ __device__ __forceinline__ uint32_t fast_rank_emit(const Grp& g, uint32_t sub_ba
 #pragma unroll
       for (int b = 0; b <= kEmitW; b++) {
         const uint32_t er = e0 + b;
-        if (er < nv && er > 0u && ((c[b] ^ c[b + 1]) >> 12) == 0u) eq20 |= 1u << b;
+        if (er < nv && er > 0u && ((c[b] ^ c[b + 1]) >> sb) == 0u) eq20 |= 1u << b;
       }
       uint32_t ps[kEmitW + 2];
 #pragma unroll
       for (int i = 0; i < kEmitW + 2; i++) {
         const uint32_t e = e0 + i - 1u;
-        const uint32_t a = c[i] & 0xFFFu;
+        const uint32_t a = c[i] & smask;
         v[i] = e < nv ? s_val[a] : kPadDist;
         ps[i] = e < nv ? __ldg(cand + a) : 0u;
       }
@@ -222,8 +226,8 @@ __device__ __forceinline__ uint32_t fast_rank_emit(const Grp& g, uint32_t sub_ba
       const uint32_t e = e0 + b;  // right slot of the bad boundary
       const uint32_t ce = s_cmp[e];
       uint32_t rs = e - 1u, re = e + 1u;
-      while (rs > 0u && e - rs <= kFastRunMax && ((ce ^ s_cmp[rs - 1]) >> 12) == 0u) rs--;
-      while (re < nv && re - e <= kFastRunMax && ((ce ^ s_cmp[re]) >> 12) == 0u) re++;
+      while (rs > 0u && e - rs <= kFastRunMax && ((ce ^ s_cmp[rs - 1]) >> sb) == 0u) rs--;
+      while (re < nv && re - e <= kFastRunMax && ((ce ^ s_cmp[re]) >> sb) == 0u) re++;
       if (re - rs > kFastRunMax + 1u) flag |= 2u;  // every member must see the whole run in its window
       for (uint32_t j = rs; j < re; j++) atomicOr(&s_fix[j >> 5], 1u << (j & 31u));
     }
@@ -244,10 +248,11 @@ __device__ __forceinline__ uint32_t fast_rank_emit(const Grp& g, uint32_t sub_ba
       // (pads beyond nv already carry kPadDist / kPadIdx)
       float4* od = reinterpret_cast<float4*>(out_dist + e0);
       uint4* oi = reinterpret_cast<uint4*>(out_idx + e0);
-      od[0] = make_float4(v[1], v[2], v[3], v[4]);
-      od[1] = make_float4(v[5], v[6], v[7], v[8]);
-      oi[0] = make_uint4(id[1], id[2], id[3], id[4]);
-      oi[1] = make_uint4(id[5], id[6], id[7], id[8]);
+#pragma unroll
+      for (int q = 0; q < kEmitW / 4; q++) {
+        od[q] = make_float4(v[4 * q + 1], v[4 * q + 2], v[4 * q + 3], v[4 * q + 4]);
+        oi[q] = make_uint4(id[4 * q + 1], id[4 * q + 2], id[4 * q + 3], id[4 * q + 4]);
+      }
     } else {
 #pragma unroll
       for (int i = 1; i <= kEmitW; i++) {
@@ -258,15 +263,15 @@ __device__ __forceinline__ uint32_t fast_rank_emit(const Grp& g, uint32_t sub_ba
         }
       }
       // slots of runs with unequal full keys: rank inside the run by (full key, slot).  The
-      // slots are sorted by their 20-bit keys, so the run is exactly the neighbours with an
-      // equal 20-bit key: a fixed window, no data-dependent walk (longer runs were flagged).
+      // slots are sorted by their truncated keys, so the run is exactly the neighbours with an
+      // equal truncated key: a fixed window, no data-dependent walk (longer runs were flagged).
       uint32_t fx = fix;
       while (fx) {
         const uint32_t e = e0 + (uint32_t)__ffs(fx) - 1u;
         fx &= fx - 1u;
         if (e >= e_end) continue;
         const uint32_t ce = s_cmp[e];
-        const uint32_t a = ce & 0xFFFu;
+        const uint32_t a = ce & smask;
         const float ve = s_val[a];
         const uint32_t u = sortable_key(ve);
         uint32_t before = 0, rank = 0;
@@ -274,8 +279,8 @@ __device__ __forceinline__ uint32_t fast_rank_emit(const Grp& g, uint32_t sub_ba
         for (int d = -(int)kFastRunMax; d < (int)kFastRunMax; d++) {
           const uint32_t j = e + (uint32_t)(d < 0 ? d : d + 1);  // wraps below 0: fails j < nv
           const uint32_t cj = j < nv ? s_cmp[j] : ~ce;
-          const bool in_run = ((cj ^ ce) >> 12) == 0u;
-          const uint32_t uj = sortable_key(s_val[in_run ? (cj & 0xFFFu) : a]);
+          const bool in_run = ((cj ^ ce) >> sb) == 0u;
+          const uint32_t uj = sortable_key(s_val[in_run ? (cj & smask) : a]);
           if (in_run) {
             if (d < 0) before++;
             if (uj < u || (uj == u && d < 0)) rank++;

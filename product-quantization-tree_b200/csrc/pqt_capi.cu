@@ -542,12 +542,16 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
     a.out_val = d_val;
     a.out_idx = d_idx;
     size_t smem = ((size_t)h->c1 * h->c1 * 32 + 2 * (size_t)h->c1 * 32) * 4 + 64;
-    // cbd + per group (2 LUT buffers + 3 candidate arrays) + barriers/flags
-    const size_t smem_fused = ((size_t)h->c1 * h->c1 * 32 + kRerankGroups * 2 * (size_t)h->c1 * 32 +
-                               0) * 4 + kRerankGroups * ((size_t)8 * max_vec + 512) + 128;
-    if (fused_out_dist && smem_fused <= 227 * 1024) {
+    // fused scan + rank: 4 thread groups per CTA over the canonical c^2 table when that fits
+    // (LP <= 16), else 2 groups over the replicated table
+    const size_t kSmemMax = 227 * 1024;
+    const bool four = h->LP <= 16 && rerank_smem_bytes(h->c1, h->LP, max_vec, 4, false) <= kSmemMax;
+    const size_t smem_fused = four ? rerank_smem_bytes(h->c1, h->LP, max_vec, 4, false)
+                                   : rerank_smem_bytes(h->c1, h->LP, max_vec, 2, true);
+    if (fused_out_dist && smem_fused <= kSmemMax) {
       RerankArgs g{};
       g.s = a;
+      if (four) g.s.cbd_dup = h->d_cbd.as<float>();  // canonical [c1][c1][LP]
       g.k = k;
       g.out_dist = fused_out_dist;
       g.out_idx = fused_out_idx;
@@ -560,20 +564,31 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
         CU_TRY(h, h->g_phases.ensure((size_t)QN * 8 * 8));
         g.phase_dbg = h->g_phases.as<unsigned long long>();
       }
-      uint32_t grid = std::min<uint32_t>((QN + kRerankGroups - 1) / kRerankGroups, (uint32_t)h->num_sms);
-#define LAUNCH_RERANK(LPV)                                                                       \
+      const uint32_t ng = four ? 4u : 2u;
+      uint32_t grid = std::min<uint32_t>((QN + ng - 1) / ng, (uint32_t)h->num_sms);
+#define LAUNCH_RERANK(LPV, NGV, CREPV)                                                           \
   do {                                                                                           \
-    CU_TRY(h, cudaFuncSetAttribute(rerank_kernel<LPV>,                                           \
+    CU_TRY(h, cudaFuncSetAttribute(rerank_kernel<LPV, NGV, CREPV>,                               \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused)); \
-    rerank_kernel<LPV><<<grid, kScanThreads, smem_fused, h->stream>>>(g);                        \
+    rerank_kernel<LPV, NGV, CREPV><<<grid, kScanThreads, smem_fused, h->stream>>>(g);            \
   } while (0)
-      switch (h->LP) {
-        case 1: LAUNCH_RERANK(1); break;
-        case 2: LAUNCH_RERANK(2); break;
-        case 4: LAUNCH_RERANK(4); break;
-        case 8: LAUNCH_RERANK(8); break;
-        case 16: LAUNCH_RERANK(16); break;
-        default: LAUNCH_RERANK(32); break;
+      if (four) {
+        switch (h->LP) {
+          case 1: LAUNCH_RERANK(1, 4, false); break;
+          case 2: LAUNCH_RERANK(2, 4, false); break;
+          case 4: LAUNCH_RERANK(4, 4, false); break;
+          case 8: LAUNCH_RERANK(8, 4, false); break;
+          default: LAUNCH_RERANK(16, 4, false); break;
+        }
+      } else {
+        switch (h->LP) {
+          case 1: LAUNCH_RERANK(1, 2, true); break;
+          case 2: LAUNCH_RERANK(2, 2, true); break;
+          case 4: LAUNCH_RERANK(4, 2, true); break;
+          case 8: LAUNCH_RERANK(8, 2, true); break;
+          case 16: LAUNCH_RERANK(16, 2, true); break;
+          default: LAUNCH_RERANK(32, 2, true); break;
+        }
       }
 #undef LAUNCH_RERANK
     } else if (smem <= 220 * 1024) {

@@ -537,15 +537,28 @@ struct RerankArgs {
                                       // statically assigned tail
 };
 
-constexpr int kRerankGroups = 2;
+constexpr int kRerankGroups = 2;  // rank2_kernel / default configuration
 constexpr int kRerankGroupThreads = kScanThreads / kRerankGroups;  // 512
 
-template <int LP>
+// NG thread groups per CTA (each on its own query): more groups hide more of the per-query
+// latency chains (code loads -> scan -> sort -> emit) but need NG candidate arrays in shared
+// memory.  CREP: the c^2 table has 32-float rows (LP values replicated 32/LP times, conflict
+// free, c1*c1*128 bytes); otherwise its rows are the LP values only (the canonical cbDist
+// layout, c1*c1*LP*4 bytes; the 32/LP candidates of a warp step may collide on a bank).
+inline size_t rerank_smem_bytes(uint32_t c1, uint32_t LP, uint32_t max_vec, int NG, bool crep) {
+  return ((size_t)c1 * c1 * (crep ? 32 : LP) + (size_t)NG * 2 * c1 * 32) * 4 +
+         (size_t)NG * ((size_t)8 * max_vec + 512 + 4 + 16 + 16) + 64;
+}
+
+template <int LP, int NG, bool CREP>
 __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
   const ScanArgs& a = g.s;
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr uint32_t kRerankGroups = NG;
+  constexpr uint32_t kRerankGroupThreads = kScanThreads / NG;
+  constexpr uint32_t CROW = CREP ? 32u : (uint32_t)LP;  // floats per row of the c^2 table
   const uint32_t lut_floats = a.c1 * 32;
-  const uint32_t cbd_floats = a.c1 * a.c1 * 32;
+  const uint32_t cbd_floats = a.c1 * a.c1 * CROW;
   const uint32_t grp = threadIdx.x / kRerankGroupThreads;
   Grp G{threadIdx.x - grp * kRerankGroupThreads, (uint32_t)kRerankGroupThreads, 1 + grp};
 
@@ -553,7 +566,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
   float* s_luts = s_cbd + cbd_floats;                                  // [groups][2][lut_floats]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_luts + kRerankGroups * 2 * lut_floats);  // [groups][2] + cbd
   uint32_t* s_flags = reinterpret_cast<uint32_t*>(bars + 2 * kRerankGroups + 2);
-  uint32_t* s_red = s_flags + 4;                                       // [groups][4]: umin, umax, bad
+  uint32_t* s_red = s_flags + kRerankGroups;                           // [groups][4]: umin, umax, bad, next query
   uint32_t* s_fixes = s_red + 4 * kRerankGroups;                       // [groups][128]: emit bitmap
   float* s_arr = reinterpret_cast<float*>(s_fixes + 128 * kRerankGroups);  // [groups][2][max_vec]
   float* s_lut0 = s_luts + grp * 2 * lut_floats;
@@ -576,11 +589,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
   const uint32_t lane = G.t & 31, warp = G.t >> 5, nwarps = G.n >> 5;
   const uint32_t lp = lane & (LP - 1);
   const uint32_t grp_base = lane & ~(uint32_t)(LP - 1);
-  const uint32_t worker = blockIdx.x * kRerankGroups + grp;
-  const uint32_t nworkers = gridDim.x * kRerankGroups;
+  const uint32_t cbd_b = smem_u32(s_cbd) + (CREP ? lane : lp) * 4u;
+  const uint32_t* __restrict__ codes_lp = a.codes + lp;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2 * kRerankGroups + 1; i++) mbar_init(&bars[i], 1);
+    for (uint32_t i = 0; i < 2 * kRerankGroups + 1; i++) mbar_init(&bars[i], 1);
     mbar_fence_init();
   }
   __syncthreads();
@@ -637,12 +650,15 @@ __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
     G.sync();
     const uint32_t q_next = *s_q;
     // ---- scan: only chunks that hold real candidates
+    const uint32_t lut_b = smem_u32(s_lut) + lane * 4u;
     uint32_t umin = 0xFFFFFFFFu, umax = 0u, bad = 0u;
     uint32_t pos_next = (warp * 32 + lane < nv) ? __ldg(cand + warp * 32 + lane) : 0u;
     for (uint32_t base = warp * 32; base < nv; base += nwarps * 32) {
       const uint32_t ca = base + lane;
       const bool valid = ca < nv;
       const uint32_t pos = pos_next;  // 0 for lanes past the end: a valid code row, result unused
+      // the id is read when the result is emitted: pull its sector into L2 now
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ids + pos));
       {
         const uint32_t cn = ca + nwarps * 32;
         pos_next = cn < nv ? __ldg(cand + cn) : 0u;
@@ -652,17 +668,20 @@ __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
         uint32_t w[LP];
 #pragma unroll
         for (int s = 0; s < LP; s++) {
-          const uint32_t cpos = __shfl_sync(0xffffffffu, pos, grp_base + s);
-          w[s] = __ldg(a.codes + (size_t)cpos * LP + lp);
+          // position of candidate s of this lane group (shuffle inside the LP-lane segment)
+          const uint32_t cpos = __shfl_sync(0xffffffffu, pos, s, LP);
+          w[s] = __ldg(codes_lp + (size_t)cpos * LP);
         }
 #pragma unroll
         for (int s = 0; s < LP; s++) {
+          // lineDescr {p1, p2, lambda} (pqt/PerturbationProTree.hh:21-25); table rows are
+          // addressed in shared-space bytes: row * 128 (or LP * 4) + this lane's column
           const uint32_t p1 = w[s] & 0xFFu;
-          const uint32_t p2 = (w[s] >> 8) & 0xFFu;
+          const uint32_t p2 = __byte_perm(w[s], 0u, 0x4441u);
           const float lam = lambda_of(w[s]);
-          const float a2 = s_lut[p1 * 32 + lane];
-          const float b2 = s_lut[p2 * 32 + lane];
-          const float c2 = s_cbd[(p2 * a.c1 + p1) * 32 + lane];
+          const float a2 = lds_f32(lut_b + (p1 << 7));
+          const float b2 = lds_f32(lut_b + (p2 << 7));
+          const float c2 = lds_f32(cbd_b + (p2 * a.c1 + p1) * (CROW * 4u));
           d[s] = tri_dist(a2, b2, c2, lam);
         }
       }
@@ -712,7 +731,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
     bool done = false;
     if (g.fast_rank && n2 >= kFastMinN2 && *s_bad == 0u) {
       FastRankState st{*s_min, *s_max};
-      const uint32_t f = fast_rank_emit(G, 3 + grp, s_val, s_cmp, s_fix, s_flag, nv, n2, g.k, st,
+      const uint32_t f = fast_rank_emit<(4096 / kRerankGroupThreads)>(G, 1 + kRerankGroups + grp, s_val, s_cmp, s_fix, s_flag, nv, n2, g.k, st,
                                                 od, oi, cand, a.ids, ph);
       done = (f == 0u);
       if (ph && G.t == 0) ph[5] = clock64();
