@@ -67,9 +67,10 @@ __device__ __forceinline__ void reg_clean_u32(uint32_t (&c)[E]) {
 
 // One cross-thread step: thread t exchanges with thread t ^ m (register r with register r,
 // or with register E-1-r when REV) and keeps the minima when it holds the lower indices.
-// m < 32: shuffles; otherwise through s_x ([E][T] words) with the sub-group barrier.
+// m < 32: shuffles; otherwise through s_x ([E][Ta] words) with the sub-group barrier.
+// Threads >= Ta hold only pad words (0xFFFFFFFF) and do not take part.
 template <int E, bool REV>
-__device__ __forceinline__ void xthread_step_u32(uint32_t (&c)[E], uint32_t t, uint32_t T,
+__device__ __forceinline__ void xthread_step_u32(uint32_t (&c)[E], uint32_t t, uint32_t Ta,
                                                  uint32_t m, bool keep_min, uint32_t* s_x,
                                                  uint32_t bar_id) {
   uint32_t o[E];
@@ -78,30 +79,35 @@ __device__ __forceinline__ void xthread_step_u32(uint32_t (&c)[E], uint32_t t, u
     for (int r = 0; r < E; r++) o[r] = __shfl_xor_sync(0xffffffffu, c[REV ? E - 1 - r : r], m);
   } else {
 #pragma unroll
-    for (int r = 0; r < E; r++) s_x[r * T + t] = c[r];
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(T) : "memory");
+    for (int r = 0; r < E; r++) s_x[r * Ta + t] = c[r];
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(Ta) : "memory");
     const uint32_t tp = t ^ m;
+    if (tp < Ta) {
 #pragma unroll
-    for (int r = 0; r < E; r++) o[r] = s_x[(REV ? E - 1 - r : r) * T + tp];
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(T) : "memory");
+      for (int r = 0; r < E; r++) o[r] = s_x[(REV ? E - 1 - r : r) * Ta + tp];
+    } else {
+#pragma unroll
+      for (int r = 0; r < E; r++) o[r] = 0xFFFFFFFFu;
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(Ta) : "memory");
   }
 #pragma unroll
   for (int r = 0; r < E; r++) c[r] = keep_min ? min(c[r], o[r]) : max(c[r], o[r]);
 }
 
-// Ascending sort of n2 = E*T distinct words by T threads (T a multiple of 32, threads
-// t = 0..T-1 of consecutive warps; all of them must call).  Thread t ends with the sorted
+// Ascending sort of n2 = E*T distinct words of which only the first E*Ta (Ta a multiple of
+// 32, Ta <= T) can differ from the pad word 0xFFFFFFFF; run by threads t = 0..Ta-1 (all of
+// them must call).  Pads are the maximum and the network only moves minima down, so the
+// threads >= Ta would never change: they are left out.  Thread t ends with the sorted
 // elements t*E .. t*E+E-1 in c[0..E-1].
 template <int E>
-__device__ __forceinline__ void block_sort_u32(uint32_t (&c)[E], uint32_t t, uint32_t T,
+__device__ __forceinline__ void block_sort_u32(uint32_t (&c)[E], uint32_t t, uint32_t T, uint32_t Ta,
                                                uint32_t* s_x, uint32_t bar_id) {
   reg_sort_u32<E>(c);
-  const uint32_t n2 = E * T;
-  for (uint32_t k = 2u * E; k <= n2; k <<= 1) {
-    const uint32_t kt = k / E;  // threads per merged block
-    xthread_step_u32<E, true>(c, t, T, kt - 1u, (t & (kt >> 1)) == 0u, s_x, bar_id);
+  for (uint32_t kt = 2u; kt <= T; kt <<= 1) {  // kt: threads per merged block
+    xthread_step_u32<E, true>(c, t, Ta, kt - 1u, (t & (kt >> 1)) == 0u, s_x, bar_id);
     for (uint32_t jt = kt >> 2; jt > 0u; jt >>= 1)
-      xthread_step_u32<E, false>(c, t, T, jt, (t & jt) == 0u, s_x, bar_id);
+      xthread_step_u32<E, false>(c, t, Ta, jt, (t & jt) == 0u, s_x, bar_id);
     reg_clean_u32<E>(c);
   }
 }
@@ -114,36 +120,131 @@ struct FastRankState {
   uint32_t umin, umax;  // sortable keys of the real candidates
 };
 
-// composite words of the nv real candidates, sorted ascending into s_cmp[0 .. n2)
+// Sort + emit by the sorter threads, E sorted slots each, straight from their registers.
+// Every slot is stored at its sorted position; slots of runs (equal truncated keys) that hold
+// unequal full keys are marked in s_fix and re-ordered afterwards by the caller.
+//   flag bits: 1 = bit-equal distances of different vectors seen, 2 = run too long to
+//   repair, 4 = some slots are marked in s_fix
 template <int E>
-__device__ __forceinline__ void fast_sort_composites(uint32_t t, uint32_t sub_bar, const float* s_val,
-                                                     uint32_t* s_cmp, uint32_t nv, uint32_t n2,
-                                                     uint32_t umin, uint32_t shift, uint32_t sb) {
+__device__ __forceinline__ uint32_t fast_sort_emit(uint32_t t, uint32_t gn, uint32_t sub_bar,
+                                                   const float* s_val, uint32_t* s_cmp,
+                                                   uint32_t* s_fix, uint32_t nv, uint32_t n2,
+                                                   uint32_t k, uint32_t umin, uint32_t shift,
+                                                   uint32_t sb, float* out_dist, uint32_t* out_idx,
+                                                   const uint32_t* __restrict__ cand,
+                                                   const uint32_t* __restrict__ ids) {
+  constexpr int CH = E < 8 ? E : 8;  // slots handled together (loads of a level issued together)
   const uint32_t T = n2 / E;
-  if (t < T) {
+  const uint32_t Ta = min(T, ((nv + E - 1u) / E + 31u) & ~31u);  // sorter threads
+  const uint32_t smask = n2 - 1u;
+  uint32_t flag = 0;
+  if (t < Ta) {
     uint32_t c[E];
 #pragma unroll
     for (int r = 0; r < E; r++) {
-      const uint32_t e = r * T + t;  // any assignment of slots to threads will do
+      const uint32_t e = t * E + r;
       c[r] = e < nv ? ((((sortable_key(s_val[e]) - umin) >> shift) << sb) | e) : 0xFFFFFFFFu;
     }
-    block_sort_u32<E>(c, t, T, s_cmp, sub_bar);
+    block_sort_u32<E>(c, t, T, Ta, s_cmp, sub_bar);
+    // publish: neighbours' edge slots and the repair windows read s_cmp
 #pragma unroll
     for (int r = 0; r < E; r++) s_cmp[t * E + r] = c[r];
+    asm volatile("bar.sync %0, %1;" ::"r"(sub_bar), "r"(Ta) : "memory");
+    // left neighbour of the thread's first slot
+    uint32_t c_prev = t > 0u ? s_cmp[t * E - 1u] : 0xFFFFFFFFu;
+    float v_prev = 0.f;
+    uint32_t p_prev = 0u;
+    if (t > 0u && t * E - 1u < nv) {
+      const uint32_t a = c_prev & smask;
+      v_prev = s_val[a];
+      p_prev = __ldg(cand + a);
+    }
+#pragma unroll
+    for (int h = 0; h < E / CH; h++) {
+      const uint32_t e0 = t * E + h * CH;
+      float v[CH];
+      uint32_t ps[CH], id[CH];
+#pragma unroll
+      for (int i = 0; i < CH; i++) {
+        const uint32_t a = c[h * CH + i] & smask;
+        const bool real = e0 + i < nv;
+        v[i] = real ? s_val[a] : kPadDist;
+        ps[i] = real ? __ldg(cand + a) : 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < CH; i++) id[i] = (e0 + i < nv) ? __ldg(ids + ps[i]) : kPadIdx;
+      // boundaries between slot e0+i-1 and e0+i
+      uint32_t bad = 0;
+#pragma unroll
+      for (int i = 0; i < CH; i++) {
+        const uint32_t cl = i ? c[h * CH + i - 1] : c_prev;
+        const float vl = i ? v[i - 1] : v_prev;
+        const uint32_t pl = i ? ps[i - 1] : p_prev;
+        const uint32_t er = e0 + i;
+        if (er < nv && er > 0u && ((cl ^ c[h * CH + i]) >> sb) == 0u) {
+          if (sortable_key(vl) != sortable_key(v[i]))
+            bad |= 1u << i;
+          else if (pl != ps[i])
+            flag |= 1u;  // bit-equal distances of different vectors
+        }
+      }
+      c_prev = c[h * CH + CH - 1];
+      v_prev = v[CH - 1];
+      p_prev = ps[CH - 1];
+      // mark every slot of a run that holds unequal full keys (rare)
+      if (bad) flag |= 4u;
+      while (bad) {
+        const uint32_t e = e0 + (uint32_t)__ffs(bad) - 1u;  // right slot of the bad boundary
+        bad &= bad - 1u;
+        const uint32_t ce = s_cmp[e];
+        uint32_t rs = e - 1u, re = e + 1u;
+        while (rs > 0u && e - rs <= kFastRunMax && ((ce ^ s_cmp[rs - 1]) >> sb) == 0u) rs--;
+        while (re < nv && re - e <= kFastRunMax && ((ce ^ s_cmp[re]) >> sb) == 0u) re++;
+        if (re - rs > kFastRunMax + 1u) flag |= 2u;  // every member must see the whole run in its window
+        for (uint32_t j = rs; j < re; j++) atomicOr(&s_fix[j >> 5], 1u << (j & 31u));
+      }
+      // store at the sorted position (marked slots are overwritten by the repair pass)
+      const bool vec_ok = (CH % 4 == 0) && e0 + CH <= k &&
+                          (((uintptr_t)(out_dist + e0) | (uintptr_t)(out_idx + e0)) & 15u) == 0u;
+      if (vec_ok) {
+        float4* od = reinterpret_cast<float4*>(out_dist + e0);
+        uint4* oi = reinterpret_cast<uint4*>(out_idx + e0);
+#pragma unroll
+        for (int q = 0; q < CH / 4; q++) {
+          od[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          oi[q] = make_uint4(id[4 * q], id[4 * q + 1], id[4 * q + 2], id[4 * q + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+          if (e0 + i < k) {
+            out_dist[e0 + i] = v[i];
+            out_idx[e0 + i] = id[i];
+          }
+        }
+      }
+    }
+  } else {
+    // the other threads of the group write the pads behind the sorters' slots
+    const uint32_t first = Ta * E;
+    const uint32_t nt = gn - Ta;
+    for (uint32_t e = first + (t - Ta); e < k; e += nt) {
+      out_dist[e] = kPadDist;
+      out_idx[e] = kPadIdx;
+    }
   }
+  return flag;
 }
 
 // Fast ranking of the nv real candidates of one query (all < 1e7, finite).
 //   s_val[a]: distance of candidate slot a (candidate order, untouched)
 //   s_cmp   : scratch, n2 words (n2 = pow2ceil(nv), kFastMinN2 <= n2 <= 4096)
-//   s_fix   : scratch bitmap, one bit per result slot (max_vec / 32 words)
+//   s_fix   : scratch bitmap, one bit per result slot (128 words)
 //   cand[a] : bin-order position of candidate slot a (identifies the vector), ids[pos] its id
 // Writes the first k results (pads after nv).  Returns (to every thread of the group) a
 // flag word: bit 0 = some bit-equal distances belong to different vectors (their order in
 // the output is by candidate slot, not yet the network's), bit 1 = a run of colliding keys
-// was too long to repair (output incomplete).  kEmitW = consecutive result slots per
-// thread in the emit pass (a multiple of 4; g.n * kEmitW >= max_vec).
-template <int kEmitW>
+// was too long to repair (output incomplete).  g.n * 16 >= max_vec.
 __device__ __forceinline__ uint32_t fast_rank_emit(const Grp& g, uint32_t sub_bar, const float* s_val,
                                                    uint32_t* s_cmp, uint32_t* s_fix, uint32_t* s_flag,
                                                    uint32_t nv, uint32_t n2, uint32_t k,
@@ -159,158 +260,64 @@ __device__ __forceinline__ uint32_t fast_rank_emit(const Grp& g, uint32_t sub_ba
   const uint32_t smask = n2 - 1u;
   const uint32_t bits = 32u - (uint32_t)__clz((int)range);
   const uint32_t shift = bits > 32u - sb ? bits - (32u - sb) : 0u;
-  if (t == 0) *s_flag = 0;
-  if (t < 128u) s_fix[t] = 0;  // one bit per result slot (<= 4096)
-  // 16 elements per thread cost the fewest instructions (the kernel is issue-bound; other
-  // thread groups of the CTA cover the latency); short lists take 4 so that a warp is filled
+  // (s_flag and s_fix were cleared by the caller before the barrier that ended the scan)
+  // 16 elements per thread cost the fewest instructions; short lists take 4 so that a warp
+  // is filled
+  uint32_t flag;
   if (n2 >= 512u)
-    fast_sort_composites<16>(t, sub_bar, s_val, s_cmp, nv, n2, st.umin, shift, sb);
+    flag = fast_sort_emit<16>(t, g.n, sub_bar, s_val, s_cmp, s_fix, nv, n2, k, st.umin, shift, sb,
+                              out_dist, out_idx, cand, ids);
   else
-    fast_sort_composites<4>(t, sub_bar, s_val, s_cmp, nv, n2, st.umin, shift, sb);
-  g.sync();
-  if (ph && t == 0) ph[3] = clock64();
-  // ---- emit.  Sorted slot e holds composite s_cmp[e]; neighbours whose truncated keys collide
-  // are in candidate-slot order and may have to be re-ordered by their full keys.  A thread
-  // looks at kEmitW consecutive slots plus one neighbour on each side, with all loads of a
-  // level issued together (slot -> distance and position, position -> id).
-  // slots just past k can still move below k when a run of equal keys straddles k
-  const uint32_t e_end = k < nv ? min(nv, k + kFastRunMax) : k;
-  const uint32_t e0 = t * kEmitW;
-  uint32_t flag = 0;
-  uint32_t id[kEmitW + 2];
-  float v[kEmitW + 2];
-  const bool active = e0 < e_end;
-  if (active) {
-    uint32_t eq20 = 0;  // bit b: slots e0-1+b and e0+b are real and share their truncated key
-    {
-      uint32_t c[kEmitW + 2];
-#pragma unroll
-      for (int i = 0; i < kEmitW + 2; i++) {
-        const uint32_t e = e0 + i - 1u;  // e0 == 0: wraps, fails the range test
-        c[i] = e < nv ? s_cmp[e] : 0xFFFFFFFFu;
-      }
-#pragma unroll
-      for (int b = 0; b <= kEmitW; b++) {
-        const uint32_t er = e0 + b;
-        if (er < nv && er > 0u && ((c[b] ^ c[b + 1]) >> sb) == 0u) eq20 |= 1u << b;
-      }
-      uint32_t ps[kEmitW + 2];
-#pragma unroll
-      for (int i = 0; i < kEmitW + 2; i++) {
-        const uint32_t e = e0 + i - 1u;
-        const uint32_t a = c[i] & smask;
-        v[i] = e < nv ? s_val[a] : kPadDist;
-        ps[i] = e < nv ? __ldg(cand + a) : 0u;
-      }
-#pragma unroll
-      for (int i = 0; i < kEmitW + 2; i++) {
-        const uint32_t e = e0 + i - 1u;
-        id[i] = e < nv ? __ldg(ids + ps[i]) : kPadIdx;
-      }
-    }
-    uint32_t bad = 0;
-#pragma unroll
-    for (int b = 0; b <= kEmitW; b++) {
-      if ((eq20 >> b) & 1u) {
-        if (sortable_key(v[b]) != sortable_key(v[b + 1]))
-          bad |= 1u << b;
-        else if (id[b] != id[b + 1])
-          flag |= 1u;  // bit-equal distances of different vectors
-      }
-    }
-    // mark every slot of a run that holds unequal full keys (rare)
-    if (bad) flag |= 4u;
-    while (bad) {
-      const uint32_t b = __ffs(bad) - 1u;
-      bad &= bad - 1u;
-      const uint32_t e = e0 + b;  // right slot of the bad boundary
-      const uint32_t ce = s_cmp[e];
-      uint32_t rs = e - 1u, re = e + 1u;
-      while (rs > 0u && e - rs <= kFastRunMax && ((ce ^ s_cmp[rs - 1]) >> sb) == 0u) rs--;
-      while (re < nv && re - e <= kFastRunMax && ((ce ^ s_cmp[re]) >> sb) == 0u) re++;
-      if (re - rs > kFastRunMax + 1u) flag |= 2u;  // every member must see the whole run in its window
-      for (uint32_t j = rs; j < re; j++) atomicOr(&s_fix[j >> 5], 1u << (j & 31u));
-    }
-  }
+    flag = fast_sort_emit<4>(t, g.n, sub_bar, s_val, s_cmp, s_fix, nv, n2, k, st.umin, shift, sb,
+                             out_dist, out_idx, cand, ids);
   if (flag) atomicOr(s_flag, flag);
   g.sync();
   if (ph && t == 0) ph[4] = clock64();
   const uint32_t f1 = *s_flag;
-  if (f1 & 2u) {  // a run too long to repair: the caller ranks this query with the network
-    g.sync();
-    return 2u;
-  }
-  uint32_t fix = 0;
-  if (active) {
-    if (f1 & 4u) fix = (s_fix[e0 >> 5] >> (e0 & 31u)) & ((1u << kEmitW) - 1u);
-    const bool vec_ok = (((uintptr_t)(out_dist + e0) | (uintptr_t)(out_idx + e0)) & 15u) == 0u;
-    if (fix == 0u && vec_ok && e0 + kEmitW <= k) {
-      // (pads beyond nv already carry kPadDist / kPadIdx)
-      float4* od = reinterpret_cast<float4*>(out_dist + e0);
-      uint4* oi = reinterpret_cast<uint4*>(out_idx + e0);
-#pragma unroll
-      for (int q = 0; q < kEmitW / 4; q++) {
-        od[q] = make_float4(v[4 * q + 1], v[4 * q + 2], v[4 * q + 3], v[4 * q + 4]);
-        oi[q] = make_uint4(id[4 * q + 1], id[4 * q + 2], id[4 * q + 3], id[4 * q + 4]);
-      }
-    } else {
-#pragma unroll
-      for (int i = 1; i <= kEmitW; i++) {
-        const uint32_t e = e0 + i - 1u;
-        if (e < e_end && e < k && !((fix >> (i - 1)) & 1u)) {
-          out_dist[e] = v[i];
-          out_idx[e] = id[i];
-        }
-      }
-      // slots of runs with unequal full keys: rank inside the run by (full key, slot).  The
-      // slots are sorted by their truncated keys, so the run is exactly the neighbours with an
-      // equal truncated key: a fixed window, no data-dependent walk (longer runs were flagged).
-      uint32_t fx = fix;
-      while (fx) {
-        const uint32_t e = e0 + (uint32_t)__ffs(fx) - 1u;
-        fx &= fx - 1u;
-        if (e >= e_end) continue;
-        const uint32_t ce = s_cmp[e];
-        const uint32_t a = ce & smask;
-        const float ve = s_val[a];
-        const uint32_t u = sortable_key(ve);
-        uint32_t before = 0, rank = 0;
+  if ((f1 & 6u) != 4u) return f1 & 3u;  // nothing to repair, or not repairable here
+  // ---- repair pass: slots of runs with unequal full keys get their rank inside the run by
+  // (full key, slot).  The slots are sorted by their truncated keys, so the run is exactly
+  // the neighbours with an equal truncated key: a fixed window, no data-dependent walk.
+  // slots just past k can still move below k when a run straddles k
+  const uint32_t e_end = k < nv ? min(nv, k + kFastRunMax) : min(k, nv);
+  const uint32_t W = 4096u / g.n;  // slots per thread: g.n * W covers every slot
+  uint32_t tie = 0;
+  {
+    const uint32_t e0 = t * W;
+    uint32_t fx = e0 < e_end ? ((s_fix[e0 >> 5] >> (e0 & 31u)) & ((W < 32u) ? ((1u << W) - 1u) : 0xFFFFFFFFu)) : 0u;
+    while (fx) {
+      const uint32_t e = e0 + (uint32_t)__ffs(fx) - 1u;
+      fx &= fx - 1u;
+      if (e >= e_end) continue;
+      const uint32_t ce = s_cmp[e];
+      const uint32_t a = ce & smask;
+      const float ve = s_val[a];
+      const uint32_t u = sortable_key(ve);
+      const uint32_t pe = __ldg(cand + a);
+      uint32_t before = 0, rank = 0;
 #pragma unroll 8
-        for (int d = -(int)kFastRunMax; d < (int)kFastRunMax; d++) {
-          const uint32_t j = e + (uint32_t)(d < 0 ? d : d + 1);  // wraps below 0: fails j < nv
-          const uint32_t cj = j < nv ? s_cmp[j] : ~ce;
-          const bool in_run = ((cj ^ ce) >> sb) == 0u;
-          const uint32_t uj = sortable_key(s_val[in_run ? (cj & smask) : a]);
-          if (in_run) {
-            if (d < 0) before++;
-            if (uj < u || (uj == u && d < 0)) rank++;
-          }
+      for (int d = -(int)kFastRunMax; d < (int)kFastRunMax; d++) {
+        const uint32_t j = e + (uint32_t)(d < 0 ? d : d + 1);  // wraps below 0: fails j < nv
+        const uint32_t cj = j < nv ? s_cmp[j] : ~ce;
+        const bool in_run = ((cj ^ ce) >> sb) == 0u;
+        const uint32_t aj = in_run ? (cj & smask) : a;
+        const uint32_t uj = sortable_key(s_val[aj]);
+        if (in_run) {
+          if (d < 0) before++;
+          if (uj < u || (uj == u && d < 0)) rank++;
+          if (uj == u && __ldg(cand + aj) != pe) tie = 1u;
         }
-        const uint32_t dst = e - before + rank;
-        if (dst < k) {
-          out_dist[dst] = ve;
-          out_idx[dst] = __ldg(ids + __ldg(cand + a));
-        }
+      }
+      const uint32_t dst = e - before + rank;
+      if (dst < k) {
+        out_dist[dst] = ve;
+        out_idx[dst] = __ldg(ids + pe);
       }
     }
   }
-  if (f1 & 4u) {
-    // re-ordered runs: bit-equal distances of different vectors are now adjacent in the output
-    g.sync();
-    if (fix) {
-#pragma unroll
-      for (int i = 0; i < kEmitW; i++) {
-        const uint32_t e = e0 + i;
-        if (((fix >> i) & 1u) && e > 0u && e < k && e < nv) {
-          if (out_dist[e] == out_dist[e - 1] && out_idx[e] != out_idx[e - 1]) atomicOr(s_flag, 1u);
-        }
-      }
-    }
-  }
+  if (tie) atomicOr(s_flag, 1u);
   g.sync();
-  const uint32_t f = *s_flag & 3u;
-  g.sync();
-  return f;
+  return *s_flag & 3u;
 }
 
 }  // namespace pqtb

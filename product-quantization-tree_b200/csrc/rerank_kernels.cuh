@@ -634,7 +634,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
       *s_min = 0xFFFFFFFFu;
       *s_max = 0u;
       *s_bad = 0u;
+      *s_flag = 0u;
     }
+    if (G.t < 128u) s_fix[G.t] = 0u;  // repair bitmap of the ranking pass
     const float* s_lut = buf ? s_lut1 : s_lut0;
     unsigned long long* ph = g.phase_dbg ? g.phase_dbg + (size_t)qi * 8 : nullptr;
     if (ph && G.t == 0) ph[0] = clock64();
@@ -731,7 +733,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
     bool done = false;
     if (g.fast_rank && n2 >= kFastMinN2 && *s_bad == 0u) {
       FastRankState st{*s_min, *s_max};
-      const uint32_t f = fast_rank_emit<(4096 / kRerankGroupThreads)>(G, 1 + kRerankGroups + grp, s_val, s_cmp, s_fix, s_flag, nv, n2, g.k, st,
+      const uint32_t f = fast_rank_emit(G, 1 + kRerankGroups + grp, s_val, s_cmp, s_fix, s_flag, nv, n2, g.k, st,
                                                 od, oi, cand, a.ids, ph);
       done = (f == 0u);
       if (ph && G.t == 0) ph[5] = clock64();
