@@ -400,6 +400,7 @@ def run_b200(a, rank, world, local_rank):
         "clocks": clocks,
         "recall_at_1": recall1,
         "exact_rank_queries_per_step": st.exact_rank_queries / a.steps,
+        "tie_resolved_queries_per_step": st.tie_resolved_queries / a.steps,
         "parity_vs_oracle_on_cpu_sample": parity,
     }
     print(json.dumps(out), flush=True)

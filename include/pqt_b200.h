@@ -88,7 +88,9 @@ typedef struct pqt_stats {
   uint64_t scan_launches;   /* launches of the ADC scan kernel              */
   uint64_t exact_rank_queries; /* queries whose ranking needed the exact bitonic network
                                   (tied or >= 1e7 distances); all others use the fast sort */
-  uint64_t reserved[6];
+  uint64_t tie_resolved_queries; /* queries whose groups of bit-equal distances were put into
+                                    the network's order by the bit-plane simulation */
+  uint64_t reserved[5];
 } pqt_stats;
 
 /* ---- lifetime ------------------------------------------------------------- */

@@ -106,7 +106,7 @@ struct pqt_index {
   uint32_t* x_peer_idx[8] = {nullptr};
   bool x_ipc_opened[8] = {false};
   DevBuf d_sched;  // one uint32: work counter of the fused scan+rank kernel
-  DevBuf d_exact;  // one uint64: queries ranked by the exact-network fallback
+  DevBuf d_exact;  // two uint64: queries ranked by the exact-network fallback, queries with re-ordered ties
 
   // profiling
   bool profile = false;
@@ -556,6 +556,7 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
       g.out_dist = fused_out_dist;
       g.out_idx = fused_out_idx;
       g.exact_counter = h->d_exact.as<unsigned long long>();
+      g.tie_counter = h->d_exact.as<unsigned long long>() + 1;
       g.fast_rank = (P.rank_mode == 0) ? 1u : 0u;
       CU_TRY(h, h->d_sched.ensure(4));
       CU_TRY(h, cudaMemsetAsync(h->d_sched.p, 0, 4, h->stream));
@@ -744,7 +745,7 @@ int pqt_create(uint32_t dim, uint32_t p, uint32_t p2, int device, pqt_index** ou
     return PQT_ERR_CUDA;
   }
   for (auto& e : h->ev) cudaEventCreate(&e);
-  if (h->d_exact.ensure(8) != cudaSuccess || cudaMemset(h->d_exact.p, 0, 8) != cudaSuccess) {
+  if (h->d_exact.ensure(16) != cudaSuccess || cudaMemset(h->d_exact.p, 0, 16) != cudaSuccess) {
     pqt_destroy(h);
     return PQT_ERR_CUDA;
   }
@@ -1557,11 +1558,12 @@ int pqt_profile_enable(pqt_index* h, int on) {
 int pqt_get_stats(const pqt_index* h, pqt_stats* st) {
   if (!h || !st) return PQT_ERR_INVALID;
   *st = h->stats;
-  unsigned long long ex = 0;
+  unsigned long long ex[2] = {0, 0};
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  cudaMemcpy(&ex, h->d_exact.p, 8, cudaMemcpyDeviceToHost);
-  st->exact_rank_queries = ex;
+  cudaMemcpy(ex, h->d_exact.p, 16, cudaMemcpyDeviceToHost);
+  st->exact_rank_queries = ex[0];
+  st->tie_resolved_queries = ex[1];
   return PQT_OK;
 }
 int pqt_reset_stats(pqt_index* h) {
@@ -1569,7 +1571,7 @@ int pqt_reset_stats(pqt_index* h) {
   std::memset(&h->stats, 0, sizeof(h->stats));
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  cudaMemset(h->d_exact.p, 0, 8);
+  cudaMemset(h->d_exact.p, 0, 16);
   return PQT_OK;
 }
 int pqt_debug_enable(pqt_index* h, int on) {

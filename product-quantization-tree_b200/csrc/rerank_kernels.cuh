@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "query_kernels.cuh"
 #include "fast_rank.cuh"
+#include "tie_resolve.cuh"
 
 namespace pqtb {
 
@@ -530,6 +531,7 @@ struct RerankArgs {
   float* out_dist;    // [QN][k]
   uint32_t* out_idx;  // [QN][k]
   unsigned long long* exact_counter;  // queries ranked by the exact network (may be null)
+  unsigned long long* tie_counter;    // queries whose ties were re-ordered by tie_resolve (may be null)
   uint32_t fast_rank;                 // 1: composite-key sort first (fast_rank.cuh); 0: network only
   unsigned long long* phase_dbg;      // optional [QN][8] clock64 stamps per query (debug)
   uint32_t* next_query;               // work counter (zeroed before the launch): the thread groups
@@ -733,8 +735,14 @@ __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
     bool done = false;
     if (g.fast_rank && n2 >= kFastMinN2 && *s_bad == 0u) {
       FastRankState st{*s_min, *s_max};
-      const uint32_t f = fast_rank_emit(G, 1 + kRerankGroups + grp, s_val, s_cmp, s_fix, s_flag, nv, n2, g.k, st,
+      uint32_t f = fast_rank_emit(G, 1 + kRerankGroups + grp, s_val, s_cmp, s_fix, s_flag, nv, n2, g.k, st,
                                                 od, oi, cand, a.ids, ph);
+      if (ph && G.t == 0) ph[3] = clock64();
+      // bit-equal distances of different vectors: re-order them the way the network does
+      if (f == 1u && g.k >= nv && tie_resolve(G, s_val, s_cmp, s_flag, nv, a.max_vec, od, oi, cand, a.ids)) {
+        f = 0u;
+        if (G.t == 0 && g.tie_counter) atomicAdd(g.tie_counter, 1ull);
+      }
       done = (f == 0u);
       if (ph && G.t == 0) ph[5] = clock64();
     }

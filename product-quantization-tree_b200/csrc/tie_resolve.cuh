@@ -1,0 +1,225 @@
+// tie_resolve.cuh -- the reference network's order inside groups of bit-equal distances,
+// without running the network on the data.
+//
+// The reference ranks with a bitonic network whose compare-exchanges are strict
+// (pqt/bitonicSort.cuh:16-44: swap iff val[i] > val[ixj], resp. <), so candidates with
+// bit-equal distances are never swapped with each other and their final order depends on
+// how the rest of the input pushes them around.  For one group of equal distances (value v)
+// every comparator outcome that matters is decided by three classes: Lower (< v), Equal,
+// Higher (> v, pads included) -- a monotone image of the input, and the network commutes with
+// monotone maps.  The classes of all max_vec input positions are held as bit planes (one
+// 32-bit word per 32 positions, one thread per word) and the whole network is run on the
+// planes with bitwise operations: 32 comparators per instruction instead of one.  A third
+// plane carries which of the (two) different vectors an Equal position holds; it is moved by
+// the same swaps.  When the network is done the Equal positions are the group's output slots
+// and the label plane says which vector goes where.
+//
+// Handles groups with exactly two different vectors (any number of duplicates of each), up to
+// kTieMaxGroups groups per query; anything else is left to the caller (the full network).
+#pragma once
+#include "common.cuh"
+
+namespace pqtb {
+
+constexpr uint32_t kTieMaxGroups = 8;
+constexpr uint32_t kTieMaxLen = 64;
+
+// One network substage at bit distance j < 32 inside the 32-position words.
+//   M: positions with (pos & j) == 0; D: those of them that sit in a descending block
+__device__ __forceinline__ void tie_substage_inword(uint32_t& L, uint32_t& H, uint32_t& B, uint32_t j,
+                                                    uint32_t M, uint32_t D) {
+  const uint32_t aL = L & M, bL = (L >> j) & M;
+  const uint32_t aH = H & M, bH = (H >> j) & M;
+  const uint32_t aB = B & M, bB = (B >> j) & M;
+  const uint32_t gt = (aH & ~bH) | (~aL & bL);  // val[i] > val[ixj]   (classes L < E < H)
+  const uint32_t lt = (bH & ~aH) | (~bL & aL);  // val[i] < val[ixj]
+  const uint32_t sw = (gt & ~D) | (lt & D);
+  const uint32_t dL = (aL ^ bL) & sw, dH = (aH ^ bH) & sw, dB = (aB ^ bB) & sw;
+  L ^= dL | (dL << j);
+  H ^= dH | (dH << j);
+  B ^= dB | (dB << j);
+}
+
+// One network substage between this thread's word and the word of its partner (oL, oH, oB).
+__device__ __forceinline__ void tie_substage_xword(uint32_t& L, uint32_t& H, uint32_t& B, uint32_t oL,
+                                                   uint32_t oH, uint32_t oB, bool lo, bool desc) {
+  const uint32_t aL = lo ? L : oL, bL = lo ? oL : L;
+  const uint32_t aH = lo ? H : oH, bH = lo ? oH : H;
+  const uint32_t gt = (aH & ~bH) | (~aL & bL);
+  const uint32_t lt = (bH & ~aH) | (~bL & aL);
+  const uint32_t sw = desc ? lt : gt;
+  L ^= (L ^ oL) & sw;
+  H ^= (H ^ oH) & sw;
+  B ^= (B ^ oB) & sw;
+}
+
+// Re-orders the ids inside every group of bit-equal distances of one query's result the way
+// the reference's network (width max_vec, input = candidate order + 1e7 pads) leaves them.
+//   s_val[a]  : distance of candidate slot a (a < nv), candidate order
+//   s_scr     : scratch, max_vec words
+//   out_dist / out_idx: the query's first k results, sorted by distance (k >= nv: every real
+//               candidate is in the output); ids inside equal-distance groups in any order
+//   cand / ids: candidate slot -> bin-order position -> vector id
+// Every thread of the group must call.  Returns 1 when all groups were resolved, 0 when the
+// caller has to rank the query with the network itself.  g.n is a multiple of 128.
+__device__ __forceinline__ uint32_t tie_resolve(const Grp& g, const float* s_val, uint32_t* s_scr,
+                                                uint32_t* s_flag, uint32_t nv, uint32_t max_vec,
+                                                const float* out_dist, uint32_t* out_idx,
+                                                const uint32_t* __restrict__ cand,
+                                                const uint32_t* __restrict__ ids) {
+  const uint32_t t = g.t;
+  uint32_t* s_cnt = s_scr;           // [1]
+  uint32_t* s_gr = s_scr + 8;        // [kTieMaxGroups] first slot
+  uint32_t* s_gm = s_gr + 8;         // length
+  uint32_t* s_ga = s_gm + 8;         // first vector's id
+  uint32_t* s_gb = s_ga + 8;         // the other vector's id
+  uint32_t* s_planes = s_scr + 64;   // [teams][2][3][nW]: class planes / exchange buffer
+  const uint32_t teams = g.n >> 7;
+  const uint32_t nW = max_vec >> 5;  // words per plane
+  if (nW == 0u || 64u + 6u * teams * nW > max_vec) return 0u;  // scratch too small (uniform)
+  if (t == 0) *s_cnt = 0;
+  g.sync();
+  // ---- A. find the groups: slot e starts a tie when it repeats the distance of e-1 with a
+  // different id; the first such slot of a group registers the group
+  bool fail = false;
+  for (uint32_t e = t + 1u; e < nv; e += g.n) {
+    const float d1 = out_dist[e];
+    if (out_dist[e - 1] != d1 || out_idx[e - 1] == out_idx[e]) continue;
+    uint32_t r = e - 1u;
+    bool first = true;
+    while (r > 0u && out_dist[r - 1] == d1) {
+      if (out_idx[r - 1] != out_idx[r]) {
+        first = false;
+        break;
+      }
+      if (e - r > kTieMaxLen) break;
+      r--;
+    }
+    if (!first) continue;
+    if (e - r > kTieMaxLen) {
+      fail = true;
+      continue;
+    }
+    uint32_t m = e - r + 1u;
+    const uint32_t idA = out_idx[r], idB = out_idx[e];
+    while (r + m < nv && out_dist[r + m] == d1 && m <= kTieMaxLen) {
+      const uint32_t x = out_idx[r + m];
+      if (x != idA && x != idB) fail = true;  // a third vector
+      m++;
+    }
+    if (m > kTieMaxLen) fail = true;
+    const uint32_t slot = atomicAdd(s_cnt, 1u);
+    if (slot < kTieMaxGroups) {
+      s_gr[slot] = r;
+      s_gm[slot] = m;
+      s_ga[slot] = idA;
+      s_gb[slot] = idB;
+    } else {
+      fail = true;
+    }
+  }
+  if (fail) atomicOr(s_flag, 8u);
+  g.sync();
+  const uint32_t cnt = *s_cnt;
+  if ((*s_flag & 8u) || cnt == 0u) return 0u;
+
+  // ---- B. one team of 128 threads per group; thread x of a team owns word x of the planes
+  const uint32_t team = t >> 7, x = t & 127u, lane = t & 31u, wteam = x >> 5;
+  uint32_t* pl = s_planes + team * (6u * nW);
+  uint32_t* xb = pl + 3u * nW;
+  for (uint32_t g0 = 0; g0 < cnt; g0 += teams) {
+    const uint32_t gi = g0 + team;
+    const bool act = gi < cnt;
+    const uint32_t r = act ? s_gr[gi] : 0u, m = act ? s_gm[gi] : 0u;
+    const uint32_t idA = act ? s_ga[gi] : 0u, idB = act ? s_gb[gi] : 0u;
+    if (act) {
+      const float v = out_dist[r];
+      for (uint32_t w = wteam; w < nW; w += 4u) {
+        const uint32_t a = (w << 5) + lane;
+        const float val = a < nv ? s_val[a] : kPadDist;
+        const bool isL = val < v, isH = val > v;
+        bool isB = false;
+        if (!isL && !isH) isB = __ldg(ids + __ldg(cand + a)) != idA;
+        const uint32_t bl = __ballot_sync(0xffffffffu, isL);
+        const uint32_t bh = __ballot_sync(0xffffffffu, isH);
+        const uint32_t bb = __ballot_sync(0xffffffffu, isB);
+        if (lane == 0) {
+          pl[w] = bl;
+          pl[nW + w] = bh;
+          pl[2u * nW + w] = bb;
+        }
+      }
+    }
+    g.sync();
+    uint32_t L = 0, H = 0, B = 0;
+    if (act && x < nW) {
+      L = pl[x];
+      H = pl[nW + x];
+      B = pl[2u * nW + x];
+    }
+    // the network of pqt/bitonicSort.cuh:16-44 / :47-78: for k = 2..n, for j = k/2..1:
+    // pairs (i, i^j), ascending iff (i & k) == 0
+    for (uint32_t kk = 2u; kk <= max_vec; kk <<= 1) {
+      for (uint32_t j = kk >> 1; j > 0u; j >>= 1) {
+        if (j < 32u) {
+          const uint32_t M = j == 1u ? 0x55555555u : j == 2u ? 0x33333333u : j == 4u ? 0x0F0F0F0Fu
+                             : j == 8u ? 0x00FF00FFu : 0x0000FFFFu;
+          uint32_t D;
+          if (kk < 32u) {
+            const uint32_t Mk = kk == 2u ? 0x33333333u : kk == 4u ? 0x0F0F0F0Fu
+                                : kk == 8u ? 0x00FF00FFu : 0x0000FFFFu;
+            D = ~Mk & M;  // positions with (pos & kk) != 0
+          } else {
+            D = (x & (kk >> 5)) ? M : 0u;
+          }
+          tie_substage_inword(L, H, B, j, M, D);
+        } else {
+          const uint32_t wd = j >> 5;
+          uint32_t oL, oH, oB;
+          if (wd < 32u) {
+            oL = __shfl_xor_sync(0xffffffffu, L, wd);
+            oH = __shfl_xor_sync(0xffffffffu, H, wd);
+            oB = __shfl_xor_sync(0xffffffffu, B, wd);
+          } else {
+            if (x < nW) {
+              xb[x] = L;
+              xb[nW + x] = H;
+              xb[2u * nW + x] = B;
+            }
+            g.sync();
+            oL = oH = oB = 0u;
+            if (x < nW) {
+              oL = xb[x ^ wd];
+              oH = xb[nW + (x ^ wd)];
+              oB = xb[2u * nW + (x ^ wd)];
+            }
+            g.sync();
+          }
+          tie_substage_xword(L, H, B, oL, oH, oB, (x & wd) == 0u, (x & (kk >> 5)) != 0u);
+        }
+      }
+    }
+    // ---- the Equal positions are now the group's output slots r .. r+m-1
+    if (act && x < nW) {
+      const uint32_t base = x << 5;
+      uint32_t want = 0;
+      if (base < r + m && base + 32u > r) {
+        const uint32_t lo = r > base ? r - base : 0u;
+        const uint32_t hi = min(32u, r + m - base);
+        want = (hi >= 32u ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+      }
+      const uint32_t eq = ~(L | H);
+      if (eq != want) atomicOr(s_flag, 8u);  // cannot happen for a sorted result; be safe
+      uint32_t todo = want;
+      while (todo) {
+        const uint32_t b = __ffs(todo) - 1u;
+        todo &= todo - 1u;
+        out_idx[base + b] = ((B >> b) & 1u) ? idB : idA;
+      }
+    }
+    g.sync();
+  }
+  return (*s_flag & 8u) ? 0u : 1u;
+}
+
+}  // namespace pqtb

@@ -43,7 +43,8 @@ class Stats(C.Structure):
                 ("kernel_launches", C.c_uint64), ("ms_tables", C.c_double),
                 ("ms_bins", C.c_double), ("ms_scan", C.c_double), ("ms_sort", C.c_double),
                 ("ms_total", C.c_double), ("scan_launches", C.c_uint64),
-                ("exact_rank_queries", C.c_uint64), ("reserved", C.c_uint64 * 6)]
+                ("exact_rank_queries", C.c_uint64), ("tie_resolved_queries", C.c_uint64),
+                ("reserved", C.c_uint64 * 5)]
 
 
 class PqtError(RuntimeError):

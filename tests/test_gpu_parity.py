@@ -131,7 +131,9 @@ def test_dense_candidate_lists_fast_ranking(case_dense, k):
         assert np.array_equal(d1, d0), "rank_mode %d" % mode
         assert np.array_equal(i1, i0), "rank_mode %d" % mode
         if mode == 0:
-            assert st.exact_rank_queries < QN  # the network is the exception, not the rule
+            assert st.exact_rank_queries < QN // 8  # the network is the exception, not the rule
+            if k == 4096:
+                assert st.tie_resolved_queries > QN // 8  # ties re-ordered by the bit-plane simulation
         t.close()
 
 
