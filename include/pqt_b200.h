@@ -244,8 +244,8 @@ typedef enum pqt_stage {
   PQT_STAGE_BIG_BINS = 11,  /* uint32 [QN][candidate width] bins listed by getBIGBins2D (last BIG query) */
   PQT_STAGE_BIG_NBINS = 12, /* uint32 [QN] */
   PQT_STAGE_RERANK_PHASES = 13 /* uint64 [QN][8] clock64 stamps of the fused scan+rank kernel per
-                                  query: start, LUT ready, scan done, (unused), sort + emit done,
-                                  repair done, query done, (SM << 32 | nVec << 1 | fast) */
+                                  query: start, LUT ready, scan done, repair done, sort + emit done,
+                                  ties done, query done, (SM << 32 | nVec << 1 | fast) */
 } pqt_stage;
 int pqt_debug_enable(pqt_index *h, int on);
 int pqt_debug_stage(const pqt_index *h, int stage, void *host_out, size_t bytes);

@@ -242,8 +242,8 @@ __device__ __forceinline__ uint32_t fast_sort_emit(uint32_t t, uint32_t gn, uint
 //   s_fix   : scratch bitmap, one bit per result slot (128 words)
 //   cand[a] : bin-order position of candidate slot a (identifies the vector), ids[pos] its id
 // Writes the first k results (pads after nv).  Returns (to every thread of the group) a
-// flag word: bit 0 = some bit-equal distances belong to different vectors (their order in
-// the output is by candidate slot, not yet the network's), bit 1 = a run of colliding keys
+// flag word: bit 0 = some bit-equal distances may belong to different vectors (their order
+// in the output is by candidate slot, not yet the network's; tie_resolve checks), bit 1 = a run of colliding keys
 // was too long to repair (output incomplete).  g.n * 16 >= max_vec.
 __device__ __forceinline__ uint32_t fast_rank_emit(const Grp& g, uint32_t sub_bar, const float* s_val,
                                                    uint32_t* s_cmp, uint32_t* s_fix, uint32_t* s_flag,
@@ -280,33 +280,74 @@ __device__ __forceinline__ uint32_t fast_rank_emit(const Grp& g, uint32_t sub_ba
   // the neighbours with an equal truncated key: a fixed window, no data-dependent walk.
   // slots just past k can still move below k when a run straddles k
   const uint32_t e_end = k < nv ? min(nv, k + kFastRunMax) : min(k, nv);
-  const uint32_t W = 4096u / g.n;  // slots per thread: g.n * W covers every slot
+  // The marked slots are compacted into a list (which takes the place of the bitmap) so that
+  // every marked slot gets its own thread: thread w < 128 owns word w of the bitmap.
   uint32_t tie = 0;
+  uint32_t word = 0;
+  if (t < 128u) {
+    word = s_fix[t];
+    const uint32_t lo = t << 5;
+    if (lo >= e_end) word = 0u;
+    else if (lo + 32u > e_end) word &= (1u << (e_end - lo)) - 1u;
+  }
+  // exclusive prefix of the popcounts over threads 0..127 (4 warps; totals through s_flag+...)
+  uint32_t cntw = __popc(word);
+  uint32_t incl = cntw;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((t & 31u) >= (uint32_t)o) incl += n;
+  }
+  g.sync();  // every word has been read: the bitmap area becomes scratch
+  uint32_t* s_tot = s_fix;                                  // [4] warp totals
+  uint16_t* s_list = reinterpret_cast<uint16_t*>(s_fix + 4);  // [248] marked slots
+  constexpr uint32_t kListCap = 248;
+  if (t < 128u && (t & 31u) == 31u) s_tot[t >> 5] = incl;
+  g.sync();
+  uint32_t base = 0, total = 0;
   {
-    const uint32_t e0 = t * W;
-    uint32_t fx = e0 < e_end ? ((s_fix[e0 >> 5] >> (e0 & 31u)) & ((W < 32u) ? ((1u << W) - 1u) : 0xFFFFFFFFu)) : 0u;
-    while (fx) {
-      const uint32_t e = e0 + (uint32_t)__ffs(fx) - 1u;
-      fx &= fx - 1u;
-      if (e >= e_end) continue;
+    const uint32_t t0 = s_tot[0], t1 = s_tot[1], t2 = s_tot[2], t3 = s_tot[3];
+    total = t0 + t1 + t2 + t3;
+    const uint32_t wq = t >> 5;
+    base = (wq > 0u ? t0 : 0u) + (wq > 1u ? t1 : 0u) + (wq > 2u ? t2 : 0u);
+  }
+  const uint32_t my_first = base + incl - cntw;  // list index of this word's first marked slot
+  for (uint32_t r0 = 0; r0 < total; r0 += kListCap) {
+    if (r0) g.sync();  // the previous round's list has been consumed
+    if (t < 128u) {
+      uint32_t wv = word, li = my_first;
+      while (wv) {
+        const uint32_t bpos = __ffs(wv) - 1u;
+        wv &= wv - 1u;
+        if (li >= r0 && li < r0 + kListCap) s_list[li - r0] = (uint16_t)((t << 5) + bpos);
+        li++;
+      }
+    }
+    g.sync();
+    const uint32_t nlist = min(kListCap, total - r0);
+    for (uint32_t li = t; li < nlist; li += g.n) {
+      const uint32_t e = s_list[li];
       const uint32_t ce = s_cmp[e];
       const uint32_t a = ce & smask;
+      const uint32_t pe = __ldg(cand + a);  // in flight during the walk
       const float ve = s_val[a];
       const uint32_t u = sortable_key(ve);
-      const uint32_t pe = __ldg(cand + a);
+      // walk the run outwards from e (runs are short; longer ones were flagged)
       uint32_t before = 0, rank = 0;
-#pragma unroll 8
-      for (int d = -(int)kFastRunMax; d < (int)kFastRunMax; d++) {
-        const uint32_t j = e + (uint32_t)(d < 0 ? d : d + 1);  // wraps below 0: fails j < nv
-        const uint32_t cj = j < nv ? s_cmp[j] : ~ce;
-        const bool in_run = ((cj ^ ce) >> sb) == 0u;
-        const uint32_t aj = in_run ? (cj & smask) : a;
-        const uint32_t uj = sortable_key(s_val[aj]);
-        if (in_run) {
-          if (d < 0) before++;
-          if (uj < u || (uj == u && d < 0)) rank++;
-          if (uj == u && __ldg(cand + aj) != pe) tie = 1u;
-        }
+      for (uint32_t d = 1; d <= kFastRunMax && d <= e; d++) {
+        const uint32_t cj = s_cmp[e - d];
+        if (((cj ^ ce) >> sb) != 0u) break;
+        const uint32_t uj = sortable_key(s_val[cj & smask]);
+        before++;
+        if (uj <= u) rank++;
+        if (uj == u) tie = 1u;  // a duplicate of this vector or another vector: tie_resolve looks
+      }
+      for (uint32_t d = 1; d <= kFastRunMax && e + d < nv; d++) {
+        const uint32_t cj = s_cmp[e + d];
+        if (((cj ^ ce) >> sb) != 0u) break;
+        const uint32_t uj = sortable_key(s_val[cj & smask]);
+        if (uj < u) rank++;
+        if (uj == u) tie = 1u;
       }
       const uint32_t dst = e - before + rank;
       if (dst < k) {

@@ -80,48 +80,69 @@ __device__ __forceinline__ uint32_t tie_resolve(const Grp& g, const float* s_val
   if (t == 0) *s_cnt = 0;
   g.sync();
   // ---- A. find the groups: slot e starts a tie when it repeats the distance of e-1 with a
-  // different id; the first such slot of a group registers the group
+  // different id; the first such slot of a group registers the group.  A thread looks at
+  // kScan consecutive slots, all loads issued together.
   bool fail = false;
-  for (uint32_t e = t + 1u; e < nv; e += g.n) {
-    const float d1 = out_dist[e];
-    if (out_dist[e - 1] != d1 || out_idx[e - 1] == out_idx[e]) continue;
-    uint32_t r = e - 1u;
-    bool first = true;
-    while (r > 0u && out_dist[r - 1] == d1) {
-      if (out_idx[r - 1] != out_idx[r]) {
-        first = false;
-        break;
+  constexpr uint32_t kScan = 8;
+  for (uint32_t e0 = t * kScan; e0 < nv; e0 += g.n * kScan) {
+    float d[kScan + 1];
+    uint32_t id[kScan + 1];
+#pragma unroll
+    for (uint32_t i = 0; i <= kScan; i++) {
+      const uint32_t e = e0 + i - 1u;  // e0 == 0: wraps, fails the range test
+      const bool ok = e < nv;
+      d[i] = ok ? out_dist[e] : 0.f;
+      id[i] = ok ? out_idx[e] : 0u;
+    }
+    uint32_t hits = 0;
+#pragma unroll
+    for (uint32_t i = 1; i <= kScan; i++) {
+      const uint32_t e = e0 + i - 1u;
+      if (e > 0u && e < nv && d[i - 1] == d[i] && id[i - 1] != id[i]) hits |= 1u << (i - 1u);
+    }
+    while (hits) {
+      const uint32_t e = e0 + (uint32_t)__ffs(hits) - 1u;
+      hits &= hits - 1u;
+      const float d1 = out_dist[e];
+      uint32_t r = e - 1u;
+      bool first = true;
+      while (r > 0u && out_dist[r - 1] == d1) {
+        if (out_idx[r - 1] != out_idx[r]) {
+          first = false;
+          break;
+        }
+        if (e - r > kTieMaxLen) break;
+        r--;
       }
-      if (e - r > kTieMaxLen) break;
-      r--;
-    }
-    if (!first) continue;
-    if (e - r > kTieMaxLen) {
-      fail = true;
-      continue;
-    }
-    uint32_t m = e - r + 1u;
-    const uint32_t idA = out_idx[r], idB = out_idx[e];
-    while (r + m < nv && out_dist[r + m] == d1 && m <= kTieMaxLen) {
-      const uint32_t x = out_idx[r + m];
-      if (x != idA && x != idB) fail = true;  // a third vector
-      m++;
-    }
-    if (m > kTieMaxLen) fail = true;
-    const uint32_t slot = atomicAdd(s_cnt, 1u);
-    if (slot < kTieMaxGroups) {
-      s_gr[slot] = r;
-      s_gm[slot] = m;
-      s_ga[slot] = idA;
-      s_gb[slot] = idB;
-    } else {
-      fail = true;
+      if (!first) continue;
+      if (e - r > kTieMaxLen) {
+        fail = true;
+        continue;
+      }
+      uint32_t m = e - r + 1u;
+      const uint32_t idA = out_idx[r], idB = out_idx[e];
+      while (r + m < nv && out_dist[r + m] == d1 && m <= kTieMaxLen) {
+        const uint32_t x = out_idx[r + m];
+        if (x != idA && x != idB) fail = true;  // a third vector
+        m++;
+      }
+      if (m > kTieMaxLen) fail = true;
+      const uint32_t slot = atomicAdd(s_cnt, 1u);
+      if (slot < kTieMaxGroups) {
+        s_gr[slot] = r;
+        s_gm[slot] = m;
+        s_ga[slot] = idA;
+        s_gb[slot] = idB;
+      } else {
+        fail = true;
+      }
     }
   }
   if (fail) atomicOr(s_flag, 8u);
   g.sync();
   const uint32_t cnt = *s_cnt;
-  if ((*s_flag & 8u) || cnt == 0u) return 0u;
+  if (*s_flag & 8u) return 0u;
+  if (cnt == 0u) return 1u;  // only duplicates of one vector shared a distance: nothing to do
 
   // ---- B. one team of 128 threads per group; thread x of a team owns word x of the planes
   const uint32_t team = t >> 7, x = t & 127u, lane = t & 31u, wteam = x >> 5;

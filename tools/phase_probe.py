@@ -34,10 +34,11 @@ def main():
     nv = (ph[:, 7] & 0xFFFFFFFF) >> 1
     fast = ph[:, 7] & 1
     sm = ph[:, 7] >> 32
-    names = ["lut_wait", "scan", "sort+emit", "repair", "network/tail"]
+    names = ["lut_wait", "scan", "sort+emit", "repair", "ties", "network/tail"]
     d = np.stack([ph[:, 1] - ph[:, 0], ph[:, 2] - ph[:, 1],
                   np.where(ph[:, 4] > 0, ph[:, 4] - ph[:, 2], 0),
-                  np.where(ph[:, 5] > 0, ph[:, 5] - ph[:, 4], 0),
+                  np.where(ph[:, 3] > 0, ph[:, 3] - ph[:, 4], 0),
+                  np.where(ph[:, 5] > 0, ph[:, 5] - ph[:, 3], 0),
                   ph[:, 6] - np.where(ph[:, 5] > 0, ph[:, 5], ph[:, 2])], 1)
     tot = ph[:, 6] - ph[:, 0]
     print("queries", a.qn, "fast", int(fast.sum()), "mean nv", nv.mean())
