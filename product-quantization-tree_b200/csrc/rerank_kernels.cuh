@@ -290,9 +290,13 @@ __global__ void __launch_bounds__(kBins2Threads, 6) bins3_kernel(Bins3Args a) {
       if (threadIdx.x == 0) a.dbg_nbins[qi] = nb;
     }
 
-    // ---- Step E1 (:4339-4417)
+    // ---- Step E1 (:4339-4417).  The candidate slots of a chunk of bins are written by the
+    // whole CTA (slot -> bin by binary search over the chunk's exclusive scan): coalesced
+    // stores, and a bin with hundreds of vectors does not serialise one thread.
     uint32_t offset = 0;
     uint32_t* cand = a.cand_pos + (size_t)qi * a.max_vec;
+    uint32_t* s_pos = binbuf;                  // the probe buffer is free now
+    uint32_t* s_start = binbuf + kBins2Threads;
     for (uint32_t c0 = 0; c0 < nb && offset < a.max_vec; c0 += blockDim.x) {
       uint32_t b = c0 + threadIdx.x;
       uint32_t start = 0, nv = 0;
@@ -302,10 +306,21 @@ __global__ void __launch_bounds__(kBins2Threads, 6) bins3_kernel(Bins3Args a) {
         nv = cnt < a.max_vec_per_bin ? cnt : a.max_vec_per_bin;
       }
       uint32_t total;
-      uint32_t pos = offset + block_exscan(nv, warp_sums, total);
-      if (pos + nv > a.max_vec) nv = (pos >= a.max_vec) ? 0 : (a.max_vec - pos);
-      for (uint32_t v = 0; v < nv; v++) cand[pos + v] = start + v;
+      const uint32_t pos = offset + block_exscan(nv, warp_sums, total);
+      s_pos[threadIdx.x] = pos;
+      s_start[threadIdx.x] = start;
+      __syncthreads();
+      const uint32_t hi = offset + total < a.max_vec ? offset + total : a.max_vec;
+      for (uint32_t slot = offset + threadIdx.x; slot < hi; slot += blockDim.x) {
+        // the bin that holds this slot = the last one whose first slot is <= slot
+        uint32_t j = 0;
+#pragma unroll
+        for (uint32_t step = kBins2Threads >> 1; step > 0; step >>= 1)
+          if (s_pos[j + step] <= slot) j += step;
+        cand[slot] = s_start[j] + (slot - s_pos[j]);
+      }
       offset += total;
+      __syncthreads();
     }
     if (threadIdx.x == 0) a.n_vec[qi] = offset < a.max_vec ? offset : a.max_vec;
   }
