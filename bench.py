@@ -352,7 +352,7 @@ def run_b200(a, rank, world, local_rank):
     traffic = None
     try:  # DRAM bytes per launch from the committed ncu --set full capture of this workload
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if not sharded:
+        if not sharded and a.lineparts == 16:  # the captures are of the lineparts=16 workloads
             traffic = tj["rerank_kernel"].get(str(a.n), {}).get("bytes")
     except Exception:
         traffic = None
