@@ -112,6 +112,19 @@ __device__ __forceinline__ void block_sort_u32(uint32_t (&c)[E], uint32_t t, uin
   }
 }
 
+// Where a candidate slot's vector identity and id come from.  Fused single-GPU kernel:
+// slot -> bin-order position (cand) -> id (ids).  DIRECT (candidates assembled from shards):
+// ids[slot] is the id itself and doubles as the identity.
+template <bool DIRECT>
+__device__ __forceinline__ uint32_t slot_ident(const uint32_t* __restrict__ cand,
+                                               const uint32_t* __restrict__ ids, uint32_t a) {
+  return DIRECT ? __ldg(ids + a) : __ldg(cand + a);
+}
+template <bool DIRECT>
+__device__ __forceinline__ uint32_t ident_id(const uint32_t* __restrict__ ids, uint32_t ident) {
+  return DIRECT ? ident : __ldg(ids + ident);
+}
+
 constexpr uint32_t kFastRunMax = 16;  // slots on either side of one that a run of colliding truncated
                                       // keys may reach and still be repaired in place
 constexpr uint32_t kFastMinN2 = 128;  // shortest list the composite sort takes (32 threads x 4)
@@ -125,7 +138,7 @@ struct FastRankState {
 // unequal full keys are marked in s_fix and re-ordered afterwards by the caller.
 //   flag bits: 1 = bit-equal distances of different vectors seen, 2 = run too long to
 //   repair, 4 = some slots are marked in s_fix
-template <int E>
+template <int E, bool DIRECT>
 __device__ __forceinline__ uint32_t fast_sort_emit(uint32_t t, uint32_t gn, uint32_t sub_bar,
                                                    const float* s_val, uint32_t* s_cmp,
                                                    uint32_t* s_fix, uint32_t nv, uint32_t n2,
@@ -157,7 +170,7 @@ __device__ __forceinline__ uint32_t fast_sort_emit(uint32_t t, uint32_t gn, uint
     if (t > 0u && t * E - 1u < nv) {
       const uint32_t a = c_prev & smask;
       v_prev = s_val[a];
-      p_prev = __ldg(cand + a);
+      p_prev = slot_ident<DIRECT>(cand, ids, a);
     }
 #pragma unroll
     for (int h = 0; h < E / CH; h++) {
@@ -169,10 +182,10 @@ __device__ __forceinline__ uint32_t fast_sort_emit(uint32_t t, uint32_t gn, uint
         const uint32_t a = c[h * CH + i] & smask;
         const bool real = e0 + i < nv;
         v[i] = real ? s_val[a] : kPadDist;
-        ps[i] = real ? __ldg(cand + a) : 0u;
+        ps[i] = real ? slot_ident<DIRECT>(cand, ids, a) : 0u;
       }
 #pragma unroll
-      for (int i = 0; i < CH; i++) id[i] = (e0 + i < nv) ? __ldg(ids + ps[i]) : kPadIdx;
+      for (int i = 0; i < CH; i++) id[i] = (e0 + i < nv) ? ident_id<DIRECT>(ids, ps[i]) : kPadIdx;
       // boundaries between slot e0+i-1 and e0+i
       uint32_t bad = 0;
 #pragma unroll
@@ -245,6 +258,7 @@ __device__ __forceinline__ uint32_t fast_sort_emit(uint32_t t, uint32_t gn, uint
 // flag word: bit 0 = some bit-equal distances may belong to different vectors (their order
 // in the output is by candidate slot, not yet the network's; tie_resolve checks), bit 1 = a run of colliding keys
 // was too long to repair (output incomplete).  g.n * 16 >= max_vec.
+template <bool DIRECT>
 __device__ __forceinline__ uint32_t fast_rank_emit(const Grp& g, uint32_t sub_bar, const float* s_val,
                                                    uint32_t* s_cmp, uint32_t* s_fix, uint32_t* s_flag,
                                                    uint32_t nv, uint32_t n2, uint32_t k,
@@ -265,10 +279,10 @@ __device__ __forceinline__ uint32_t fast_rank_emit(const Grp& g, uint32_t sub_ba
   // is filled
   uint32_t flag;
   if (n2 >= 512u)
-    flag = fast_sort_emit<16>(t, g.n, sub_bar, s_val, s_cmp, s_fix, nv, n2, k, st.umin, shift, sb,
+    flag = fast_sort_emit<16, DIRECT>(t, g.n, sub_bar, s_val, s_cmp, s_fix, nv, n2, k, st.umin, shift, sb,
                               out_dist, out_idx, cand, ids);
   else
-    flag = fast_sort_emit<4>(t, g.n, sub_bar, s_val, s_cmp, s_fix, nv, n2, k, st.umin, shift, sb,
+    flag = fast_sort_emit<4, DIRECT>(t, g.n, sub_bar, s_val, s_cmp, s_fix, nv, n2, k, st.umin, shift, sb,
                              out_dist, out_idx, cand, ids);
   if (flag) atomicOr(s_flag, flag);
   g.sync();
@@ -329,7 +343,7 @@ __device__ __forceinline__ uint32_t fast_rank_emit(const Grp& g, uint32_t sub_ba
       const uint32_t e = s_list[li];
       const uint32_t ce = s_cmp[e];
       const uint32_t a = ce & smask;
-      const uint32_t pe = __ldg(cand + a);  // in flight during the walk
+      const uint32_t pe = slot_ident<DIRECT>(cand, ids, a);  // in flight during the walk
       const float ve = s_val[a];
       const uint32_t u = sortable_key(ve);
       // walk the run outwards from e (runs are short; longer ones were flagged)
@@ -352,7 +366,7 @@ __device__ __forceinline__ uint32_t fast_rank_emit(const Grp& g, uint32_t sub_ba
       const uint32_t dst = e - before + rank;
       if (dst < k) {
         out_dist[dst] = ve;
-        out_idx[dst] = __ldg(ids + pe);
+        out_idx[dst] = ident_id<DIRECT>(ids, pe);
       }
     }
   }

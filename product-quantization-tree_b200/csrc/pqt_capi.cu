@@ -637,7 +637,8 @@ int run_rank(pqt_index* h, const float* d_val, const uint32_t* d_idx, uint32_t Q
   a.val = d_val; a.idx = d_idx; a.QN = QN; a.max_vec = max_vec; a.k = k;
   a.out_dist = d_out_dist; a.out_idx = d_out_idx;
   a.exact_counter = h->d_exact.as<unsigned long long>();
-  size_t smem = (size_t)max_vec * 10 + 16;
+  a.fast_rank = (h->prm.rank_mode == 0) ? 1u : 0u;
+  size_t smem = rank2_smem_bytes(max_vec);
   if (smem > 48 * 1024)
     CU_TRY(h, cudaFuncSetAttribute(rank2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 4);
@@ -1465,7 +1466,7 @@ int pqt_shard_rank(pqt_index* h, const uint32_t* n_vec_own, uint32_t q_own, uint
     d_out_idx = h->s_outi.as<uint32_t>();
   }
   if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
-  size_t smem = (size_t)max_vec * 10 + 16;
+  size_t smem = rank2_smem_bytes(max_vec);
   if (smem > 48 * 1024)
     CU_TRY(h, cudaFuncSetAttribute(rank2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // host outputs: rank in slabs so that the device->host copy of one slab overlaps the
@@ -1497,6 +1498,7 @@ int pqt_shard_rank(pqt_index* h, const uint32_t* n_vec_own, uint32_t q_own, uint
     a.out_dist = d_out_dist + (size_t)q0 * k;
     a.out_idx = d_out_idx + (size_t)q0 * k;
     a.exact_counter = h->d_exact.as<unsigned long long>();
+    a.fast_rank = (h->prm.rank_mode == 0) ? 1u : 0u;
     a.n_vec = n_vec_own + q0;
     rank2_kernel<<<std::min<uint32_t>(n, (uint32_t)h->num_sms * 4), kRerankGroupThreads, smem, h->stream>>>(a);
     CU_TRY(h, cudaGetLastError());

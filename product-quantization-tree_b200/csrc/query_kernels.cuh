@@ -395,6 +395,54 @@ __global__ void __launch_bounds__(kBinsThreads) bins_kernel(BinsArgs a) {
 // LUT (c1*32 floats) is double-buffered with TMA bulk copies (cp.async.bulk +
 // mbarrier).
 // ============================================================================
+// ADC distances of the 32 candidates of one warp step (Step E2, :5277-5329).  `pos` = this
+// lane's candidate (code row; 0 for idle lanes: a valid row, result unused).  Lane = g*LP + lp
+// evaluates line part lp of the LP candidates of its lane group g, one after the other, and
+// the LP partial distances of all of them are then summed with the reference's pairwise tree
+// (warpReduceSum, :5183-5187: v += shfl_down(v, st), st = LP/2 .. 1) in one transposed
+// butterfly: at distance st a lane keeps the half of its partial sums whose candidate index
+// has bit st equal to its own lane bit and hands the other half to its partner, so every step
+// adds exactly the two operands the reference adds (fp32 addition is commutative) and lane lp
+// ends with candidate lp -- i.e. every lane returns the distance of its own candidate.
+//   codes_lp: code array + lp;  lut_b / cbd_b: shared-space byte address of this lane's column
+//   of the LUT (rows of 32 floats) / of the c^2 table (rows of CROW floats)
+template <int LP, uint32_t CROW>
+__device__ __forceinline__ float adc_warp_step(uint32_t pos, const uint32_t* __restrict__ codes_lp,
+                                               uint32_t lut_b, uint32_t cbd_b, uint32_t c1, uint32_t lp) {
+  float d[LP];
+  {
+    uint32_t w[LP];
+#pragma unroll
+    for (int s = 0; s < LP; s++) {
+      // position of candidate s of this lane group (shuffle inside the LP-lane segment)
+      const uint32_t cpos = __shfl_sync(0xffffffffu, pos, s, LP);
+      w[s] = __ldg(codes_lp + (size_t)cpos * LP);
+    }
+#pragma unroll
+    for (int s = 0; s < LP; s++) {
+      // lineDescr {p1, p2, lambda} (pqt/PerturbationProTree.hh:21-25)
+      const uint32_t p1 = w[s] & 0xFFu;
+      const uint32_t p2 = __byte_perm(w[s], 0u, 0x4441u);
+      const float lam = lambda_of(w[s]);
+      const float a2 = lds_f32(lut_b + (p1 << 7));
+      const float b2 = lds_f32(lut_b + (p2 << 7));
+      const float c2 = lds_f32(cbd_b + (p2 * c1 + p1) * (CROW * 4u));
+      d[s] = tri_dist(a2, b2, c2, lam);
+    }
+  }
+#pragma unroll
+  for (int st = LP >> 1; st > 0; st >>= 1) {
+    const bool up = (lp & (uint32_t)st) != 0u;
+#pragma unroll
+    for (int s = 0; s < st; s++) {
+      const float send = up ? d[s] : d[s + st];
+      const float keep = up ? d[s + st] : d[s];
+      d[s] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, st));
+    }
+  }
+  return d[0];
+}
+
 struct ScanArgs {
   const uint32_t* codes;     // [n_local][LP] line codes in bin order (this shard's slice)
   const uint32_t* ids;       // [n_local] vector id of each position
@@ -502,29 +550,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) adc_scan_kernel(ScanArgs a) {
       const uint32_t any_mine = __ballot_sync(0xffffffffu, mine);
       if (any_mine) {
         if (mine) myid = __ldg(a.ids + lpos);
-        // issue all code loads of the chunk first (LP independent 128-byte requests)
-        uint32_t w[LP];
-#pragma unroll
-        for (int s = 0; s < LP; s++) {
-          const uint32_t src = grp_base + s;
-          const uint32_t cpos = __shfl_sync(0xffffffffu, lpos, src);
-          const bool cm = (any_mine >> src) & 1u;
-          w[s] = cm ? __ldg(a.codes + (size_t)cpos * LP + lp) : 0u;
-        }
-#pragma unroll
-        for (int s = 0; s < LP; s++) {
-          const uint32_t p1 = w[s] & 0xFFu;         // lineDescr.p1 (pqt/PerturbationProTree.hh:21-25)
-          const uint32_t p2 = (w[s] >> 8) & 0xFFu;  // lineDescr.p2
-          const float lam = lambda_of(w[s]);
-          const float a2 = s_lut[p1 * 32 + lane];
-          const float b2 = s_lut[p2 * 32 + lane];
-          const float c2 = s_cbd[(p2 * a.c1 + p1) * 32 + lane];
-          float d = tri_dist(a2, b2, c2, lam);
-#pragma unroll
-          for (int st = LP >> 1; st > 0; st >>= 1)
-            d = __fadd_rn(d, __shfl_xor_sync(0xffffffffu, d, st));
-          if (lp == (uint32_t)s) myval = d;
-        }
+        myval = adc_warp_step<LP, 32u>(mine ? lpos : 0u, a.codes + lp, smem_u32(s_lut) + lane * 4u,
+                                       smem_u32(s_cbd) + lane * 4u, a.c1, lp);
       }
       float v;
       uint32_t id;
@@ -670,30 +697,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) adc_scan_p2p_kernel(ScanArgs 
       const bool valid = e < M;
       const uint32_t lpos = valid ? s_lpos[e] : 0u;
       const uint32_t ca = valid ? s_ca[e] : 0u;
-      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
       const uint32_t myid = valid ? __ldg(a.ids + lpos) : 0u;
-      uint32_t w[LP];
-#pragma unroll
-      for (int s = 0; s < LP; s++) {
-        const uint32_t src = grp_base + s;
-        const uint32_t cpos = __shfl_sync(0xffffffffu, lpos, src);
-        w[s] = ((vmask >> src) & 1u) ? __ldg(a.codes + (size_t)cpos * LP + lp) : 0u;
-      }
-      float myval = 0.f;
-#pragma unroll
-      for (int s = 0; s < LP; s++) {
-        const uint32_t p1 = w[s] & 0xFFu;
-        const uint32_t p2 = (w[s] >> 8) & 0xFFu;
-        const float lam = lambda_of(w[s]);
-        const float a2 = s_lut[p1 * 32 + lane];
-        const float b2 = s_lut[p2 * 32 + lane];
-        const float c2 = s_cbd[(p2 * a.c1 + p1) * 32 + lane];
-        float d = tri_dist(a2, b2, c2, lam);
-#pragma unroll
-        for (int st = LP >> 1; st > 0; st >>= 1)
-          d = __fadd_rn(d, __shfl_xor_sync(0xffffffffu, d, st));
-        if (lp == (uint32_t)s) myval = d;
-      }
+      const float myval = adc_warp_step<LP, 32u>(lpos, a.codes + lp, smem_u32(s_lut) + lane * 4u,
+                                                 smem_u32(s_cbd) + lane * 4u, a.c1, lp);
       if (valid) {
         oval[ca] = myval;  // peer store (NVLink) when the query is ranked by another GPU
         oidx[ca] = myid;

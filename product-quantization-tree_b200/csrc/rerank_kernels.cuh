@@ -682,45 +682,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
         const uint32_t cn = ca + nwarps * 32;
         pos_next = cn < nv ? __ldg(cand + cn) : 0u;
       }
-      float d[LP];
-      {
-        uint32_t w[LP];
-#pragma unroll
-        for (int s = 0; s < LP; s++) {
-          // position of candidate s of this lane group (shuffle inside the LP-lane segment)
-          const uint32_t cpos = __shfl_sync(0xffffffffu, pos, s, LP);
-          w[s] = __ldg(codes_lp + (size_t)cpos * LP);
-        }
-#pragma unroll
-        for (int s = 0; s < LP; s++) {
-          // lineDescr {p1, p2, lambda} (pqt/PerturbationProTree.hh:21-25); table rows are
-          // addressed in shared-space bytes: row * 128 (or LP * 4) + this lane's column
-          const uint32_t p1 = w[s] & 0xFFu;
-          const uint32_t p2 = __byte_perm(w[s], 0u, 0x4441u);
-          const float lam = lambda_of(w[s]);
-          const float a2 = lds_f32(lut_b + (p1 << 7));
-          const float b2 = lds_f32(lut_b + (p2 << 7));
-          const float c2 = lds_f32(cbd_b + (p2 * a.c1 + p1) * (CROW * 4u));
-          d[s] = tri_dist(a2, b2, c2, lam);
-        }
-      }
-      // Sum over the LP lanes of a candidate with the reference's pairwise tree
-      // (warpReduceSum, :5183-5187: v += shfl_down(v, st), st = LP/2 .. 1), for all LP
-      // candidates of the lane group at once: at distance st a lane keeps the half of its
-      // partial sums whose candidate index has bit st equal to its own lane bit and hands
-      // the other half to its partner, so every step adds exactly the two operands the
-      // reference adds (fp32 addition is commutative) and lane lp ends with candidate lp.
-#pragma unroll
-      for (int st = LP >> 1; st > 0; st >>= 1) {
-        const bool up = (lp & (uint32_t)st) != 0u;
-#pragma unroll
-        for (int s = 0; s < st; s++) {
-          const float send = up ? d[s] : d[s + st];
-          const float keep = up ? d[s + st] : d[s];
-          d[s] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, st));
-        }
-      }
-      const float myval = d[0];
+      const float myval = adc_warp_step<LP, CROW>(pos, codes_lp, lut_b, cbd_b, a.c1, lp);
       if (valid) {
         s_val[ca] = myval;
         const uint32_t u = sortable_key(myval);
@@ -750,11 +712,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
     bool done = false;
     if (g.fast_rank && n2 >= kFastMinN2 && *s_bad == 0u) {
       FastRankState st{*s_min, *s_max};
-      uint32_t f = fast_rank_emit(G, 1 + kRerankGroups + grp, s_val, s_cmp, s_fix, s_flag, nv, n2, g.k, st,
+      uint32_t f = fast_rank_emit<false>(G, 1 + kRerankGroups + grp, s_val, s_cmp, s_fix, s_flag, nv, n2, g.k, st,
                                                 od, oi, cand, a.ids, ph);
       if (ph && G.t == 0) ph[3] = clock64();
       // bit-equal distances of different vectors: re-order them the way the network does
-      if (f == 1u && g.k >= nv && tie_resolve(G, s_val, s_cmp, s_flag, nv, a.max_vec, od, oi, cand, a.ids)) {
+      if (f == 1u && g.k >= nv && tie_resolve<false>(G, s_val, s_cmp, s_flag, nv, a.max_vec, od, oi, cand, a.ids)) {
         f = 0u;
         if (G.t == 0 && g.tie_counter) atomicAdd(g.tie_counter, 1ull);
       }
@@ -782,46 +744,80 @@ struct Rank2Args {
   unsigned long long* exact_counter;
   const uint32_t* n_vec;  // optional [QN]: number of real candidates; slots beyond are padding
                           // and are NOT read (peer-store mode leaves them unwritten)
+  uint32_t fast_rank;     // 1: composite-key sort first; 0: the network only
 };
 
-__global__ void __launch_bounds__(kRerankGroupThreads) rank2_kernel(Rank2Args a) {
+inline size_t rank2_smem_bytes(uint32_t max_vec) { return (size_t)max_vec * 8 + 512 + 64; }
+
+__global__ void __launch_bounds__(kRerankGroupThreads, 2) rank2_kernel(Rank2Args a) {
   extern __shared__ float smem_f[];
   float* s_val = smem_f;
-  uint32_t* s_id = reinterpret_cast<uint32_t*>(s_val + a.max_vec);
-  uint32_t* s_flag = s_id + a.max_vec;
-  uint32_t* s_nv = s_flag + 1;
-  uint16_t* s_pay = reinterpret_cast<uint16_t*>(s_nv + 1);
+  uint32_t* s_cmp = reinterpret_cast<uint32_t*>(s_val + a.max_vec);  // sort words / network payloads
+  uint32_t* s_fix = s_cmp + a.max_vec;                               // [128] repair bitmap
+  uint32_t* s_misc = s_fix + 128;                                    // flag, nv, umin, umax, bad
+  uint32_t* s_flag = s_misc;
+  uint32_t* s_nv = s_misc + 1;
+  uint32_t* s_min = s_misc + 2;
+  uint32_t* s_max = s_misc + 3;
+  uint32_t* s_bad = s_misc + 4;
+  uint16_t* s_pay = reinterpret_cast<uint16_t*>(s_cmp);
   const Grp G{threadIdx.x, blockDim.x, 0};
+  const uint32_t lane = threadIdx.x & 31u;
   for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
     __syncthreads();
-    if (threadIdx.x == 0) *s_nv = 0;
-    __syncthreads();
-    uint32_t nv;
-    if (a.n_vec) {
-      nv = min(a.n_vec[qi], a.max_vec);
-      for (uint32_t e = threadIdx.x; e < nv; e += blockDim.x) {
-        s_val[e] = a.val[(size_t)qi * a.max_vec + e];
-        s_id[e] = a.idx[(size_t)qi * a.max_vec + e];
-      }
-      __syncthreads();
-    } else {
-      // real candidates form a prefix: slots >= nVec hold (1e7, PAD)
-      uint32_t local = 0;
-      for (uint32_t e = threadIdx.x; e < a.max_vec; e += blockDim.x) {
-        const float v = a.val[(size_t)qi * a.max_vec + e];
-        const uint32_t id = a.idx[(size_t)qi * a.max_vec + e];
-        s_val[e] = v;
-        s_id[e] = id;
-        if (!(id == kPadIdx && v == kPadDist)) local = e + 1;
-      }
-      atomicMax(s_nv, local);
-      __syncthreads();
-      nv = *s_nv;
-      __syncthreads();
+    if (threadIdx.x == 0) {
+      *s_flag = 0;
+      *s_nv = 0;
+      *s_min = 0xFFFFFFFFu;
+      *s_max = 0u;
+      *s_bad = 0u;
     }
-    auto id_of = [&](uint32_t slot) { return s_id[slot]; };
-    rank_and_emit(G, s_val, s_pay, id_of, s_flag, nv, a.max_vec, a.k, a.out_dist + (size_t)qi * a.k,
-                  a.out_idx + (size_t)qi * a.k, a.exact_counter);
+    if (threadIdx.x < 128u) s_fix[threadIdx.x] = 0u;
+    __syncthreads();
+    const float* val_row = a.val + (size_t)qi * a.max_vec;
+    const uint32_t* idx_row = a.idx + (size_t)qi * a.max_vec;
+    // real candidates form a prefix: given (n_vec) or found (slots >= nVec hold (1e7, PAD))
+    const uint32_t limit = a.n_vec ? min(a.n_vec[qi], a.max_vec) : a.max_vec;
+    uint32_t local = 0, umin = 0xFFFFFFFFu, umax = 0u, bad = 0u;
+    for (uint32_t e = threadIdx.x; e < limit; e += blockDim.x) {
+      const float v = val_row[e];
+      s_val[e] = v;
+      const bool real = a.n_vec ? true : !(idx_row[e] == kPadIdx && v == kPadDist);
+      if (real) {
+        local = e + 1;
+        const uint32_t u = sortable_key(v);
+        umin = min(umin, u);
+        umax = max(umax, u);
+        if (!(v < kPadDist) || !(v > -__int_as_float(0x7f800000))) bad = 1u;
+      }
+    }
+    local = __reduce_max_sync(0xffffffffu, local);
+    umin = __reduce_min_sync(0xffffffffu, umin);
+    umax = __reduce_max_sync(0xffffffffu, umax);
+    bad = __any_sync(0xffffffffu, bad) ? 1u : 0u;
+    if (lane == 0) {
+      atomicMax(s_nv, local);
+      atomicMin(s_min, umin);
+      atomicMax(s_max, umax);
+      if (bad) atomicOr(s_bad, 1u);
+    }
+    __syncthreads();
+    const uint32_t nv = a.n_vec ? limit : *s_nv;
+    float* od = a.out_dist + (size_t)qi * a.k;
+    uint32_t* oi = a.out_idx + (size_t)qi * a.k;
+    auto id_of = [&](uint32_t slot) { return __ldg(idx_row + slot); };
+    const uint32_t n2 = nv ? pow2ceil(nv) : 0u;
+    bool done = false;
+    if (a.fast_rank && n2 >= kFastMinN2 && *s_bad == 0u) {
+      FastRankState st{*s_min, *s_max};
+      uint32_t f = fast_rank_emit<true>(G, 1, s_val, s_cmp, s_fix, s_flag, nv, n2, a.k, st, od, oi, nullptr,
+                                        idx_row, nullptr);
+      if (f == 1u && a.k >= nv && tie_resolve<true>(G, s_val, s_cmp, s_flag, nv, a.max_vec, od, oi, nullptr, idx_row))
+        f = 0u;
+      done = (f == 0u);
+    }
+    if (!done)
+      rank_and_emit(G, s_val, s_pay, id_of, s_flag, nv, a.max_vec, a.k, od, oi, a.exact_counter);
   }
 }
 

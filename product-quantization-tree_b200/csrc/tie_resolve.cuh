@@ -18,6 +18,7 @@
 // kTieMaxGroups groups per query; anything else is left to the caller (the full network).
 #pragma once
 #include "common.cuh"
+#include "fast_rank.cuh"
 
 namespace pqtb {
 
@@ -62,6 +63,8 @@ __device__ __forceinline__ void tie_substage_xword(uint32_t& L, uint32_t& H, uin
 //   cand / ids: candidate slot -> bin-order position -> vector id
 // Every thread of the group must call.  Returns 1 when all groups were resolved, 0 when the
 // caller has to rank the query with the network itself.  g.n is a multiple of 128.
+// DIRECT: ids[slot] is the id (see fast_rank.cuh).
+template <bool DIRECT>
 __device__ __forceinline__ uint32_t tie_resolve(const Grp& g, const float* s_val, uint32_t* s_scr,
                                                 uint32_t* s_flag, uint32_t nv, uint32_t max_vec,
                                                 const float* out_dist, uint32_t* out_idx,
@@ -160,7 +163,7 @@ __device__ __forceinline__ uint32_t tie_resolve(const Grp& g, const float* s_val
         const float val = a < nv ? s_val[a] : kPadDist;
         const bool isL = val < v, isH = val > v;
         bool isB = false;
-        if (!isL && !isH) isB = __ldg(ids + __ldg(cand + a)) != idA;
+        if (!isL && !isH) isB = ident_id<DIRECT>(ids, slot_ident<DIRECT>(cand, ids, a)) != idA;
         const uint32_t bl = __ballot_sync(0xffffffffu, isL);
         const uint32_t bh = __ballot_sync(0xffffffffu, isH);
         const uint32_t bb = __ballot_sync(0xffffffffu, isB);

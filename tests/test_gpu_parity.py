@@ -289,6 +289,29 @@ def test_sharded_scan_assembles_the_single_gpu_result(case_small):
     t.close()
 
 
+def test_rank_candidates_dense_lists_with_ties(case_dense):
+    """The shard ranking kernel (rank2_kernel) on assembled 4096-candidate lists: composite-key
+    sort + repair + tie resolver return the oracle's order, ties included; so does the
+    network-only mode."""
+    import torch
+    c = case_dense
+    QN, k = c["Q"].shape[0], 4096
+    d0, i0 = oracle_query(c, k)
+    Qd = torch.from_numpy(c["Q"]).cuda()
+    for mode in (0, 1):
+        t = make_gpu_index(c, rank_mode=mode)
+        mv = t.candidateWidth(k)
+        v = torch.empty((QN, mv), dtype=torch.float32, device="cuda")
+        i = torch.empty((QN, mv), dtype=torch.int32, device="cuda")
+        t.queryScanShard(Qd, QN, k, v, i)
+        oi = torch.zeros((QN, k), dtype=torch.int32, device="cuda")
+        od = torch.zeros((QN, k), dtype=torch.float32, device="cuda")
+        t.rankCandidates(v, i, QN, mv, k, oi, od)
+        assert np.array_equal(od.cpu().numpy(), d0), "rank_mode %d" % mode
+        assert np.array_equal(oi.cpu().numpy().view(np.uint32), i0), "rank_mode %d" % mode
+        t.close()
+
+
 def test_peer_store_shards_in_one_process(case_small):
     """The fused scan + exchange path with three shard handles on one device: every shard
     stores the distances of its own candidates straight into the owner's candidate arrays
