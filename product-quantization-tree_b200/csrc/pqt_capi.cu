@@ -642,7 +642,7 @@ int run_rank(pqt_index* h, const float* d_val, const uint32_t* d_idx, uint32_t Q
   if (smem > 48 * 1024)
     CU_TRY(h, cudaFuncSetAttribute(rank2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 4);
-  rank2_kernel<<<grid, kRerankGroupThreads, smem, h->stream>>>(a);
+  rank2_kernel<<<grid, kRank2Threads, smem, h->stream>>>(a);
   CU_TRY(h, cudaGetLastError());
   h->stats.kernel_launches++;
   return PQT_OK;
@@ -1500,7 +1500,7 @@ int pqt_shard_rank(pqt_index* h, const uint32_t* n_vec_own, uint32_t q_own, uint
     a.exact_counter = h->d_exact.as<unsigned long long>();
     a.fast_rank = (h->prm.rank_mode == 0) ? 1u : 0u;
     a.n_vec = n_vec_own + q0;
-    rank2_kernel<<<std::min<uint32_t>(n, (uint32_t)h->num_sms * 4), kRerankGroupThreads, smem, h->stream>>>(a);
+    rank2_kernel<<<std::min<uint32_t>(n, (uint32_t)h->num_sms * 4), kRank2Threads, smem, h->stream>>>(a);
     CU_TRY(h, cudaGetLastError());
     h->stats.kernel_launches++;
     if (!out_on_device) {

@@ -748,8 +748,9 @@ struct Rank2Args {
 };
 
 inline size_t rank2_smem_bytes(uint32_t max_vec) { return (size_t)max_vec * 8 + 512 + 64; }
+constexpr int kRank2Threads = 256;  // one query per CTA, 4 CTAs per SM
 
-__global__ void __launch_bounds__(kRerankGroupThreads, 2) rank2_kernel(Rank2Args a) {
+__global__ void __launch_bounds__(kRank2Threads, 4) rank2_kernel(Rank2Args a) {
   extern __shared__ float smem_f[];
   float* s_val = smem_f;
   uint32_t* s_cmp = reinterpret_cast<uint32_t*>(s_val + a.max_vec);  // sort words / network payloads
