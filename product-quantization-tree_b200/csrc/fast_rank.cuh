@@ -275,15 +275,19 @@ __device__ __forceinline__ uint32_t fast_rank_emit(const Grp& g, uint32_t sub_ba
   const uint32_t bits = 32u - (uint32_t)__clz((int)range);
   const uint32_t shift = bits > 32u - sb ? bits - (32u - sb) : 0u;
   // (s_flag and s_fix were cleared by the caller before the barrier that ended the scan)
-  // 16 elements per thread cost the fewest instructions; short lists take 4 so that a warp
-  // is filled
+  // Elements per thread: 16 cost the fewest instructions, fewer shorten the dependent chain
+  // of a query (the sorters are the only busy warps of their group in this phase), which is
+  // what counts while the SM has issue slots to spare.
   uint32_t flag;
-  if (n2 >= 512u)
+  if (n2 >= 4096u)
     flag = fast_sort_emit<16, DIRECT>(t, g.n, sub_bar, s_val, s_cmp, s_fix, nv, n2, k, st.umin, shift, sb,
-                              out_dist, out_idx, cand, ids);
+                                      out_dist, out_idx, cand, ids);
+  else if (n2 >= 2048u)
+    flag = fast_sort_emit<8, DIRECT>(t, g.n, sub_bar, s_val, s_cmp, s_fix, nv, n2, k, st.umin, shift, sb,
+                                     out_dist, out_idx, cand, ids);
   else
     flag = fast_sort_emit<4, DIRECT>(t, g.n, sub_bar, s_val, s_cmp, s_fix, nv, n2, k, st.umin, shift, sb,
-                             out_dist, out_idx, cand, ids);
+                                     out_dist, out_idx, cand, ids);
   if (flag) atomicOr(s_flag, flag);
   g.sync();
   if (ph && t == 0) ph[4] = clock64();
