@@ -237,6 +237,13 @@ __device__ __forceinline__ uint32_t fast_sort_emit(uint32_t t, uint32_t gn, uint
         }
       }
     }
+    // every thread is a sorter: the pads behind the sorters' slots are theirs as well
+    if (Ta == gn) {
+      for (uint32_t e = Ta * E + t; e < k; e += gn) {
+        out_dist[e] = kPadDist;
+        out_idx[e] = kPadIdx;
+      }
+    }
   } else {
     // the other threads of the group write the pads behind the sorters' slots
     const uint32_t first = Ta * E;

@@ -137,6 +137,29 @@ def test_dense_candidate_lists_fast_ranking(case_dense, k):
         t.close()
 
 
+def test_mid_length_candidate_lists_into_poisoned_outputs():
+    """Candidate lists of a few hundred to a few thousand entries with k = 4096: every output
+    slot, pads included, must be written (the outputs start out poisoned).  Covers the list
+    lengths at which every thread of a group sorts (no idle thread left for the pads)."""
+    import conftest
+    import torch
+    c = conftest.make_case(N=120000, QN=192, c1=32, c2=32, LP=16, hash_size=3000017,
+                           n_clusters=512, seed=9)
+    QN, k = c["Q"].shape[0], 4096
+    d0, i0 = oracle_query(c, k)
+    nv = (i0 != po.PAD_IDX).sum(1)
+    assert ((nv > 256) & (nv <= 1024)).any() and ((nv > 1024) & (nv <= 2048)).any(), np.percentile(nv, [0, 25, 50, 75, 100])
+    t = make_gpu_index(c)
+    Qd = torch.from_numpy(c["Q"]).cuda()
+    for poison in (0x7FC00000, 0):
+        oi = torch.full((QN, k), 0x12345678, dtype=torch.int32, device="cuda")
+        od = torch.full((QN, k), poison, dtype=torch.int32, device="cuda").view(torch.float32)
+        t.queryKNN(Qd, QN, k, oi, od)
+        assert np.array_equal(od.cpu().numpy(), d0)
+        assert np.array_equal(oi.cpu().numpy().view(np.uint32), i0)
+    t.close()
+
+
 def test_distances_at_or_above_the_pad_value(case_small):
     """Distances >= 1e7 sort behind / among the 1e7 padding in the reference's network."""
     c = dict(case_small)
