@@ -418,15 +418,26 @@ __device__ __forceinline__ float adc_warp_step(uint32_t pos, const uint32_t* __r
       const uint32_t cpos = __shfl_sync(0xffffffffu, pos, s, LP);
       w[s] = __ldg(codes_lp + (size_t)cpos * LP);
     }
+    // byte selector of the lambda conversion, pinned in a register for the whole step (the
+    // compiler would otherwise re-create it next to every use)
+    uint32_t sel;
+    asm volatile("mov.u32 %0, 0x7632;" : "=r"(sel));
 #pragma unroll
     for (int s = 0; s < LP; s++) {
-      // lineDescr {p1, p2, lambda} (pqt/PerturbationProTree.hh:21-25)
+      // lineDescr {p1, p2, lambda} (pqt/PerturbationProTree.hh:21-25); one multiply-add per
+      // table address: column base + row * row bytes
       const uint32_t p1 = w[s] & 0xFFu;
       const uint32_t p2 = __byte_perm(w[s], 0u, 0x4441u);
-      const float lam = lambda_of(w[s]);
-      const float a2 = lds_f32(lut_b + (p1 << 7));
-      const float b2 = lds_f32(lut_b + (p2 << 7));
-      const float c2 = lds_f32(cbd_b + (p2 * c1 + p1) * (CROW * 4u));
+      uint32_t aa, ab, ac, pr;
+      asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(aa) : "r"(p1), "r"(lut_b));
+      asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(ab) : "r"(p2), "r"(lut_b));
+      asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(pr) : "r"(p2), "r"(c1), "r"(p1));
+      asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ac) : "r"(pr), "n"(CROW * 4u), "r"(cbd_b));
+      // toFloat (pqt/triangle.cuh:14-18): u16 dropped into the mantissa of 2^23, one FFMA
+      const float lam = __fmaf_rn(__uint_as_float(__byte_perm(w[s], 0x4B000000u, sel)), 1.220703125e-4f, -1028.f);
+      const float a2 = lds_f32(aa);
+      const float b2 = lds_f32(ab);
+      const float c2 = lds_f32(ac);
       d[s] = tri_dist(a2, b2, c2, lam);
     }
   }
