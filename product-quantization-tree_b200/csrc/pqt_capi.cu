@@ -420,10 +420,14 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
       w.cb2T = h->d_cb2T.as<float>();
       size_t smem = (size_t)(h->dim + h->c1 * 32 + 2 * kTablesWarps * a.npC) * 4;
       uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 12);
-      switch (h->vl) {
-        case 8: tables_warp_kernel<8><<<grid, kTablesWarps * 32, smem, h->stream>>>(w); break;
-        case 16: tables_warp_kernel<16><<<grid, kTablesWarps * 32, smem, h->stream>>>(w); break;
-        default: tables_warp_kernel<32><<<grid, kTablesWarps * 32, smem, h->stream>>>(w); break;
+      if (h->vl == 32 && h->c1 == 32 && h->c2 == 32) {  // the SIFT-shaped configuration
+        tables_warp_kernel<32, 32><<<grid, kTablesWarps * 32, smem, h->stream>>>(w);
+      } else {
+        switch (h->vl) {
+          case 8: tables_warp_kernel<8, 0><<<grid, kTablesWarps * 32, smem, h->stream>>>(w); break;
+          case 16: tables_warp_kernel<16, 0><<<grid, kTablesWarps * 32, smem, h->stream>>>(w); break;
+          default: tables_warp_kernel<32, 0><<<grid, kTablesWarps * 32, smem, h->stream>>>(w); break;
+        }
       }
     } else {
       const uint32_t npMax = std::max(a.npA, a.npC);
@@ -1324,10 +1328,14 @@ int pqt_shard_candidates(pqt_index* h, const float* Q, int q_on_device, uint32_t
     w.cb2T = h->d_cb2T.as<float>();
     size_t smem = (size_t)(h->dim + h->c1 * 32 + 2 * kTablesWarps * a.npC) * 4;
     uint32_t grid = std::min<uint32_t>(nq, (uint32_t)h->num_sms * 12);
-    switch (h->vl) {
-      case 8: tables_warp_kernel<8><<<grid, kTablesWarps * 32, smem, h->stream>>>(w); break;
-      case 16: tables_warp_kernel<16><<<grid, kTablesWarps * 32, smem, h->stream>>>(w); break;
-      default: tables_warp_kernel<32><<<grid, kTablesWarps * 32, smem, h->stream>>>(w); break;
+    if (h->vl == 32 && h->c1 == 32 && h->c2 == 32) {
+      tables_warp_kernel<32, 32><<<grid, kTablesWarps * 32, smem, h->stream>>>(w);
+    } else {
+      switch (h->vl) {
+        case 8: tables_warp_kernel<8, 0><<<grid, kTablesWarps * 32, smem, h->stream>>>(w); break;
+        case 16: tables_warp_kernel<16, 0><<<grid, kTablesWarps * 32, smem, h->stream>>>(w); break;
+        default: tables_warp_kernel<32, 0><<<grid, kTablesWarps * 32, smem, h->stream>>>(w); break;
+      }
     }
     CU_TRY(h, cudaGetLastError());
     h->stats.kernel_launches++;

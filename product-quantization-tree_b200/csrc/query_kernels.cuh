@@ -900,18 +900,22 @@ __device__ __forceinline__ void warp_sort_regs(float* sv, uint32_t* si, uint32_t
   __syncwarp();
 }
 
-template <int VL>
+// CC != 0: c1 == c2 == CC known at compile time (codebook strides become immediate load
+// offsets, the entry -> (cell, centroid) split a shift); CC == 0: any c1, c2.
+template <int VL, int CC>
 __global__ void __launch_bounds__(kTablesWarps * 32) tables_warp_kernel(TablesWarpArgs w) {
   const TablesArgs& a = w.t;
+  const uint32_t c1 = CC ? (uint32_t)CC : a.c1;
+  const uint32_t c2 = CC ? (uint32_t)CC : a.c2;
   extern __shared__ float smem_f[];
   float* sq = smem_f;                                   // [dim]
   float* s_lut = sq + a.dim;                            // [c1*32]
-  float* s_sortv = s_lut + a.c1 * 32;                   // [warps][npC]
+  float* s_sortv = s_lut + c1 * 32;                   // [warps][npC]
   uint32_t* s_sorti = reinterpret_cast<uint32_t*>(s_sortv + kTablesWarps * a.npC);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t segs = a.LP / a.p;  // line segments inside one part
   const uint32_t R = 32 / a.LP;
-  const uint32_t n = a.k1 * a.c2;
+  const uint32_t n = a.k1 * c2;
 
   for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
     __syncthreads();
@@ -926,12 +930,12 @@ __global__ void __launch_bounds__(kTablesWarps * 32) tables_warp_kernel(TablesWa
       // ---- Steps A + B: lane = L1 centroid
       float va = kPadSortA;
       uint32_t ia = kPadIdx;
-      if (lane < a.c1) {
+      if (lane < c1) {
         float s[VL], tb[VL];
-        const float* cb = w.cb1T + (size_t)(part * VL) * a.c1 + lane;
+        const float* cb = w.cb1T + (size_t)(part * VL) * c1 + lane;
 #pragma unroll
         for (int t = 0; t < VL; t++) {
-          float d = __fsub_rn(qreg[t], __ldg(cb + (size_t)t * a.c1));
+          float d = __fsub_rn(qreg[t], __ldg(cb + (uint32_t)t * c1));
           s[t] = __fmul_rn(d, d);
           tb[t] = s[t];
         }
@@ -949,7 +953,7 @@ __global__ void __launch_bounds__(kTablesWarps * 32) tables_warp_kernel(TablesWa
           if (((uint32_t)j & (a.sl - 1)) == 0) {
             const uint32_t lp = part * segs + (uint32_t)j / a.sl;
             for (uint32_t r = 0; r < R; r++) s_lut[lane * 32 + r * a.LP + lp] = tb[j];
-            if (a.dbg_lut) a.dbg_lut[((size_t)qi * a.LP + lp) * a.c1 + lane] = tb[j];
+            if (a.dbg_lut) a.dbg_lut[((size_t)qi * a.LP + lp) * c1 + lane] = tb[j];
           }
         }
         // Step A tree over vl (:7151-7159)
@@ -985,14 +989,14 @@ __global__ void __launch_bounds__(kTablesWarps * 32) tables_warp_kernel(TablesWa
         float v = kPadSortC;
         uint32_t id = kPadIdx;
         // all lanes take part in the shuffle; k is warp-uniform only when c2 >= 32
-        const uint32_t k = e < n ? e / a.c2 : 0, l2 = e < n ? e - k * a.c2 : 0;
+        const uint32_t k = e < n ? e / c2 : 0, l2 = e < n ? e - k * c2 : 0;
         const uint32_t l1 = __shfl_sync(0xffffffffu, ia, k);
         if (e < n) {
-          const float* cb = w.cb2T + ((size_t)(part * a.c1 + l1) * VL) * a.c2 + l2;
+          const float* cb = w.cb2T + ((size_t)(part * c1 + l1) * VL) * c2 + l2;
           float s[VL];
 #pragma unroll
           for (int t = 0; t < VL; t++) {
-            float d = __fsub_rn(qreg[t], __ldg(cb + (size_t)t * a.c2));
+            float d = __fsub_rn(qreg[t], __ldg(cb + (uint32_t)t * c2));
             s[t] = __fmul_rn(d, d);
           }
 #pragma unroll
@@ -1001,7 +1005,7 @@ __global__ void __launch_bounds__(kTablesWarps * 32) tables_warp_kernel(TablesWa
             for (int j = 0; j < stride; j++) s[j] = __fadd_rn(s[j], s[j + stride]);
           }
           v = s[0];
-          id = l2 + l1 * a.c2;
+          id = l2 + l1 * c2;
         }
         if (e < a.npC) {
           sv[e] = v;
@@ -1033,9 +1037,9 @@ __global__ void __launch_bounds__(kTablesWarps * 32) tables_warp_kernel(TablesWa
     }
     __syncthreads();
     // LUT rows out, coalesced
-    float4* dst = reinterpret_cast<float4*>(a.lut_dup + (size_t)qi * a.c1 * 32);
+    float4* dst = reinterpret_cast<float4*>(a.lut_dup + (size_t)qi * c1 * 32);
     const float4* src = reinterpret_cast<const float4*>(s_lut);
-    for (uint32_t e = threadIdx.x; e < a.c1 * 8; e += blockDim.x) dst[e] = src[e];
+    for (uint32_t e = threadIdx.x; e < c1 * 8; e += blockDim.x) dst[e] = src[e];
   }
 }
 
