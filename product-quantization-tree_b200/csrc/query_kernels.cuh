@@ -12,6 +12,7 @@
 // bit-for-bit against oracle/pqt_oracle.c.
 #pragma once
 #include "common.cuh"
+#include "fast_rank.cuh"
 
 namespace pqtb {
 
@@ -1013,14 +1014,61 @@ __global__ void __launch_bounds__(kTablesWarps * 32) tables_warp_kernel(TablesWa
         }
       }
       __syncwarp();
-      switch (a.npC) {  // :1639 bitonic3(shm, shmIdx, _NP2)
-        case 32: warp_sort_regs<1>(sv, si, lane); break;
-        case 64: warp_sort_regs<2>(sv, si, lane); break;
-        case 128: warp_sort_regs<4>(sv, si, lane); break;
-        case 256: warp_sort_regs<8>(sv, si, lane); break;
-        default: bitonic_warp_smem(sv, si, a.npC, lane); break;
+      // Only the 16 best entries are consumed unless a caller wants the sorted table (the 1-B
+      // variant, debug stages).  They are found with the composite-key sort of fast_rank.cuh:
+      // 24-bit order-preserving key | entry number, unsigned min/max compare-exchanges.  If
+      // two of the first 17 keys collide (equal or nearly equal distances: the network's own
+      // order would decide) the network below runs instead.
+      bool top16_done = false;
+      if (a.npC == 256 && !a.top_val && !a.dbg_aval) {
+        uint32_t c[8];
+        uint32_t umin = 0xFFFFFFFFu, umax = 0u;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+          const uint32_t e = lane * 8 + r;
+          c[r] = __float_as_uint(sv[e]);  // distances are sums of squares: >= +0, bits ordered
+          if (e < n) {
+            umin = min(umin, c[r]);
+            umax = max(umax, c[r]);
+          }
+        }
+        umin = __reduce_min_sync(0xffffffffu, umin);
+        umax = __reduce_max_sync(0xffffffffu, umax);
+        const uint32_t bits = 32u - (uint32_t)__clz((int)(umax - umin));
+        const uint32_t shift = bits > 24u ? bits - 24u : 0u;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+          const uint32_t e = lane * 8 + r;
+          c[r] = e < n ? ((((c[r] - umin) >> shift) << 8) | e) : 0xFFFFFFFFu;
+        }
+        block_sort_u32<8>(c, lane, 32u, 32u, nullptr, 0u);  // lane t: sorted slots 8t .. 8t+7
+        // slots 0..16 must have pairwise different keys
+        uint32_t clash = 0;
+#pragma unroll
+        for (int r = 0; r < 7; r++) clash |= (((c[r] ^ c[r + 1]) >> 8) == 0u) ? 1u : 0u;
+        const uint32_t nxt = __shfl_down_sync(0xffffffffu, c[0], 1);
+        clash |= (((c[7] ^ nxt) >> 8) == 0u) ? 1u : 0u;
+        if (!(__ballot_sync(0xffffffffu, clash != 0u) & 3u)) {
+          if (lane < 2) {
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+              const uint32_t slot = lane * 8 + r;
+              a.idx16[((size_t)qi * a.p + part) * 16 + slot] = (slot < a.m) ? si[c[r] & 0xFFu] : 0u;
+            }
+          }
+          top16_done = true;
+        }
       }
-      if (lane < 16) a.idx16[((size_t)qi * a.p + part) * 16 + lane] = (lane < a.m) ? si[lane] : 0u;
+      if (!top16_done) {
+        switch (a.npC) {  // :1639 bitonic3(shm, shmIdx, _NP2)
+          case 32: warp_sort_regs<1>(sv, si, lane); break;
+          case 64: warp_sort_regs<2>(sv, si, lane); break;
+          case 128: warp_sort_regs<4>(sv, si, lane); break;
+          case 256: warp_sort_regs<8>(sv, si, lane); break;
+          default: bitonic_warp_smem(sv, si, a.npC, lane); break;
+        }
+        if (lane < 16) a.idx16[((size_t)qi * a.p + part) * 16 + lane] = (lane < a.m) ? si[lane] : 0u;
+      }
       if (a.top_val) {
         for (uint32_t e = lane; e < a.top_n; e += 32) {
           a.top_val[((size_t)qi * a.p + part) * a.top_n + e] = sv[e];
