@@ -75,6 +75,7 @@ struct pqt_index {
   DevBuf g_bigbins, g_bignbins, g_phases;
   uint32_t dbg_big_QN = 0, dbg_big_cap = 0;
   DevBuf d_seqsorted;  // per 4096-batch, sorted by the ranks of all parts but the last (bins3)
+  DevBuf d_seqmega, d_seqplain;  // the same per 16384 codes + plain nibble codes (bins4)
   std::vector<uint32_t> h_distseq;
   uint32_t seq_m = 0, seq_p = 0;
 
@@ -212,6 +213,28 @@ int ensure_dist_seq(pqt_index* h, uint32_t max_cluster) {
     }
     CU_TRY(h, h->d_seqsorted.ensure(kNumDistSeq * sizeof(uint32_t)));
     CU_TRY(h, cudaMemcpyAsync(h->d_seqsorted.p, sorted.data(), kNumDistSeq * sizeof(uint32_t),
+                              cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    // bins4_kernel: the same order over mega-batches of 16384 codes, plus the nibble codes
+    // in plain traversal order (for the few kept probes)
+    std::vector<uint32_t> mega(kNumDistSeq, 0u), plain(kNumDistSeq, 0u);
+    std::vector<std::pair<uint32_t, uint32_t>> mkey(kBins4Mega);
+    for (uint32_t b = 0; b < kNumDistSeq / kBins4Mega; b++) {
+      for (uint32_t u = 0; u < (uint32_t)kBins4Mega; u++) {
+        uint32_t code = h->h_distseq[b * kBins4Mega + u], v = 0;
+        for (uint32_t j = 0; j < h->p; j++) v |= ((code / den[j]) % m) << (4 * j);
+        plain[b * kBins4Mega + u] = v;
+        uint32_t prefix = v & ((1u << last_shift) - 1u), last = v >> last_shift;
+        mkey[u] = std::make_pair((prefix << 4) | last, (u << 16) | v);
+      }
+      std::sort(mkey.begin(), mkey.end());
+      for (uint32_t e = 0; e < (uint32_t)kBins4Mega; e++) mega[b * kBins4Mega + e] = mkey[e].second;
+    }
+    CU_TRY(h, h->d_seqmega.ensure(kNumDistSeq * sizeof(uint32_t)));
+    CU_TRY(h, h->d_seqplain.ensure(kNumDistSeq * sizeof(uint32_t)));
+    CU_TRY(h, cudaMemcpyAsync(h->d_seqmega.p, mega.data(), kNumDistSeq * sizeof(uint32_t),
+                              cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->d_seqplain.p, plain.data(), kNumDistSeq * sizeof(uint32_t),
                               cudaMemcpyHostToDevice, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
   }
@@ -352,6 +375,69 @@ struct QueryPlan {
   const float* dQ;
 };
 
+// Steps D + E1 for p <= 4: bins4_kernel (visiting order sorted over 16384 codes) unless the
+// index is so dense that the walk would stop inside the first codes, where bins3_kernel
+// (early stop every 4096 codes) does less work.  Same output either way.
+int launch_bins_p4(pqt_index* h, const pqt_params& P, uint32_t max_vec, uint32_t nq,
+                   const uint32_t* idx16, uint32_t* cand_pos, uint32_t* n_vec, uint32_t* dbg_bins,
+                   uint32_t* dbg_nbins) {
+  const uint32_t n_probes = P.max_trials * P.bin_threads;
+  const double density = (double)h->n_nonempty / (double)std::max<uint32_t>(1u, h->db_hash_size);
+  const bool early_stop_likely = density * kBins3Batch * 2.0 >= (double)P.max_bins;
+  static const int force = getenv("PQT_BINS_KERNEL") ? atoi(getenv("PQT_BINS_KERNEL")) : 0;  // 3 / 4: A/B runs
+  const bool use4 = force == 4 || (force != 3 && !early_stop_likely && n_probes > kBins3Batch);
+  uint32_t grid = std::min<uint32_t>(nq, (uint32_t)h->num_sms * 6);
+  if (use4) {
+    Bins4Args a{};
+    a.idx16 = idx16;
+    a.seq_mega = h->d_seqmega.as<uint32_t>();
+    a.seq_plain = h->d_seqplain.as<uint32_t>();
+    a.dir.bitmap = h->d_bitmap.as<uint32_t>();
+    a.dir.rank_base = h->d_rank_base.as<uint32_t>();
+    a.dir.cprefix = h->d_cprefix.as<uint32_t>();
+    a.hash = make_magicmod(h->db_hash_size);
+    a.QN = nq; a.p = h->p; a.c1c2 = h->c1 * h->c2;
+    a.n_probes = n_probes;
+    a.max_bins = P.max_bins; a.max_vec_per_bin = P.max_vec_per_bin; a.max_vec = max_vec;
+    a.cand_pos = cand_pos; a.n_vec = n_vec; a.dbg_bins = dbg_bins; a.dbg_nbins = dbg_nbins;
+    const size_t smem = (size_t)(P.max_bins + kBins4Mega / 32 + 2 * 256 + 2 * kBins2Threads + 32) * 4;
+    if (h->p <= 2) {
+      if (smem > 48 * 1024)
+        CU_TRY(h, cudaFuncSetAttribute(bins4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      bins4_kernel<1><<<grid, kBins2Threads, smem, h->stream>>>(a);
+    } else {
+      if (smem > 48 * 1024)
+        CU_TRY(h, cudaFuncSetAttribute(bins4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      bins4_kernel<2><<<grid, kBins2Threads, smem, h->stream>>>(a);
+    }
+  } else {
+    Bins3Args a{};
+    a.idx16 = idx16;
+    a.seq_sorted = h->d_seqsorted.as<uint32_t>();
+    a.dir.bitmap = h->d_bitmap.as<uint32_t>();
+    a.dir.rank_base = h->d_rank_base.as<uint32_t>();
+    a.dir.cprefix = h->d_cprefix.as<uint32_t>();
+    a.hash = make_magicmod(h->db_hash_size);
+    a.QN = nq; a.p = h->p; a.c1c2 = h->c1 * h->c2;
+    a.n_probes = n_probes;
+    a.max_bins = P.max_bins; a.max_vec_per_bin = P.max_vec_per_bin; a.max_vec = max_vec;
+    a.cand_pos = cand_pos; a.n_vec = n_vec; a.dbg_bins = dbg_bins; a.dbg_nbins = dbg_nbins;
+    const size_t smem = (size_t)(P.max_bins + kBins3Batch + 2 * 256 + kBins3Batch / 32 + 32) * 4;
+    if (h->p <= 2) {
+      if (smem > 48 * 1024)
+        CU_TRY(h, cudaFuncSetAttribute(bins3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      bins3_kernel<1><<<grid, kBins2Threads, smem, h->stream>>>(a);
+    } else {
+      if (smem > 48 * 1024)
+        CU_TRY(h, cudaFuncSetAttribute(bins3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      bins3_kernel<2><<<grid, kBins2Threads, smem, h->stream>>>(a);
+    }
+  }
+  CU_TRY(h, cudaGetLastError());
+  h->stats.kernel_launches++;
+  return PQT_OK;
+}
+
 // Steps A..E2 (distance part) for QN queries already on the device; fills
 // val/idx [QN][max_vec].  Records profile events ev[0..3] when enabled.
 // With fused_out_* set (single GPU) the scan, the ranking and the first-k emit run in one
@@ -475,35 +561,9 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
     CU_TRY(h, cudaGetLastError());
     h->stats.kernel_launches++;
   } else if (h->p <= 4) {
-    Bins3Args a{};
-    a.idx16 = h->s_idx16.as<uint32_t>();
-    a.seq_sorted = h->d_seqsorted.as<uint32_t>();
-    a.dir.bitmap = h->d_bitmap.as<uint32_t>();
-    a.dir.rank_base = h->d_rank_base.as<uint32_t>();
-    a.dir.cprefix = h->d_cprefix.as<uint32_t>();
-    a.hash = make_magicmod(h->db_hash_size);
-    a.QN = QN; a.p = h->p; a.c1c2 = h->c1 * h->c2;
-    a.n_probes = P.max_trials * P.bin_threads;
-    a.max_bins = P.max_bins; a.max_vec_per_bin = P.max_vec_per_bin; a.max_vec = max_vec;
-    a.cand_pos = h->s_cand.as<uint32_t>();
-    a.n_vec = h->s_nvec.as<uint32_t>();
-    if (h->debug) {
-      a.dbg_bins = h->g_bins.as<uint32_t>();
-      a.dbg_nbins = h->g_nbins.as<uint32_t>();
-    }
-    size_t smem = (size_t)(P.max_bins + kBins3Batch + 2 * 256 + kBins3Batch / 32 + 32) * 4;
-    uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 6);
-    if (h->p <= 2) {
-      if (smem > 48 * 1024)
-        CU_TRY(h, cudaFuncSetAttribute(bins3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      bins3_kernel<1><<<grid, kBins2Threads, smem, h->stream>>>(a);
-    } else {
-      if (smem > 48 * 1024)
-        CU_TRY(h, cudaFuncSetAttribute(bins3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      bins3_kernel<2><<<grid, kBins2Threads, smem, h->stream>>>(a);
-    }
-    CU_TRY(h, cudaGetLastError());
-    h->stats.kernel_launches++;
+    PQ_TRY(launch_bins_p4(h, P, max_vec, QN, h->s_idx16.as<uint32_t>(), h->s_cand.as<uint32_t>(),
+                          h->s_nvec.as<uint32_t>(), h->debug ? h->g_bins.as<uint32_t>() : nullptr,
+                          h->debug ? h->g_nbins.as<uint32_t>() : nullptr));
   } else {
     Bins2Args a{};
     a.idx16 = h->s_idx16.as<uint32_t>();
@@ -762,7 +822,7 @@ int pqt_destroy(pqt_index* h) {
   if (!h) return PQT_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  for (DevBuf* b : {&h->d_cb1, &h->d_cb2, &h->d_cb1T, &h->d_cb2T, &h->d_distseq, &h->d_seqnib, &h->d_seqsorted, &h->d_seq2d, &h->s_topv, &h->s_topi, &h->g_bigbins, &h->g_bignbins, &h->d_bitmap, &h->d_rank_base, &h->d_cprefix,
+  for (DevBuf* b : {&h->d_cb1, &h->d_cb2, &h->d_cb1T, &h->d_cb2T, &h->d_distseq, &h->d_seqnib, &h->d_seqsorted, &h->d_seqmega, &h->d_seqplain, &h->d_seq2d, &h->s_topv, &h->s_topi, &h->g_bigbins, &h->g_bignbins, &h->d_bitmap, &h->d_rank_base, &h->d_cprefix,
                     &h->d_dbidx, &h->d_codes, &h->d_cbd, &h->d_cbd_dup, &h->s_q, &h->s_lut, &h->s_idx16,
                     &h->s_cand, &h->s_nvec, &h->s_val, &h->s_idx, &h->s_outd, &h->s_outi, &h->g_assign,
                     &h->g_lut, &h->g_aval, &h->g_aidx, &h->g_bins, &h->g_nbins, &h->g_sel, &h->d_exact, &h->x_val, &h->x_idx})
@@ -1354,33 +1414,8 @@ int pqt_shard_candidates(pqt_index* h, const float* Q, int q_on_device, uint32_t
     CU_TRY(h, cudaGetLastError());
   }
   if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[1], h->stream));
-  {
-    Bins3Args a{};
-    a.idx16 = h->s_idx16.as<uint32_t>();
-    a.seq_sorted = h->d_seqsorted.as<uint32_t>();
-    a.dir.bitmap = h->d_bitmap.as<uint32_t>();
-    a.dir.rank_base = h->d_rank_base.as<uint32_t>();
-    a.dir.cprefix = h->d_cprefix.as<uint32_t>();
-    a.hash = make_magicmod(h->db_hash_size);
-    a.QN = nq; a.p = h->p; a.c1c2 = h->c1 * h->c2;
-    a.n_probes = P.max_trials * P.bin_threads;
-    a.max_bins = P.max_bins; a.max_vec_per_bin = P.max_vec_per_bin; a.max_vec = max_vec;
-    a.cand_pos = cand_pos + (size_t)q_lo * max_vec;
-    a.n_vec = n_vec + q_lo;
-    size_t smem = (size_t)(P.max_bins + kBins3Batch + 2 * 256 + kBins3Batch / 32 + 32) * 4;
-    uint32_t grid = std::min<uint32_t>(nq, (uint32_t)h->num_sms * 6);
-    if (h->p <= 2) {
-      if (smem > 48 * 1024)
-        CU_TRY(h, cudaFuncSetAttribute(bins3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      bins3_kernel<1><<<grid, kBins2Threads, smem, h->stream>>>(a);
-    } else {
-      if (smem > 48 * 1024)
-        CU_TRY(h, cudaFuncSetAttribute(bins3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      bins3_kernel<2><<<grid, kBins2Threads, smem, h->stream>>>(a);
-    }
-    CU_TRY(h, cudaGetLastError());
-    h->stats.kernel_launches++;
-  }
+  PQ_TRY(launch_bins_p4(h, P, max_vec, nq, h->s_idx16.as<uint32_t>(), cand_pos + (size_t)q_lo * max_vec,
+                        n_vec + q_lo, nullptr, nullptr));
   if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   if (h->profile) {

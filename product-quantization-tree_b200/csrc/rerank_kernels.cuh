@@ -327,6 +327,155 @@ __global__ void __launch_bounds__(kBins2Threads, 6) bins3_kernel(Bins3Args a) {
 }
 
 // ============================================================================
+// Steps D + E1, v4 (p <= 4): as bins3_kernel, but the static visiting order is sorted over
+// 16384 traversal codes at once.  The 16 probes that share the ranks of all parts but the
+// last hit one 128-byte line of the bitmap; the traversal order spreads them over its
+// 4096-code batches, so bins3 touches that line in up to four batches (7429 line visits per
+// query) where one visit suffices (2913).  The walk is bound by L2 sector traffic, so this is
+// what counts; the price is that the early stop (max_bins kept) is only checked every
+// 16384 codes -- same output, more probes on indexes dense enough to stop early.
+// Kept probes are flagged in a bit array indexed by traversal position; their bins are
+// recomputed from the plain traversal table when the list is compacted (few are kept).
+// ============================================================================
+struct Bins4Args {
+  const uint32_t* idx16;      // [QN][p][16]
+  const uint32_t* seq_mega;   // [4 mega-batches][16384]: (position inside the mega-batch << 16) | nibble code
+  const uint32_t* seq_plain;  // [65536] nibble codes in traversal order
+  BinDir dir;
+  MagicMod hash;
+  uint32_t QN, p, c1c2;
+  uint32_t n_probes;
+  uint32_t max_bins, max_vec_per_bin, max_vec;
+  uint32_t* cand_pos;
+  uint32_t* n_vec;
+  uint32_t* dbg_bins;
+  uint32_t* dbg_nbins;
+};
+
+constexpr int kBins4Mega = 4 * kBins3Batch;  // 16384
+
+// dynamic smem: list[max_bins] | bits[512] | pairs[2][256] | stage[2][256] | warp_sums[32]
+template <int NPAIRS>
+__global__ void __launch_bounds__(kBins2Threads, 6) bins4_kernel(Bins4Args a) {
+  extern __shared__ uint32_t smem_u[];
+  uint32_t* list = smem_u;
+  uint32_t* bits = list + a.max_bins;
+  uint32_t* pairs = bits + kBins4Mega / 32;
+  uint32_t* s_pos = pairs + 2 * 256;
+  uint32_t* s_start = s_pos + kBins2Threads;
+  uint32_t* warp_sums = s_start + kBins2Threads;
+  const uint32_t K = a.c1c2;
+  const uint32_t p = a.p;
+  const uint32_t mul1 = (p == 4) ? K * K : K;
+  const uint32_t n_probes = a.n_probes, max_bins = a.max_bins;
+  const MagicMod hash = a.hash;
+  const uint32_t* __restrict__ bitmap = a.dir.bitmap;
+
+  for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
+    __syncthreads();
+    const uint32_t* gi = a.idx16 + (size_t)qi * p * 16;
+    for (uint32_t e = threadIdx.x; e < NPAIRS * 256; e += blockDim.x) {
+      uint32_t pr = e >> 8, r0 = e & 15, r1 = (e >> 4) & 15;
+      uint32_t j0 = 2 * pr, j1 = j0 + 1;
+      uint32_t v = __ldg(gi + j0 * 16 + r0);
+      if (j1 < p) v = v * K + __ldg(gi + j1 * 16 + r1);
+      pairs[e] = v;
+    }
+    if (threadIdx.x == 0) list[0] = 0;  // slot 0 keeps the memset value (:3561)
+    __syncthreads();
+
+    uint32_t n_out = 0;
+    for (uint32_t m0 = 0; m0 < n_probes && n_out < max_bins; m0 += kBins4Mega) {
+      bits[threadIdx.x] = 0;
+      bits[threadIdx.x + kBins2Threads] = 0;
+      __syncthreads();
+#pragma unroll 1
+      for (uint32_t b0 = m0; b0 < m0 + kBins4Mega; b0 += kBins3Batch) {
+        uint32_t words[kProbesPerThread];
+        uint32_t sh[kProbesPerThread / 4];
+#pragma unroll
+        for (int r = 0; r < kProbesPerThread / 4; r++) sh[r] = 0;
+#pragma unroll
+        for (int r = 0; r < kProbesPerThread; r++) {
+          const uint32_t ent = __ldg(a.seq_mega + b0 + r * kBins2Threads + threadIdx.x);
+          uint32_t o = pairs[ent & 0xFF];
+          if (NPAIRS == 2) o = o * mul1 + pairs[256 + ((ent >> 8) & 0xFF)];
+          const uint32_t bin = magicmod(o, hash);
+          sh[r >> 2] |= (bin & 31u) << (8 * (r & 3));
+          words[r] = (m0 + (ent >> 16) < n_probes) ? __ldg(bitmap + (bin >> 5)) : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < kProbesPerThread; r++) {
+          if ((words[r] >> ((sh[r >> 2] >> (8 * (r & 3))) & 31u)) & 1u) {
+            const uint32_t u = __ldg(a.seq_mega + b0 + r * kBins2Threads + threadIdx.x) >> 16;
+            atomicOr(&bits[u >> 5], 1u << (u & 31));
+          }
+        }
+      }
+      __syncthreads();
+      // ordered compaction in traversal order: thread i owns 64 consecutive positions
+      uint32_t w0 = bits[2 * threadIdx.x], w1 = bits[2 * threadIdx.x + 1];
+      uint32_t total;
+      uint32_t pos = n_out + block_exscan(__popc(w0) + __popc(w1), warp_sums, total);
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        uint32_t w = half ? w1 : w0;
+        while (w) {
+          const uint32_t bit = __ffs(w) - 1;
+          w &= w - 1;
+          pos++;  // inclusive-scan position: 1-based (:3504-3510)
+          if (pos < max_bins) {
+            const uint32_t code = __ldg(a.seq_plain + m0 + threadIdx.x * 64 + half * 32 + bit);
+            uint32_t o = pairs[code & 0xFF];
+            if (NPAIRS == 2) o = o * mul1 + pairs[256 + ((code >> 8) & 0xFF)];
+            list[pos] = magicmod(o, hash);
+          }
+        }
+      }
+      n_out += total;
+      __syncthreads();
+    }
+    __syncthreads();
+    const uint32_t nb = n_out < max_bins ? n_out : max_bins;
+    if (a.dbg_bins) {
+      for (uint32_t e = threadIdx.x; e < max_bins; e += blockDim.x)
+        a.dbg_bins[(size_t)qi * max_bins + e] =
+            (e == 0) ? 0u : ((e <= n_out && e < max_bins) ? list[e] : 0u);
+      if (threadIdx.x == 0) a.dbg_nbins[qi] = nb;
+    }
+
+    // ---- Step E1 (:4339-4417), as in bins3_kernel
+    uint32_t offset = 0;
+    uint32_t* cand = a.cand_pos + (size_t)qi * a.max_vec;
+    for (uint32_t c0 = 0; c0 < nb && offset < a.max_vec; c0 += blockDim.x) {
+      uint32_t b = c0 + threadIdx.x;
+      uint32_t start = 0, nv = 0;
+      if (b < nb) {
+        uint32_t cnt;
+        dir_lookup(a.dir, list[b], start, cnt);
+        nv = cnt < a.max_vec_per_bin ? cnt : a.max_vec_per_bin;
+      }
+      uint32_t total;
+      const uint32_t pos = offset + block_exscan(nv, warp_sums, total);
+      s_pos[threadIdx.x] = pos;
+      s_start[threadIdx.x] = start;
+      __syncthreads();
+      const uint32_t hi = offset + total < a.max_vec ? offset + total : a.max_vec;
+      for (uint32_t slot = offset + threadIdx.x; slot < hi; slot += blockDim.x) {
+        uint32_t j = 0;
+#pragma unroll
+        for (uint32_t step = kBins2Threads >> 1; step > 0; step >>= 1)
+          if (s_pos[j + step] <= slot) j += step;
+        cand[slot] = s_start[j] + (slot - s_pos[j]);
+      }
+      offset += total;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) a.n_vec[qi] = offset < a.max_vec ? offset : a.max_vec;
+  }
+}
+
+// ============================================================================
 // Thread group = a contiguous set of warps of a CTA that works on one query and
 // synchronises on its own named barrier (bar.sync id, n).  rerank_kernel runs two
 // groups of 512 threads per CTA on different queries so that the scan phase of one
