@@ -229,18 +229,27 @@ __device__ __forceinline__ bool dir_occupied(const BinDir& d, uint32_t bin) {
   return (__ldg(d.bitmap + (bin >> 5)) >> (bin & 31)) & 1u;
 }
 
-// (start, count) of a bin in the bin-ordered arrays; count 0 if empty
+// (start, count) of a bin in the bin-ordered arrays; count 0 if empty.  The 8 bitmap words of
+// the bin's 256-bin sector and the sector's rank base are fetched together (one dependent level
+// before the prefix look-up, no data-dependent load loop).
 __device__ __forceinline__ void dir_lookup(const BinDir& d, uint32_t bin, uint32_t& start,
                                            uint32_t& count) {
-  const uint32_t w = bin >> 5, g = bin >> 8;
-  uint32_t word = __ldg(d.bitmap + w);
+  const uint32_t g = bin >> 8, wi = (bin >> 5) & 7u;
+  const uint4* sec = reinterpret_cast<const uint4*>(d.bitmap + (g << 3));
+  const uint4 lo = __ldg(sec), hi = __ldg(sec + 1);
+  uint32_t r = __ldg(d.rank_base + g);
+  const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  uint32_t word = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < 8; i++) {
+    r += (i < wi) ? __popc(w[i]) : 0u;
+    word = (i == wi) ? w[i] : word;
+  }
   if (!((word >> (bin & 31)) & 1u)) {
     start = 0;
     count = 0;
     return;
   }
-  uint32_t r = __ldg(d.rank_base + g);
-  for (uint32_t ww = g << 3; ww < w; ww++) r += __popc(__ldg(d.bitmap + ww));
   r += __popc(word & ((1u << (bin & 31)) - 1u));
   start = __ldg(d.cprefix + r);
   count = __ldg(d.cprefix + r + 1) - start;
