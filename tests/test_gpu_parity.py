@@ -176,6 +176,10 @@ def test_truncation_budgets(case_small):
     _check_all_stages(case_small, 64, max_bins=8, max_vec_per_bin=3)
     _check_all_stages(case_small, 64, max_trials=1)
     _check_all_stages(case_small, 128, bin_threads=256, max_trials=7, k1=4)
+    # probe budgets that end inside / span several 16384-code visiting blocks (bins4_kernel)
+    _check_all_stages(case_small, 256, max_trials=5)
+    _check_all_stages(case_small, 256, max_trials=20)
+    _check_all_stages(case_small, 256, max_trials=64)
 
 
 def test_empty_index_and_single_query(case_small):
