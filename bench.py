@@ -43,8 +43,12 @@ def parse():
     ap.add_argument("--clusters", type=int, default=0,
                     help="cluster centres of the synthetic data (0 = max(4096, n // 256))")
     ap.add_argument("--train", type=int, default=300000)
-    ap.add_argument("--mode", default="shard", choices=["shard", "replica"],
-                    help="N>1: bin-range shards + NCCL exchange (north_star) or index replicas")
+    ap.add_argument("--mode", default="pull", choices=["pull", "shard", "replica"],
+                    help="N>1: 'pull' = index sharded by bin range, every rank answers its slice of "
+                         "the batch and reads the other shards' line codes over NVLink (no "
+                         "collective on the data path); 'shard' = same shards, candidate lists "
+                         "all-gathered and the scan results pushed to the query's owner; 'replica' "
+                         "= a full index per GPU")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -235,10 +239,18 @@ def run_b200(a, rank, world, local_rank):
         gt = synth_torch.brute_force_1nn(X8, Q8).cpu().numpy()
     del X8
     sharded = world > 1 and a.mode == "shard"
+    pull = world > 1 and a.mode == "pull"
     replica = world > 1 and a.mode == "replica"
-    if sharded:
+    if sharded or pull:
         assert QN % world == 0, "qn must be divisible by the number of ranks"
         t.setShard(rank, world)
+    if pull:
+        # every rank maps the code slices of the others (CUDA IPC); queries then run through the
+        # ordinary public call on each rank's slice of the batch
+        handles = [None] * world
+        dist.all_gather_object(handles, t.shardCodesHandle())
+        t.shardCodesOpen(handles)
+        dist.barrier()
     mv = t.candidateWidth(k)
     q_lo, q_hi = 0, QN
     if world > 1:
@@ -347,7 +359,7 @@ def run_b200(a, rank, world, local_rank):
     scan_ms = st.ms_scan / max(1, st.scan_launches)
     cand_per_launch = st.candidates / max(1, st.scan_launches)
     if sharded:
-        cand_per_launch /= world  # each rank scans its slice of the candidates
+        cand_per_launch /= world  # each rank scans its slice of the candidates of all queries
     achieved = cand_per_launch * bytes_per_cand / (scan_ms * 1e-3) / 1e9
     traffic = None
     try:  # DRAM bytes per launch from the committed ncu --set full capture of this workload
@@ -358,7 +370,7 @@ def run_b200(a, rank, world, local_rank):
         traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "kernel": "adc_scan_kernel" if sharded else "rerank_kernel (ADC scan + ranking fused)",
+                "kernel": "adc_scan_p2p_kernel" if sharded else "rerank_kernel (ADC scan + ranking fused)",
                 "peak_source": peak_src,
                 "ms_per_launch": scan_ms, "candidates_per_launch": cand_per_launch,
                 "bytes_per_candidate": bytes_per_cand,
@@ -385,11 +397,12 @@ def run_b200(a, rank, world, local_rank):
         "metric": "queries/sec", "value": QN * a.steps / (dev_ms * 1e-3), "unit": "queries/s",
         "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": dev_ms / a.steps, "higher_is_better": True,
-        "scaling": "strong" if sharded else "weak" if world > 1 else "strong",
+        "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "l2": "flushed between steps (256 MiB write)",
                    "parallelism": ("bin-range shards x%d, scan fused with peer-memory exchange (NVLink), NCCL all-gather of candidate lists" % world) if sharded
-                   else ("replicas x%d" % world) if replica else "single GPU",
+                   else ("bin-range shards x%d, batch split over the ranks, line codes of the other shards read over NVLink inside the fused scan kernel, no collective" % world) if pull
+                   else ("replicas x%d, batch split over the ranks" % world) if replica else "single GPU",
                    "index_build_s": build_s},
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -210,6 +210,17 @@ int pqt_shard_exchange_set_peers(pqt_index *h, uint32_t world, void *const *val_
 int pqt_shard_exchange_ptrs(pqt_index *h, void **val_ptr, void **idx_ptr);
 /* Q: all QN queries (device or host); cand_pos [QN][max_vec] / n_vec [QN]: DEVICE arrays,
  * rows [q_lo, q_hi) are written */
+/* Pull mode: the index stays sharded by bin range (pqt_set_shard), every rank answers its own
+ * slice of the query batch with pqt_query_knn and reads the line codes of the other shards from
+ * their memory (CUDA IPC mapping, NVLink loads inside the fused scan kernel).  No collective on
+ * the data path.  handle64 = 64-byte cudaIpcMemHandle_t of this rank's code slice; handles =
+ * world * 64 bytes in rank order; _set_peers / _ptr: the same with plain device pointers
+ * (several handles in one process). */
+int pqt_shard_codes_handle(pqt_index *h, void *handle64);
+int pqt_shard_codes_open(pqt_index *h, uint32_t world, const void *handles);
+int pqt_shard_codes_set_peers(pqt_index *h, uint32_t world, void *const *codes_ptrs);
+int pqt_shard_codes_ptr(pqt_index *h, void **codes_ptr);
+
 int pqt_shard_candidates(pqt_index *h, const float *Q, int q_on_device, uint32_t QN, uint32_t k,
                          uint32_t q_lo, uint32_t q_hi, uint32_t *cand_pos, uint32_t *n_vec);
 int pqt_shard_scan_p2p(pqt_index *h, uint32_t QN, uint32_t k, const uint32_t *cand_pos,

@@ -106,6 +106,10 @@ struct pqt_index {
   float* x_peer_val[8] = {nullptr};
   uint32_t* x_peer_idx[8] = {nullptr};
   bool x_ipc_opened[8] = {false};
+  // pull mode: the code slices of all shards (own slice + peers' slices mapped through CUDA IPC)
+  const uint32_t* c_peer[8] = {nullptr};
+  bool c_ipc_opened[8] = {false};
+  uint32_t c_world = 0;
   DevBuf d_sched;  // one uint32: work counter of the fused scan+rank kernel
   DevBuf d_exact;  // two uint64: queries ranked by the exact-network fallback, queries with re-ordered ties
 
@@ -629,6 +633,15 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
         CU_TRY(h, h->g_phases.ensure((size_t)QN * 8 * 8));
         g.phase_dbg = h->g_phases.as<unsigned long long>();
       }
+      const bool pull = h->world > 1;
+      if (pull) {
+        if (h->c_world != h->world) return fail(h, PQT_ERR_STATE, "code slices of the other shards are not connected");
+        if (h->LP != 16 && h->LP != 32) return fail(h, PQT_ERR_INVALID, "pull mode is built for lineparts 16 and 32");
+        g.n_shards = h->world;
+        for (uint32_t r = 0; r <= h->world; r++) g.shard_lo[r] = (uint32_t)((uint64_t)h->N * r / h->world);
+        for (uint32_t r = 0; r < h->world; r++) g.codes_adj[r] = h->c_peer[r] - (size_t)g.shard_lo[r] * h->LP;
+        g.s.ids = h->d_dbidx.as<uint32_t>();  // global positions
+      }
       const uint32_t ng = four ? 4u : 2u;
       uint32_t grid = std::min<uint32_t>((QN + ng - 1) / ng, (uint32_t)h->num_sms);
 #define LAUNCH_RERANK(LPV, NGV, CREPV)                                                           \
@@ -637,7 +650,21 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused)); \
     rerank_kernel<LPV, NGV, CREPV><<<grid, kScanThreads, smem_fused, h->stream>>>(g);            \
   } while (0)
-      if (four) {
+      if (pull) {
+        if (four) {
+          CU_TRY(h, cudaFuncSetAttribute(rerank_kernel<16, 4, false, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused));
+          rerank_kernel<16, 4, false, true><<<grid, kScanThreads, smem_fused, h->stream>>>(g);
+        } else if (h->LP == 16) {
+          CU_TRY(h, cudaFuncSetAttribute(rerank_kernel<16, 2, true, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused));
+          rerank_kernel<16, 2, true, true><<<grid, kScanThreads, smem_fused, h->stream>>>(g);
+        } else {
+          CU_TRY(h, cudaFuncSetAttribute(rerank_kernel<32, 2, true, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused));
+          rerank_kernel<32, 2, true, true><<<grid, kScanThreads, smem_fused, h->stream>>>(g);
+        }
+      } else if (four) {
         switch (h->LP) {
           case 1: LAUNCH_RERANK(1, 4, false); break;
           case 2: LAUNCH_RERANK(2, 4, false); break;
@@ -829,11 +856,13 @@ int pqt_destroy(pqt_index* h) {
     b->release();
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
-  for (uint32_t r = 0; r < 8; r++)
+  for (uint32_t r = 0; r < 8; r++) {
+    if (h->c_ipc_opened[r]) cudaIpcCloseMemHandle(const_cast<uint32_t*>(h->c_peer[r]));
     if (h->x_ipc_opened[r]) {
       cudaIpcCloseMemHandle(h->x_peer_val[r]);
       cudaIpcCloseMemHandle(h->x_peer_idx[r]);
     }
+  }
   for (auto& e : h->slab_ev) cudaEventDestroy(e);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1175,7 +1204,8 @@ static int query_common(pqt_index* h, const float* Q, int q_on_device, uint32_t 
     if (h->prm.big_k1 * h->c2 < kBigKMax) return fail(h, PQT_ERR_INVALID, "big_k1*c2 < 64: the 2-D merge reads 64 sorted entries per part (:3729)");
     if (pow2ceil(h->prm.big_k1 * h->c2) > 1024) return fail(h, PQT_ERR_INVALID, "big_k1*c2 > 1024");
   }
-  if (h->world != 1) return fail(h, PQT_ERR_STATE, "sharded handle: use pqt_query_scan_shard + pqt_rank_candidates");
+  if (h->world != 1 && (h->c_world != h->world || big))
+    return fail(h, PQT_ERR_STATE, "sharded handle: connect the code slices (pqt_shard_codes_open) for pqt_query_knn, or use pqt_shard_candidates / pqt_shard_scan_p2p / pqt_shard_rank");
   const uint32_t max_vec = candidate_width(h, k);
   const float* dQ = Q;
   if (!q_on_device) {
@@ -1345,6 +1375,54 @@ int pqt_shard_exchange_ptrs(pqt_index* h, void** val_ptr, void** idx_ptr) {
   if (!h->x_val.p) return fail(h, PQT_ERR_STATE, "pqt_shard_exchange_alloc first");
   *val_ptr = h->x_val.p;
   *idx_ptr = h->x_idx.p;
+  return PQT_OK;
+}
+
+// ---- multi-GPU, pull mode: every rank ranks its own queries and reads the line codes of the
+// other shards straight from their memory (NVLink); no collective on the data path -----------
+int pqt_shard_codes_handle(pqt_index* h, void* handle64) {
+  if (!h || !handle64) return PQT_ERR_INVALID;
+  if (!h->has_lines || !h->d_codes.p) return fail(h, PQT_ERR_STATE, "no line codes");
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaIpcMemHandle_t hc;
+  CU_TRY(h, cudaIpcGetMemHandle(&hc, h->d_codes.p));
+  std::memcpy(handle64, &hc, 64);
+  return PQT_OK;
+}
+
+int pqt_shard_codes_ptr(pqt_index* h, void** codes_ptr) {
+  if (!h || !codes_ptr) return PQT_ERR_INVALID;
+  if (!h->has_lines || !h->d_codes.p) return fail(h, PQT_ERR_STATE, "no line codes");
+  *codes_ptr = h->d_codes.p;
+  return PQT_OK;
+}
+
+int pqt_shard_codes_open(pqt_index* h, uint32_t world, const void* handles) {
+  if (!h || !handles || world == 0 || world > 8) return PQT_ERR_INVALID;
+  if (world != h->world) return fail(h, PQT_ERR_STATE, "world differs from pqt_set_shard");
+  if (!h->has_lines) return fail(h, PQT_ERR_STATE, "no line codes");
+  CU_TRY(h, cudaSetDevice(h->device));
+  for (uint32_t r = 0; r < world; r++) {
+    if (r == h->rank) {
+      h->c_peer[r] = h->d_codes.as<uint32_t>();
+      continue;
+    }
+    cudaIpcMemHandle_t hc;
+    std::memcpy(&hc, static_cast<const char*>(handles) + (size_t)r * 64, 64);
+    void* pc = nullptr;
+    CU_TRY(h, cudaIpcOpenMemHandle(&pc, hc, cudaIpcMemLazyEnablePeerAccess));
+    h->c_peer[r] = static_cast<const uint32_t*>(pc);
+    h->c_ipc_opened[r] = true;
+  }
+  h->c_world = world;
+  return PQT_OK;
+}
+
+int pqt_shard_codes_set_peers(pqt_index* h, uint32_t world, void* const* codes_ptrs) {
+  if (!h || !codes_ptrs || world == 0 || world > 8) return PQT_ERR_INVALID;
+  if (world != h->world) return fail(h, PQT_ERR_STATE, "world differs from pqt_set_shard");
+  for (uint32_t r = 0; r < world; r++) h->c_peer[r] = static_cast<const uint32_t*>(codes_ptrs[r]);
+  h->c_world = world;
   return PQT_OK;
 }
 

@@ -416,17 +416,27 @@ __global__ void __launch_bounds__(kBinsThreads) bins_kernel(BinsArgs a) {
 // ends with candidate lp -- i.e. every lane returns the distance of its own candidate.
 //   codes_lp: code array + lp;  lut_b / cbd_b: shared-space byte address of this lane's column
 //   of the LUT (rows of 32 floats) / of the c^2 table (rows of CROW floats)
-template <int LP, uint32_t CROW>
+// ROWS: the code rows of the candidates may live in different allocations (shards mapped
+// from peer GPUs): `row` = this lane's candidate's code row and the 64-bit pointer is
+// shuffled instead of the position.
+template <int LP, uint32_t CROW, bool ROWS = false>
 __device__ __forceinline__ float adc_warp_step(uint32_t pos, const uint32_t* __restrict__ codes_lp,
-                                               uint32_t lut_b, uint32_t cbd_b, uint32_t c1, uint32_t lp) {
+                                               uint32_t lut_b, uint32_t cbd_b, uint32_t c1, uint32_t lp,
+                                               const uint32_t* row = nullptr) {
   float d[LP];
   {
     uint32_t w[LP];
 #pragma unroll
     for (int s = 0; s < LP; s++) {
-      // position of candidate s of this lane group (shuffle inside the LP-lane segment)
-      const uint32_t cpos = __shfl_sync(0xffffffffu, pos, s, LP);
-      w[s] = __ldg(codes_lp + (size_t)cpos * LP);
+      if (ROWS) {
+        const unsigned long long rp =
+            __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)row, s, LP);
+        w[s] = __ldg(reinterpret_cast<const uint32_t*>((uintptr_t)rp) + lp);
+      } else {
+        // position of candidate s of this lane group (shuffle inside the LP-lane segment)
+        const uint32_t cpos = __shfl_sync(0xffffffffu, pos, s, LP);
+        w[s] = __ldg(codes_lp + (size_t)cpos * LP);
+      }
     }
     // byte selector of the lambda conversion, pinned in a register for the whole step (the
     // compiler would otherwise re-create it next to every use)

@@ -701,6 +701,12 @@ struct RerankArgs {
   uint32_t* next_query;               // work counter (zeroed before the launch): the thread groups
                                       // draw queries from it, so a slow query does not hold up a
                                       // statically assigned tail
+  // PULL mode (multi-GPU, index sharded by bin range): candidate positions are global; the code
+  // rows of shard r live at codes_adj[r] + pos * LP (codes_adj[r] = mapped slice - shard_lo[r]*LP),
+  // local or peer memory read over NVLink.  ids (s.ids) are indexed by global position.
+  uint32_t n_shards;
+  uint32_t shard_lo[9];
+  const uint32_t* codes_adj[8];
 };
 
 constexpr int kRerankGroups = 2;  // rank2_kernel / default configuration
@@ -716,7 +722,7 @@ inline size_t rerank_smem_bytes(uint32_t c1, uint32_t LP, uint32_t max_vec, int 
          (size_t)NG * ((size_t)8 * max_vec + 512 + 4 + 16 + 16) + 64;
 }
 
-template <int LP, int NG, bool CREP>
+template <int LP, int NG, bool CREP, bool PULL = false>
 __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
   const ScanArgs& a = g.s;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -831,7 +837,15 @@ __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
         const uint32_t cn = ca + nwarps * 32;
         pos_next = cn < nv ? __ldg(cand + cn) : 0u;
       }
-      const float myval = adc_warp_step<LP, CROW>(pos, codes_lp, lut_b, cbd_b, a.c1, lp);
+      float myval;
+      if (PULL) {
+        uint32_t r = 0;
+        for (uint32_t i = 1; i < g.n_shards; i++) r += (pos >= g.shard_lo[i]) ? 1u : 0u;
+        const uint32_t* row = g.codes_adj[r] + (size_t)pos * LP;
+        myval = adc_warp_step<LP, CROW, true>(0u, nullptr, lut_b, cbd_b, a.c1, lp, row);
+      } else {
+        myval = adc_warp_step<LP, CROW>(pos, codes_lp, lut_b, cbd_b, a.c1, lp);
+      }
       if (valid) {
         s_val[ca] = myval;
         const uint32_t u = sortable_key(myval);

@@ -23,6 +23,7 @@ EXPORTS = [
     "pqt_get_db_size", "pqt_set_shard", "pqt_query_scan_shard", "pqt_rank_candidates",
     "pqt_candidate_width", "pqt_shard_exchange_alloc", "pqt_shard_exchange_handle",
     "pqt_shard_exchange_open", "pqt_shard_exchange_set_peers", "pqt_shard_exchange_ptrs",
+    "pqt_shard_codes_handle", "pqt_shard_codes_open", "pqt_shard_codes_set_peers", "pqt_shard_codes_ptr",
     "pqt_shard_candidates", "pqt_shard_scan_p2p", "pqt_shard_rank", "pqt_profile_enable", "pqt_get_stats", "pqt_reset_stats",
     "pqt_debug_enable", "pqt_debug_stage",
 ]
@@ -109,6 +110,10 @@ def lib():
         L.pqt_shard_exchange_open.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.pqt_shard_exchange_set_peers.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.pqt_shard_exchange_ptrs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.pqt_shard_codes_handle.argtypes = [C.c_void_p, C.c_void_p]
+        L.pqt_shard_codes_open.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.pqt_shard_codes_set_peers.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.pqt_shard_codes_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.pqt_shard_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32,
                                            C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.pqt_shard_scan_p2p.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
@@ -317,6 +322,27 @@ class PerturbationProTree:
         va = (C.c_void_p * n)(*val_ptrs)
         ia = (C.c_void_p * n)(*idx_ptrs)
         self._chk(self._L.pqt_shard_exchange_set_peers(self._h, n, va, ia))
+
+    # ---- pull mode: code slices of the other shards mapped into this handle
+    def shardCodesHandle(self):
+        buf = C.create_string_buffer(64)
+        self._chk(self._L.pqt_shard_codes_handle(self._h, buf))
+        return buf.raw
+
+    def shardCodesOpen(self, handles):
+        """handles: list of 64-byte IPC handles, entry r from rank r"""
+        blob = b"".join(handles)
+        self._chk(self._L.pqt_shard_codes_open(self._h, len(handles), blob))
+
+    def shardCodesPtr(self):
+        p = C.c_void_p()
+        self._chk(self._L.pqt_shard_codes_ptr(self._h, C.byref(p)))
+        return p.value
+
+    def shardCodesSetPeers(self, ptrs):
+        n = len(ptrs)
+        pa = (C.c_void_p * n)(*ptrs)
+        self._chk(self._L.pqt_shard_codes_set_peers(self._h, n, pa))
 
     def shardCandidates(self, Q, QN, k, q_lo, q_hi, cand_pos, n_vec):
         qp, qdev = _ptr(Q)

@@ -316,6 +316,35 @@ def test_sharded_scan_assembles_the_single_gpu_result(case_small):
     t.close()
 
 
+@pytest.mark.parametrize("which", ["small", "lp32", "dense"])
+def test_pull_mode_shards_in_one_process(which, case_small, case_lp32, case_dense):
+    """Pull mode: the index cut into 3 bin-range shards (three handles on one device, wired
+    with plain device pointers instead of IPC handles); each handle answers a slice of the
+    queries with pqt_query_knn, reading the other shards' line codes from their memory.  The
+    result is the single-index result, ties included."""
+    import torch
+    c = {"small": case_small, "lp32": case_lp32, "dense": case_dense}[which]
+    QN = c["Q"].shape[0]
+    k = 4096 if which == "dense" else 256
+    d0, i0 = oracle_query(c, k)
+    world = 3
+    hs = [make_gpu_index(c, shard=(r, world)) for r in range(world)]
+    ptrs = [t.shardCodesPtr() for t in hs]
+    for t in hs:
+        t.shardCodesSetPeers(ptrs)
+    Qd = torch.from_numpy(c["Q"]).cuda()
+    per = (QN + world - 1) // world
+    for r, t in enumerate(hs):
+        lo, hi = r * per, min(QN, (r + 1) * per)
+        oi = torch.zeros((hi - lo, k), dtype=torch.int32, device="cuda")
+        od = torch.zeros((hi - lo, k), dtype=torch.float32, device="cuda")
+        t.queryKNN(Qd[lo:hi].contiguous(), hi - lo, k, oi, od)
+        assert np.array_equal(od.cpu().numpy(), d0[lo:hi]), "rank %d" % r
+        assert np.array_equal(oi.cpu().numpy().view(np.uint32), i0[lo:hi]), "rank %d" % r
+    for t in hs:
+        t.close()
+
+
 def test_rank_candidates_dense_lists_with_ties(case_dense):
     """The shard ranking kernel (rank2_kernel) on assembled 4096-candidate lists: composite-key
     sort + repair + tie resolver return the oracle's order, ties included; so does the
