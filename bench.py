@@ -246,11 +246,20 @@ def run_b200(a, rank, world, local_rank):
         t.setShard(rank, world)
     if pull:
         # every rank maps the code slices of the others (CUDA IPC); queries then run through the
-        # ordinary public call on each rank's slice of the batch
-        handles = [None] * world
-        dist.all_gather_object(handles, t.shardCodesHandle())
-        t.shardCodesOpen(handles)
-        dist.barrier()
+        # ordinary public call on each rank's slice of the batch.  If the mapping fails on any
+        # rank (peer access unavailable), all ranks fall back to the push pipeline.
+        ok = torch.ones(1, dtype=torch.int32, device=device)
+        try:
+            handles = [None] * world
+            dist.all_gather_object(handles, t.shardCodesHandle())
+            t.shardCodesOpen(handles)
+        except Exception as e:  # noqa: BLE001
+            print("rank %d: pull-mode setup failed (%r); falling back to --mode shard" % (rank, e),
+                  file=sys.stderr, flush=True)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            pull, sharded = False, True
     mv = t.candidateWidth(k)
     q_lo, q_hi = 0, QN
     if world > 1:
