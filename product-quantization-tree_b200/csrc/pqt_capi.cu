@@ -1221,8 +1221,10 @@ static int query_common(pqt_index* h, const float* Q, int q_on_device, uint32_t 
     d_out_dist = h->s_outd.as<float>();
     d_out_idx = h->s_outi.as<uint32_t>();
   }
-  const bool fused = ((size_t)h->c1 * h->c1 * 32 + kRerankGroups * 2 * (size_t)h->c1 * 32 +
-                      0) * 4 + kRerankGroups * (((size_t)10 * max_vec + 15) & ~(size_t)15) + 128 <= 227 * 1024;
+  // the fused scan + rank kernel needs its tables and candidate arrays in shared memory
+  // (same test as in run_scan_chain)
+  const bool fused = std::min(h->LP <= 16 ? rerank_smem_bytes(h->c1, h->LP, max_vec, 4, false) : ~(size_t)0,
+                              rerank_smem_bytes(h->c1, h->LP, max_vec, 2, true)) <= (size_t)227 * 1024;
   // Host outputs: queries go through in slabs so that the device->host copy of one slab
   // (on the copy stream) overlaps the kernels of the next.  Device outputs / debug
   // recording: one pass.
