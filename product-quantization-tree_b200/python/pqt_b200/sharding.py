@@ -17,6 +17,15 @@ def shard_bounds(n, rank, world):
     return (n * rank) // world, (n * (rank + 1)) // world
 
 
+def shard_of(pos, n, world):
+    """Shard that holds bin-order position `pos`: the rule of the pull-mode scan kernel
+    (rerank_kernel<..., PULL>: r = number of shard lower bounds 1..world-1 that are <= pos)."""
+    r = 0
+    for i in range(1, world):
+        r += 1 if pos >= (n * i) // world else 0
+    return r
+
+
 def query_slice(qn, rank, world):
     assert qn % world == 0, "the query batch must divide evenly over the ranks"
     per = qn // world

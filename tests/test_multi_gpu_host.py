@@ -83,3 +83,17 @@ def test_shard_bounds_cover_the_list_without_overlap():
     assert sharding.query_slice(10000, 3, 8) == (3750, 5000)
     with pytest.raises(AssertionError):
         sharding.query_slice(10, 0, 3)
+
+
+def test_pull_mode_shard_lookup_matches_the_shard_bounds():
+    """The pull-mode kernel finds the shard of a candidate position by counting lower bounds;
+    that must agree with the slices pqt_set_shard keeps, for every position and world size."""
+    for n in (1, 7, 1000, 12345, 1000003):
+        for world in range(1, 9):
+            bounds = [sharding.shard_bounds(n, r, world) for r in range(world)]
+            probe = sorted(set([0, n - 1] + [b for lo, hi in bounds for b in (lo - 1, lo, hi - 1, hi)
+                                             if 0 <= b < n]))
+            for pos in probe:
+                r = sharding.shard_of(pos, n, world)
+                lo, hi = bounds[r]
+                assert lo <= pos < hi, (n, world, pos, r)
