@@ -162,10 +162,45 @@ int pqt_build_kbest_db(pqt_index *h, const float *X, int x_on_device, uint32_t N
 /* lineDist(DB, N), :7663-7737 with an explicit LP (the reference hard-sets 16):
  * encodes and installs the line codes (same state as pqt_set_lines). */
 int pqt_line_dist(pqt_index *h, const float *X, int x_on_device, uint32_t N, uint32_t line_parts);
+/* ---- chunked build: the 1-B path (test/test1B.cpp:783-871) ------------------------------
+ * The reference's 1-B driver walks the base set in chunks of 10 M vectors: buildKBestDB on a
+ * chunk, append the chunk's bins behind the existing bin content with the ids offset by the
+ * chunk start (test/test1B.cpp:816-852), and lineDist per chunk.  The merged lists are the
+ * ids grouped by bin in ascending-id order, i.e. what one buildKBestDB over all N vectors
+ * gives; the entry points below produce exactly that without ever holding more than one
+ * chunk of raw vectors:
+ *   pass 1   pqt_assign_bins(chunk) -> bins of the chunk (any chunking, any rank)
+ *            pqt_set_db_from_bins(bin_of[N])       counts / prefix / dbIdx, installs the DB
+ *   pass 2   pqt_line_dist_begin(N, LP); pqt_line_dist_chunk(chunk, id0) ...; pqt_line_dist_end
+ * Rows are float (as the reference passes them) or the uint8 payload of a .umem file
+ * (utils/filereader.hpp:40-47 widens it on the host; here the kernels do).
+ * On a sharded handle (pqt_set_shard before pqt_set_db_from_bins) pass 2 encodes and keeps
+ * only the vectors of the own bin-range slice, so 8 ranks build a 1-B index without any of
+ * them holding the whole code array. */
+#define PQT_X_F32 0
+#define PQT_X_U8 1
+/* bins of n vectors (assignPerturbationBestBinKernel2 :830-942 after Step A with k1_build
+ * cells); bin_out: uint32[n], device pointer if out_on_device */
+int pqt_assign_bins(pqt_index *h, const void *X, int x_kind, int x_on_device, uint32_t n,
+                    uint32_t *bin_out, int out_on_device);
+/* countBins + scan + sortIdx (:1263-1300) over the bins of all N vectors (ascending id inside
+ * a bin); same state as pqt_set_db afterwards */
+int pqt_set_db_from_bins(pqt_index *h, const uint32_t *bin_of, int on_device, uint32_t N);
+int pqt_line_dist_begin(pqt_index *h, uint32_t N, uint32_t line_parts);
+/* rows = vectors id0 .. id0+n-1.  lines_out (HOST, may be NULL, unsharded handles only):
+ * lineDescr[n][LP] of the chunk in id order = the chunk's slice of the .lines file */
+int pqt_line_dist_chunk(pqt_index *h, const void *X, int x_kind, int x_on_device, uint32_t id0,
+                        uint32_t n, uint32_t *lines_out);
+int pqt_line_dist_end(pqt_index *h);
+
 /* getBinPrefix/getBinCounts/getDBIdx/getLine, pqt/PerturbationProTree.hh:97-101,
  * as host copies (any pointer may be NULL) */
 int pqt_get_db(const pqt_index *h, uint32_t *prefix, uint32_t *counts, uint32_t *db_idx);
 int pqt_get_lines(const pqt_index *h, uint32_t *lines);
+/* the resident line codes as stored: rows pos0 .. pos0+n-1 of this handle's slice of the
+ * BIN-ORDERED list (row r holds vector dbIdx[pos_lo + r]); HOST lineDescr[n][LP].  Unlike
+ * pqt_get_lines it needs no second copy on the device (1-B indexes). */
+int pqt_get_codes_binorder(const pqt_index *h, uint64_t pos0, uint64_t n, uint32_t *codes);
 int pqt_get_db_size(const pqt_index *h, uint32_t *N, uint32_t *line_parts);
 
 /* ---- multi-GPU: bin-range shards ---------------------------------------------- */

@@ -23,7 +23,7 @@ struct AssignBinsArgs {
   uint32_t N, dim, p, c1, c2, vl, k1, npA;
   FastMod hash;
   uint32_t* bin_of;  // [N]
-  uint32_t* counts;  // [hash_size], pre-zeroed
+  uint32_t* counts;  // [hash_size], pre-zeroed; null: no histogram
 };
 
 // dynamic smem: x[dim] | val[p*npA] | idx[p*npA] | assign[k1*p] | best[p]
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(128) assign_bins_kernel(AssignBinsArgs a) {
       for (uint32_t part = 1; part < a.p; part++) o = o * a.c1 * a.c2 + sbest[part];  // :929-931
       uint32_t bin = fastmod(o, a.hash);
       a.bin_of[i] = bin;
-      atomicAdd(a.counts + bin, 1u);
+      if (a.counts) atomicAdd(a.counts + bin, 1u);
     }
   }
 }
@@ -195,7 +195,8 @@ struct LineEncodeArgs {
   const float* X;       // [N][dim], indexed by vector id
   const float* cb1;     // [c1][dim]
   const float* cbd;     // [c1][c1][LP] canonical
-  const uint32_t* ids;  // [N] vector id at each bin-order position
+  const uint32_t* ids;  // [N] vector id at each bin-order position; null: row r is vector r
+                        // (chunked build: codes = the chunk's staging buffer in id order)
   uint32_t N, dim, c1, LP, sl;
   uint32_t* codes;  // [N][LP] in bin order
 };
@@ -211,7 +212,7 @@ __global__ void line_encode_kernel(LineEncodeArgs a) {
   const uint32_t lp = t / a.c1, c = t - lp * a.c1;
 
   for (uint32_t pos = blockIdx.x; pos < a.N; pos += gridDim.x) {
-    const uint32_t id = a.ids[pos];
+    const uint32_t id = a.ids ? a.ids[pos] : pos;
     __syncthreads();
     for (uint32_t e = t; e < a.dim; e += blockDim.x) sx[e] = a.X[(size_t)id * a.dim + e];
     __syncthreads();

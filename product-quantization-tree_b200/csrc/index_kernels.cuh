@@ -156,6 +156,30 @@ __global__ void cprefix_fill_kernel(const uint32_t* counts, const uint32_t* pref
   }
 }
 
+// ---- input validation (load path) -------------------------------------------------------
+// flag = 1 if any v[i] >= bound
+__global__ void check_below_kernel(const uint32_t* v, size_t n, uint32_t bound, uint32_t* flag) {
+  bool bad = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    bad |= v[i] >= bound;
+  if (bad) atomicOr(flag, 1u);
+}
+// flag = 1 if a non-empty bin's list [prefix, prefix + count) leaves the N ids
+__global__ void check_lists_kernel(const uint32_t* counts, const uint32_t* prefix, size_t hs, uint32_t N,
+                                   uint32_t* flag) {
+  bool bad = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hs; i += (size_t)gridDim.x * blockDim.x)
+    bad |= counts[i] != 0 && (uint64_t)prefix[i] + counts[i] > N;
+  if (bad) atomicOr(flag, 1u);
+}
+// flag = 1 if a lineDescr holds p1 or p2 >= c1
+__global__ void check_codes_kernel(const uint32_t* w, size_t n, uint32_t c1, uint32_t* flag) {
+  bool bad = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    bad |= ((w[i] & 0xFFu) >= c1) || (((w[i] >> 8) & 0xFFu) >= c1);
+  if (bad) atomicOr(flag, 1u);
+}
+
 // ---- bin-ordered re-layout of line codes -------------------------------------------
 // inv[id] = position of vector id in dbIdx
 __global__ void invert_perm_kernel(const uint32_t* db_idx, uint32_t N, uint32_t* inv) {

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "build_kernels.cuh"
+#include "build_fast_kernels.cuh"
 #include "common.cuh"
 #include "index_kernels.cuh"
 #include "query_kernels.cuh"
@@ -25,9 +26,29 @@ using namespace pqtb;
 
 namespace {
 
+// Owning device allocation (grow-only arena slot).  Move-only; frees on destruction, so the
+// temporaries of a call are released on every early (error) return as well.
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) {
+    o.p = nullptr;
+    o.bytes = 0;
+  }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) {
+      release();
+      p = o.p;
+      bytes = o.bytes;
+      o.p = nullptr;
+      o.bytes = 0;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
   cudaError_t ensure(size_t need) {
     if (need <= bytes) return cudaSuccess;
     if (p) cudaFree(p);
@@ -93,6 +114,9 @@ struct pqt_index {
   uint32_t LP = 0, sl = 0;
   DevBuf d_codes;  // [pos_hi - pos_lo][LP], bin order
   DevBuf d_cbd, d_cbd_dup;
+  // chunked line encoding in progress (pqt_line_dist_begin .. _end)
+  bool line_build = false;
+  DevBuf b_inv, b_stage, b_x;  // inv[N]: bin-order position of every id; per-chunk staging
 
   // per-batch scratch
   DevBuf s_q, s_lut, s_idx16, s_cand, s_nvec, s_val, s_idx, s_outd, s_outi;
@@ -304,6 +328,7 @@ int upload_tree(pqt_index* h) {
   }
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   h->has_lines = false;  // cbDist depends on cb1
+  h->has_db = false;     // the bin directory was built for the previous tree's c1 / c2 / p
   return PQT_OK;
 }
 
@@ -985,8 +1010,7 @@ int pqt_set_shard(pqt_index* h, uint32_t rank, uint32_t world) {
       CU_TRY(h, cudaMemcpyAsync(nb.p, h->d_codes.as<uint32_t>() + (size_t)(lo - h->pos_lo) * h->LP, bytes,
                                 cudaMemcpyDeviceToDevice, h->stream));
       CU_TRY(h, cudaStreamSynchronize(h->stream));
-      h->d_codes.release();
-      h->d_codes = nb;
+      h->d_codes = std::move(nb);
     }
     h->pos_lo = lo;
     h->pos_hi = hi;
@@ -1001,6 +1025,11 @@ int pqt_set_db(pqt_index* h, uint32_t N, const uint32_t* prefix, const uint32_t*
   if (!h || !prefix || !counts || !db_idx || !N) return PQT_ERR_INVALID;
   CU_TRY(h, cudaSetDevice(h->device));
   const uint32_t hs = h->prm.hash_size;
+  // the lists must stay inside the N ids (a .dbIdx shorter than what .prefix / .count describe
+  // would make the kernels read and write out of bounds)
+  if ((uint64_t)prefix[hs - 1] + counts[hs - 1] > N)
+    return fail(h, PQT_ERR_INVALID, "prefix/counts cover %llu vectors, N is only %u (hash_size %u)",
+                (unsigned long long)prefix[hs - 1] + counts[hs - 1], N, hs);
   DevBuf d_counts, d_prefix;
   CU_TRY(h, d_counts.ensure((size_t)hs * 4));
   CU_TRY(h, d_prefix.ensure((size_t)hs * 4));
@@ -1013,10 +1042,19 @@ int pqt_set_db(pqt_index* h, uint32_t N, const uint32_t* prefix, const uint32_t*
   }
   CU_TRY(h, h->d_dbidx.ensure((size_t)N * 4));
   CU_TRY(h, cudaMemcpyAsync(h->d_dbidx.p, db_idx, (size_t)N * 4, cudaMemcpyHostToDevice, h->stream));
-  int rc = build_directory(h, d_counts.as<uint32_t>(), d_prefix.as<uint32_t>(), hs, N);
-  d_counts.release();
-  d_prefix.release();
-  return rc;
+  {
+    DevBuf flag;
+    CU_TRY(h, flag.ensure(4));
+    CU_TRY(h, cudaMemsetAsync(flag.p, 0, 4, h->stream));
+    check_below_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->d_dbidx.as<uint32_t>(), N, N, flag.as<uint32_t>());
+    check_lists_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(d_counts.as<uint32_t>(), d_prefix.as<uint32_t>(), hs, N,
+                                                             flag.as<uint32_t>());
+    uint32_t bad = 0;
+    CU_TRY(h, cudaMemcpyAsync(&bad, flag.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (bad) return fail(h, PQT_ERR_INVALID, "dbIdx holds ids >= N = %u, or a bin's list leaves the N ids", N);
+  }
+  return build_directory(h, d_counts.as<uint32_t>(), d_prefix.as<uint32_t>(), hs, N);
 }
 
 int pqt_set_lines(pqt_index* h, const uint32_t* lines, uint32_t N, uint32_t line_parts) {
@@ -1037,16 +1075,22 @@ int pqt_set_lines(pqt_index* h, const uint32_t* lines, uint32_t N, uint32_t line
   invert_perm_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->d_dbidx.as<uint32_t>(), N, inv.as<uint32_t>());
   const uint32_t chunk = 4u << 20;
   CU_TRY(h, stage.ensure((size_t)std::min(chunk, N) * LP * 4));
+  DevBuf flag;
+  CU_TRY(h, flag.ensure(4));
+  CU_TRY(h, cudaMemsetAsync(flag.p, 0, 4, h->stream));
   for (uint32_t id0 = 0; id0 < N; id0 += chunk) {
     uint32_t n = std::min(chunk, N - id0);
     CU_TRY(h, cudaMemcpyAsync(stage.p, lines + (size_t)id0 * LP, (size_t)n * LP * 4, cudaMemcpyHostToDevice, h->stream));
+    // p1 / p2 index the shared-memory tables of the scan: they must be centroid numbers
+    check_codes_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(stage.as<uint32_t>(), (size_t)n * LP, h->c1, flag.as<uint32_t>());
     scatter_codes_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(
         stage.as<uint32_t>(), id0, n, LP, inv.as<uint32_t>(), h->pos_lo, h->pos_hi, h->d_codes.as<uint32_t>());
     CU_TRY(h, cudaStreamSynchronize(h->stream));  // staging buffer reuse
   }
   CU_TRY(h, cudaGetLastError());
-  inv.release();
-  stage.release();
+  uint32_t bad = 0;
+  CU_TRY(h, cudaMemcpy(&bad, flag.p, 4, cudaMemcpyDeviceToHost));
+  if (bad) return fail(h, PQT_ERR_INVALID, "line codes hold centroid numbers >= c1 = %u", h->c1);
   h->has_lines = true;
   return PQT_OK;
 }
@@ -1096,94 +1140,317 @@ int pqt_get_lines(const pqt_index* hc, uint32_t* lines) {
   return PQT_OK;
 }
 
-// ---- build side -----------------------------------------------------------------------
-int pqt_build_kbest_db(pqt_index* h, const float* X, int x_on_device, uint32_t N) {
-  if (!h || !X || !N) return PQT_ERR_INVALID;
+}  // extern "C"
+
+int pqt_get_codes_binorder(const pqt_index* hc, uint64_t pos0, uint64_t n, uint32_t* codes) {
+  pqt_index* h = const_cast<pqt_index*>(hc);
+  if (!h || !codes) return PQT_ERR_INVALID;
+  if (!h->has_lines) return fail(h, PQT_ERR_STATE, "no line codes");
+  if (pos0 + n > (uint64_t)(h->pos_hi - h->pos_lo)) return fail(h, PQT_ERR_INVALID, "rows exceed the resident slice");
   CU_TRY(h, cudaSetDevice(h->device));
-  if (!h->c1) return fail(h, PQT_ERR_STATE, "no tree loaded");
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaMemcpy(codes, h->d_codes.as<uint32_t>() + (size_t)pos0 * h->LP, (size_t)n * h->LP * 4,
+                       cudaMemcpyDeviceToHost));
+  return PQT_OK;
+}
+
+// ---- build side -----------------------------------------------------------------------
+namespace {
+
+
+__global__ void u8_to_f32_kernel(const uint8_t* in, size_t n, float* out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = (float)in[i];
+}
+
+size_t x_elem_bytes(int x_kind) { return x_kind == PQT_X_U8 ? 1 : 4; }
+
+// rows of a chunk on the device: the caller's pointer, or an upload into h->b_x
+int stage_rows(pqt_index* h, const void* X, int x_kind, int x_on_device, uint32_t n, const void** out) {
+  if (x_kind != PQT_X_F32 && x_kind != PQT_X_U8) return fail(h, PQT_ERR_INVALID, "x_kind must be PQT_X_F32 or PQT_X_U8");
+  if (x_on_device) {
+    *out = X;
+    return PQT_OK;
+  }
+  const size_t bytes = (size_t)n * h->dim * x_elem_bytes(x_kind);
+  CU_TRY(h, h->b_x.ensure(bytes));
+  CU_TRY(h, cudaMemcpyAsync(h->b_x.p, X, bytes, cudaMemcpyHostToDevice, h->stream));
+  *out = h->b_x.p;
+  return PQT_OK;
+}
+
+// float view of device rows for the generic (any-shape) kernels
+int rows_as_f32(pqt_index* h, const void* dX, int x_kind, uint32_t n, DevBuf& tmp, const float** out) {
+  if (x_kind == PQT_X_F32) {
+    *out = static_cast<const float*>(dX);
+    return PQT_OK;
+  }
+  const size_t ne = (size_t)n * h->dim;
+  CU_TRY(h, tmp.ensure(ne * 4));
+  u8_to_f32_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(static_cast<const uint8_t*>(dX), ne, tmp.as<float>());
+  CU_TRY(h, cudaGetLastError());
+  *out = tmp.as<float>();
+  return PQT_OK;
+}
+
+uint32_t build_grid(const pqt_index* h) { return ((uint32_t)h->num_sms * 2u) & ~3u; }
+
+// bins of n device rows -> d_bin (device)
+int launch_assign_bins(pqt_index* h, const void* dX, int x_kind, uint32_t n, uint32_t* d_bin) {
   const pqt_params& P = h->prm;
   if (P.k1_build > h->c1) return fail(h, PQT_ERR_INVALID, "k1_build %u > c1 %u (the reference needs c1 >= 16)", P.k1_build, h->c1);
-  const uint32_t hs = P.hash_size;
-  DevBuf dX, d_bin, d_counts, d_prefix, tmp;
-  const float* x = X;
-  if (!x_on_device) {
-    CU_TRY(h, dX.ensure((size_t)N * h->dim * 4));
-    CU_TRY(h, cudaMemcpyAsync(dX.p, X, (size_t)N * h->dim * 4, cudaMemcpyHostToDevice, h->stream));
-    x = dX.as<float>();
+  const bool fast = h->c1 <= 32 && h->c2 <= 32 && (h->vl == 8 || h->vl == 16 || h->vl == 32) &&
+                    (h->dim % 16) == 0 && ((uintptr_t)dX & 15u) == 0;
+  if (fast) {
+    AssignWarpArgs a{};
+    a.X = dX; a.n = n; a.dim = h->dim; a.p = h->p; a.c1 = h->c1; a.c2 = h->c2; a.k1 = P.k1_build;
+    a.cb1T = h->d_cb1T.as<float>(); a.cb2T = h->d_cb2T.as<float>();
+    a.hash = make_fastmod(P.hash_size);
+    a.bin_of = d_bin;
+    const uint32_t grid = build_grid(h), thr = kBuildWarpsPerCta * 32;
+    const bool cc32 = h->c1 == 32 && h->c2 == 32;
+#define LAUNCH_ASSIGN(XT)                                                                         \
+  do {                                                                                            \
+    if (h->vl == 32 && cc32) assign_bins_warp_kernel<XT, 32, 32><<<grid, thr, 0, h->stream>>>(a); \
+    else if (h->vl == 32) assign_bins_warp_kernel<XT, 32, 0><<<grid, thr, 0, h->stream>>>(a);     \
+    else if (h->vl == 16) assign_bins_warp_kernel<XT, 16, 0><<<grid, thr, 0, h->stream>>>(a);     \
+    else assign_bins_warp_kernel<XT, 8, 0><<<grid, thr, 0, h->stream>>>(a);                       \
+  } while (0)
+    if (x_kind == PQT_X_U8) LAUNCH_ASSIGN(uint8_t); else LAUNCH_ASSIGN(float);
+#undef LAUNCH_ASSIGN
+  } else {
+    DevBuf tmp;
+    const float* xf = nullptr;
+    PQ_TRY(rows_as_f32(h, dX, x_kind, n, tmp, &xf));
+    AssignBinsArgs a{};
+    a.X = xf; a.cb1 = h->d_cb1.as<float>(); a.cb2 = h->d_cb2.as<float>();
+    a.N = n; a.dim = h->dim; a.p = h->p; a.c1 = h->c1; a.c2 = h->c2; a.vl = h->vl;
+    a.k1 = P.k1_build; a.npA = pow2ceil(h->c1);
+    a.hash = make_fastmod(P.hash_size);
+    a.bin_of = d_bin;
+    a.counts = nullptr;
+    size_t smem = (size_t)(h->dim + 2 * h->p * a.npA + a.k1 * h->p + 2 * h->p * 4) * 4;
+    uint32_t grid = std::min<uint32_t>(n, (uint32_t)h->num_sms * 16);
+    assign_bins_kernel<<<grid, 128, smem, h->stream>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaStreamSynchronize(h->stream));  // tmp is freed on return
   }
-  CU_TRY(h, d_bin.ensure((size_t)N * 4));
+  CU_TRY(h, cudaGetLastError());
+  h->stats.kernel_launches++;
+  return PQT_OK;
+}
+
+// counts / exclusive prefix / ids grouped by bin (ascending id) from the bins of all N vectors;
+// installs the DB (same state as pqt_set_db)
+int install_db_from_bins(pqt_index* h, const uint32_t* d_bin, uint32_t N) {
+  const uint32_t hs = h->prm.hash_size;
+  DevBuf d_counts, d_prefix, tmp;
   CU_TRY(h, d_counts.ensure((size_t)hs * 4));
   CU_TRY(h, d_prefix.ensure((size_t)hs * 4));
   CU_TRY(h, tmp.ensure(scan_tmp_words(hs) * 4));
   CU_TRY(h, cudaMemsetAsync(d_counts.p, 0, (size_t)hs * 4, h->stream));
-  {
-    AssignBinsArgs a{};
-    a.X = x; a.cb1 = h->d_cb1.as<float>(); a.cb2 = h->d_cb2.as<float>();
-    a.N = N; a.dim = h->dim; a.p = h->p; a.c1 = h->c1; a.c2 = h->c2; a.vl = h->vl;
-    a.k1 = P.k1_build; a.npA = pow2ceil(h->c1);
-    a.hash = make_fastmod(hs);
-    a.bin_of = d_bin.as<uint32_t>();
-    a.counts = d_counts.as<uint32_t>();
-    size_t smem = (size_t)(h->dim + 2 * h->p * a.npA + a.k1 * h->p + 2 * h->p * 4) * 4;
-    uint32_t grid = std::min<uint32_t>(N, (uint32_t)h->num_sms * 16);
-    assign_bins_kernel<<<grid, 128, smem, h->stream>>>(a);
-    CU_TRY(h, cudaGetLastError());
-  }
+  bin_histogram_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(d_bin, N, d_counts.as<uint32_t>());
+  CU_TRY(h, cudaGetLastError());
   device_exscan_u32(d_counts.as<uint32_t>(), d_prefix.as<uint32_t>(), hs, tmp.as<uint32_t>(), h->stream);
   CU_TRY(h, h->d_dbidx.ensure((size_t)N * 4));
   // directory first: bin_slot_kernel consumes the histogram as its cursor
-  int rc = build_directory(h, d_counts.as<uint32_t>(), d_prefix.as<uint32_t>(), hs, N);
-  if (rc == PQT_OK) {
-    bin_slot_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(d_bin.as<uint32_t>(), N, d_counts.as<uint32_t>(),
-                                                           d_prefix.as<uint32_t>(), h->d_dbidx.as<uint32_t>());
-    sort_within_bins_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(
-        BinDir{h->d_bitmap.as<uint32_t>(), h->d_rank_base.as<uint32_t>(), h->d_cprefix.as<uint32_t>()},
-        h->n_nonempty, h->d_dbidx.as<uint32_t>());
-    cudaError_t e = cudaStreamSynchronize(h->stream);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) rc = fail(h, PQT_ERR_CUDA, "build_kbest_db: %s", cudaGetErrorString(e));
+  PQ_TRY(build_directory(h, d_counts.as<uint32_t>(), d_prefix.as<uint32_t>(), hs, N));
+  bin_slot_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(d_bin, N, d_counts.as<uint32_t>(),
+                                                         d_prefix.as<uint32_t>(), h->d_dbidx.as<uint32_t>());
+  sort_within_bins_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(
+      BinDir{h->d_bitmap.as<uint32_t>(), h->d_rank_base.as<uint32_t>(), h->d_cprefix.as<uint32_t>()},
+      h->n_nonempty, h->d_dbidx.as<uint32_t>());
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaGetLastError());
+  return PQT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pqt_assign_bins(pqt_index* h, const void* X, int x_kind, int x_on_device, uint32_t n,
+                    uint32_t* bin_out, int out_on_device) {
+  if (!h || !X || !bin_out || !n) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (!h->c1) return fail(h, PQT_ERR_STATE, "no tree loaded");
+  const void* dX = nullptr;
+  PQ_TRY(stage_rows(h, X, x_kind, x_on_device, n, &dX));
+  DevBuf d_bin;
+  uint32_t* out = bin_out;
+  if (!out_on_device) {
+    CU_TRY(h, d_bin.ensure((size_t)n * 4));
+    out = d_bin.as<uint32_t>();
   }
-  for (DevBuf* b : {&dX, &d_bin, &d_counts, &d_prefix, &tmp}) b->release();
+  PQ_TRY(launch_assign_bins(h, dX, x_kind, n, out));
+  if (!out_on_device)
+    CU_TRY(h, cudaMemcpyAsync(bin_out, out, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return PQT_OK;
+}
+
+int pqt_set_db_from_bins(pqt_index* h, const uint32_t* bin_of, int on_device, uint32_t N) {
+  if (!h || !bin_of || !N) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (!h->c1) return fail(h, PQT_ERR_STATE, "no tree loaded");
+  if (h->line_build) return fail(h, PQT_ERR_STATE, "a chunked line encoding is in progress");
+  DevBuf d_bin;
+  const uint32_t* db = bin_of;
+  if (!on_device) {
+    CU_TRY(h, d_bin.ensure((size_t)N * 4));
+    CU_TRY(h, cudaMemcpyAsync(d_bin.p, bin_of, (size_t)N * 4, cudaMemcpyHostToDevice, h->stream));
+    db = d_bin.as<uint32_t>();
+  }
+  // every bin must be a hash slot (a foreign array would index the histogram out of bounds)
+  DevBuf flag;
+  CU_TRY(h, flag.ensure(4));
+  CU_TRY(h, cudaMemsetAsync(flag.p, 0, 4, h->stream));
+  check_below_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(db, N, h->prm.hash_size, flag.as<uint32_t>());
+  uint32_t bad = 0;
+  CU_TRY(h, cudaMemcpyAsync(&bad, flag.p, 4, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  if (bad) return fail(h, PQT_ERR_INVALID, "bin_of holds values >= hash_size %u", h->prm.hash_size);
+  return install_db_from_bins(h, db, N);
+}
+
+int pqt_build_kbest_db(pqt_index* h, const float* X, int x_on_device, uint32_t N) {
+  if (!h || !X || !N) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (!h->c1) return fail(h, PQT_ERR_STATE, "no tree loaded");
+  if (h->line_build) return fail(h, PQT_ERR_STATE, "a chunked line encoding is in progress");
+  DevBuf d_bin;
+  CU_TRY(h, d_bin.ensure((size_t)N * 4));
+  // host data goes through in chunks (bounded staging), device data in one pass
+  const uint32_t chunk = x_on_device ? N : std::min<uint32_t>(N, 4u << 20);
+  for (uint32_t i0 = 0; i0 < N; i0 += chunk) {
+    const uint32_t n = std::min(chunk, N - i0);
+    const void* dX = nullptr;
+    PQ_TRY(stage_rows(h, X + (size_t)i0 * h->dim, PQT_X_F32, x_on_device, n, &dX));
+    PQ_TRY(launch_assign_bins(h, dX, PQT_X_F32, n, d_bin.as<uint32_t>() + i0));
+    if (!x_on_device) CU_TRY(h, cudaStreamSynchronize(h->stream));  // staging reuse
+  }
+  int rc = install_db_from_bins(h, d_bin.as<uint32_t>(), N);
+  h->b_x.release();
   return rc;
 }
 
-int pqt_line_dist(pqt_index* h, const float* X, int x_on_device, uint32_t N, uint32_t line_parts) {
-  if (!h || !X) return PQT_ERR_INVALID;
+int pqt_line_dist_begin(pqt_index* h, uint32_t N, uint32_t line_parts) {
+  if (!h) return PQT_ERR_INVALID;
   CU_TRY(h, cudaSetDevice(h->device));
   if (!h->c1) return fail(h, PQT_ERR_STATE, "no tree loaded");
-  if (!h->has_db) return fail(h, PQT_ERR_STATE, "pqt_line_dist must follow pqt_build_kbest_db / pqt_set_db");
+  if (!h->has_db) return fail(h, PQT_ERR_STATE, "line encoding must follow pqt_build_kbest_db / pqt_set_db / pqt_set_db_from_bins");
   if (N != h->N) return fail(h, PQT_ERR_INVALID, "N = %u differs from the DB's %u", N, h->N);
-  if (h->world != 1) return fail(h, PQT_ERR_STATE, "pqt_line_dist on a sharded handle");
   PQ_TRY(check_lp(h, line_parts));
   if (!is_pow2(h->c1)) return fail(h, PQT_ERR_INVALID, "line encoding needs c1 = 2^n (tree over centroids, pqt/PerturbationProTree.cu:7633-7641)");
   if (h->c1 * line_parts > 1024) return fail(h, PQT_ERR_INVALID, "lineparts * c1 > 1024 (:7694-7697)");
   const uint32_t LP = line_parts;
+  h->has_lines = false;
   h->LP = LP;
   h->sl = h->dim / LP;
   PQ_TRY(compute_cbd(h, LP));
-  DevBuf dX;
-  const float* x = X;
-  if (!x_on_device) {
-    CU_TRY(h, dX.ensure((size_t)N * h->dim * 4));
-    CU_TRY(h, cudaMemcpyAsync(dX.p, X, (size_t)N * h->dim * 4, cudaMemcpyHostToDevice, h->stream));
-    x = dX.as<float>();
-  }
-  CU_TRY(h, h->d_codes.ensure((size_t)N * LP * 4));
-  LineEncodeArgs a{};
-  a.X = x; a.cb1 = h->d_cb1.as<float>(); a.cbd = h->d_cbd.as<float>();
-  a.ids = h->d_dbidx.as<uint32_t>();
-  a.N = N; a.dim = h->dim; a.c1 = h->c1; a.LP = LP; a.sl = h->sl;
-  a.codes = h->d_codes.as<uint32_t>();
-  size_t smem = (size_t)(h->dim + 3 * LP * h->c1) * 4;
-  if (smem > 48 * 1024)
-    CU_TRY(h, cudaFuncSetAttribute(line_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  uint32_t grid = std::min<uint32_t>(N, (uint32_t)h->num_sms * 8);
-  line_encode_kernel<<<grid, LP * h->c1, smem, h->stream>>>(a);
+  const uint32_t n_local = h->pos_hi - h->pos_lo;
+  CU_TRY(h, h->d_codes.ensure(std::max<size_t>((size_t)n_local * LP * 4, 16)));
+  CU_TRY(h, h->b_inv.ensure((size_t)N * 4));
+  invert_perm_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->d_dbidx.as<uint32_t>(), N, h->b_inv.as<uint32_t>());
   CU_TRY(h, cudaGetLastError());
   CU_TRY(h, cudaStreamSynchronize(h->stream));
-  dX.release();
+  h->line_build = true;
+  return PQT_OK;
+}
+
+int pqt_line_dist_chunk(pqt_index* h, const void* X, int x_kind, int x_on_device, uint32_t id0,
+                        uint32_t n, uint32_t* lines_out) {
+  if (!h || !X || !n) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (!h->line_build) return fail(h, PQT_ERR_STATE, "pqt_line_dist_begin first");
+  if ((uint64_t)id0 + n > h->N) return fail(h, PQT_ERR_INVALID, "chunk [%u, %u + %u) exceeds N = %u", id0, id0, n, h->N);
+  if (lines_out && h->world != 1) return fail(h, PQT_ERR_STATE, "lines_out needs an unsharded handle (a shard encodes only its own vectors)");
+  const uint32_t LP = h->LP;
+  const void* dX = nullptr;
+  PQ_TRY(stage_rows(h, X, x_kind, x_on_device, n, &dX));
+  CU_TRY(h, h->b_stage.ensure((size_t)n * LP * 4));
+  const bool sharded = h->world > 1;
+  const bool fast = (h->c1 == 16 || h->c1 == 32) && (h->sl == 4 || h->sl == 8 || h->sl == 16) &&
+                    ((uintptr_t)dX & 15u) == 0 && (h->dim % 16) == 0;
+  if (fast) {
+    LineWarpArgs a{};
+    a.X = dX; a.n = n; a.dim = h->dim; a.LP = LP;
+    a.cb1 = h->d_cb1.as<float>(); a.cbd = h->d_cbd.as<float>();
+    a.inv = sharded ? h->b_inv.as<uint32_t>() : nullptr;
+    a.id0 = id0; a.pos_lo = h->pos_lo; a.pos_hi = h->pos_hi;
+    a.staging = h->b_stage.as<uint32_t>();
+    const uint32_t grid = build_grid(h), thr = kBuildWarpsPerCta * 32;
+#define LAUNCH_LINE(XT, SLV)                                                                      \
+  do {                                                                                            \
+    if (h->c1 == 32) line_encode_warp_kernel<XT, SLV, 32><<<grid, thr, 0, h->stream>>>(a);        \
+    else line_encode_warp_kernel<XT, SLV, 16><<<grid, thr, 0, h->stream>>>(a);                    \
+  } while (0)
+#define LAUNCH_LINE_SL(XT)                                                                        \
+  do {                                                                                            \
+    if (h->sl == 4) LAUNCH_LINE(XT, 4);                                                           \
+    else if (h->sl == 8) LAUNCH_LINE(XT, 8);                                                      \
+    else LAUNCH_LINE(XT, 16);                                                                     \
+  } while (0)
+    if (x_kind == PQT_X_U8) LAUNCH_LINE_SL(uint8_t); else LAUNCH_LINE_SL(float);
+#undef LAUNCH_LINE_SL
+#undef LAUNCH_LINE
+    CU_TRY(h, cudaGetLastError());
+  } else {
+    DevBuf tmp;
+    const float* xf = nullptr;
+    PQ_TRY(rows_as_f32(h, dX, x_kind, n, tmp, &xf));
+    LineEncodeArgs a{};
+    a.X = xf; a.cb1 = h->d_cb1.as<float>(); a.cbd = h->d_cbd.as<float>();
+    a.ids = nullptr;
+    a.N = n; a.dim = h->dim; a.c1 = h->c1; a.LP = LP; a.sl = h->sl;
+    a.codes = h->b_stage.as<uint32_t>();
+    size_t smem = (size_t)(h->dim + 3 * LP * h->c1) * 4;
+    if (smem > 48 * 1024)
+      CU_TRY(h, cudaFuncSetAttribute(line_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint32_t grid = std::min<uint32_t>(n, (uint32_t)h->num_sms * 8);
+    line_encode_kernel<<<grid, LP * h->c1, smem, h->stream>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaStreamSynchronize(h->stream));  // tmp is freed on return
+  }
+  scatter_rows_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->b_stage.as<uint32_t>(), id0, n, LP,
+                                                            h->b_inv.as<uint32_t>(), h->pos_lo, h->pos_hi,
+                                                            h->d_codes.as<uint32_t>());
+  CU_TRY(h, cudaGetLastError());
+  h->stats.kernel_launches += 2;
+  if (lines_out)
+    CU_TRY(h, cudaMemcpyAsync(lines_out, h->b_stage.p, (size_t)n * LP * 4, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return PQT_OK;
+}
+
+int pqt_line_dist_end(pqt_index* h) {
+  if (!h) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (!h->line_build) return fail(h, PQT_ERR_STATE, "pqt_line_dist_begin first");
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  h->b_inv.release();
+  h->b_stage.release();
+  h->b_x.release();
+  h->line_build = false;
   h->has_lines = true;
   return PQT_OK;
+}
+
+int pqt_line_dist(pqt_index* h, const float* X, int x_on_device, uint32_t N, uint32_t line_parts) {
+  if (!h || !X) return PQT_ERR_INVALID;
+  PQ_TRY(pqt_line_dist_begin(h, N, line_parts));
+  const uint32_t chunk = std::min<uint32_t>(N, 4u << 20);
+  int rc = PQT_OK;
+  for (uint32_t i0 = 0; i0 < N && rc == PQT_OK; i0 += chunk)
+    rc = pqt_line_dist_chunk(h, X + (size_t)i0 * h->dim, PQT_X_F32, x_on_device, i0, std::min(chunk, N - i0), nullptr);
+  if (rc != PQT_OK) {
+    h->b_inv.release();
+    h->b_stage.release();
+    h->b_x.release();
+    h->line_build = false;
+    return rc;
+  }
+  return pqt_line_dist_end(h);
 }
 
 // ---- query ----------------------------------------------------------------------------

@@ -89,11 +89,39 @@ class PerturbationProTree {
     chk(pqt_line_dist(h_, _DB, _onDevice ? 1 : 0, _N, _lineParts));
   }
 
+  // ---- chunked build: the reference's 1-B driver walks the base set in 10-M-vector chunks
+  // (test/test1B.cpp:783-871); rows are float or the uint8 payload of a .umem file
+  void assignBins(const void* _X, bool _isU8, bool _onDevice, uint _n, uint* _binOut,
+                  bool _outOnDevice) {
+    chk(pqt_assign_bins(h_, _X, _isU8 ? PQT_X_U8 : PQT_X_F32, _onDevice ? 1 : 0, _n, _binOut,
+                        _outOnDevice ? 1 : 0));
+  }
+  void setDBFromBins(const uint* _binOf, bool _onDevice, uint _N) {
+    chk(pqt_set_db_from_bins(h_, _binOf, _onDevice ? 1 : 0, _N));
+  }
+  void lineDistBegin(uint _N, uint _lineParts) { chk(pqt_line_dist_begin(h_, _N, _lineParts)); }
+  /** encodes vectors _id0 .. _id0+_n-1; _linesOut (host, may be null): the chunk's lineDescr rows */
+  void lineDistChunk(const void* _X, bool _isU8, bool _onDevice, uint _id0, uint _n,
+                     float* _linesOut = nullptr) {
+    chk(pqt_line_dist_chunk(h_, _X, _isU8 ? PQT_X_U8 : PQT_X_F32, _onDevice ? 1 : 0, _id0, _n,
+                            reinterpret_cast<uint32_t*>(_linesOut)));
+  }
+  void lineDistEnd() { chk(pqt_line_dist_end(h_)); }
+
   void queryKNN(std::vector<uint>& _resIdx, std::vector<float>& _resDist, const float* _Q,
                 uint _QN, uint _nVec, bool _qOnDevice = false) {
     _resIdx.resize((size_t)_QN * _nVec);
     _resDist.resize((size_t)_QN * _nVec);
     chk(pqt_query_knn(h_, _Q, _qOnDevice ? 1 : 0, _QN, _nVec, _resIdx.data(), _resDist.data(), 0));
+  }
+
+  /** the 1-B variant (pqt/PerturbationProTree.hh:80); the codes are the resident ones */
+  void queryBIGKNNRerank2(std::vector<uint>& _resIdx, std::vector<float>& _resDist, const float* _Q,
+                          uint _QN, uint _nVec, bool _qOnDevice = false) {
+    _resIdx.resize((size_t)_QN * _nVec);
+    _resDist.resize((size_t)_QN * _nVec);
+    chk(pqt_query_big_knn_rerank2(h_, _Q, _qOnDevice ? 1 : 0, _QN, _nVec, _resIdx.data(),
+                                  _resDist.data(), 0));
   }
 
   uint getNPerturbations() const { return 1; }

@@ -57,9 +57,11 @@ int main(int argc, char** argv) {
 
     FileReader<float> reader(fl.str("dataset"));
     if (reader.dim() != dim) throw std::runtime_error("dataset dimension differs from --dim");
-    const uint32_t N = (uint32_t)std::min<uint64_t>((uint64_t)fl.num("chunksize"), reader.num());
-    std::vector<float> data = reader.data(N);
-    std::cout << "read " << N << " x " << dim << " vectors from " << fl.str("dataset") << std::endl;
+    // The whole dataset goes in, chunk by chunk (the reference tool stops after the first
+    // chunk; its 1-B driver test/test1B.cpp:783-871 loops over the chunks like this)
+    const uint32_t N = reader.num();
+    const uint32_t chunk = (uint32_t)std::max<long long>(1, std::min<long long>(fl.num("chunksize"), N));
+    std::cout << N << " x " << dim << " vectors in " << fl.str("dataset") << ", chunks of " << chunk << std::endl;
 
     pqt::PerturbationProTree ppt(dim, p, p, (int)fl.num("device"));
     ppt.setHashSize((uint32_t)fl.num("hashsize"));
@@ -69,7 +71,7 @@ int main(int argc, char** argv) {
       ppt.readTreeFromFile(codebook_file);
     } else {
       const size_t ntrain = std::min<size_t>((size_t)fl.num("train"), N);
-      std::vector<float> cb1, cb2;
+      std::vector<float> cb1, cb2, data = reader.data(ntrain);
       pqt_train::train_tree(data.data(), ntrain, dim, p, c1, c2, cb1, cb2);
       ppt.setTree(c1, c2, cb1.data(), cb2.data());
       ppt.writeTreeToFile(codebook_file);
@@ -77,12 +79,35 @@ int main(int argc, char** argv) {
     }
 
     auto t0 = std::chrono::steady_clock::now();
-    ppt.buildKBestDB(data.data(), N);
-    ppt.lineDist(data.data(), N, LP);
+    // pass 1: bins of every chunk, then the inverted lists over all of them
+    std::vector<pqt::uint> binOf(N);
+    for (uint32_t i0 = 0; i0 < N; i0 += chunk) {
+      const uint32_t n = std::min(chunk, N - i0);
+      std::vector<uint8_t> rows = pqt_io::readPayload<uint8_t>(fl.str("dataset"), dim, n, i0);
+      ppt.assignBins(rows.data(), true, false, n, binOf.data() + i0, false);
+    }
+    ppt.setDBFromBins(binOf.data(), false, N);
+    binOf.clear();
+    binOf.shrink_to_fit();
+    // pass 2: line codes chunk by chunk, appended to the .lines file in id order
+    const std::string lines_name = pre + "_" + std::to_string(LP) + ".lines";
+    {
+      std::ofstream lf(lines_name, std::ios::out | std::ios::binary);
+      std::vector<float> lines((size_t)chunk * LP);
+      ppt.lineDistBegin(N, LP);
+      for (uint32_t i0 = 0; i0 < N; i0 += chunk) {
+        const uint32_t n = std::min(chunk, N - i0);
+        std::vector<uint8_t> rows = pqt_io::readPayload<uint8_t>(fl.str("dataset"), dim, n, i0);
+        ppt.lineDistChunk(rows.data(), true, false, i0, n, lines.data());
+        lf.write(reinterpret_cast<const char*>(lines.data()), (std::streamsize)((size_t)n * LP * 4));
+      }
+      ppt.lineDistEnd();
+      if (!lf.good()) throw std::runtime_error("write error on " + lines_name);
+    }
+    std::cout << "written " << lines_name << std::endl;
     double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     std::cout << "built DB of " << N << " vectors in " << s << " s" << std::endl;
 
-    dump(pre + "_" + std::to_string(LP) + ".lines", ppt.getLine());
     dump(pre + ".prefix", ppt.getBinPrefix());
     dump(pre + ".count", ppt.getBinCounts());
     dump(pre + ".dbIdx", ppt.getDBIdx());

@@ -35,7 +35,7 @@ int main(int argc, char** argv) {
   fl.add("p", "2", "parts per vector");
   fl.add("dim", "128", "expected dimension for each vector");
   fl.add("lineparts", "32", "vectorparts for reranking informations");
-  fl.add("chunksize", "100000", "number of vectors per chunk");
+  fl.add("chunksize", "100000", "number of vectors per chunk (kept for flag compatibility; the DB size comes from the .dbIdx file)");
   fl.add("hashsize", "400000000", "maximal number of bins");
   fl.add("basename", "tmp", "prefix for generated data");
   fl.add("dataset", "base.umem", "path to vector dataset");
@@ -76,11 +76,24 @@ int main(int argc, char** argv) {
     std::cout << "codebook exists, reading from " << codebook_file << std::endl;
     ppt.readTreeFromFile(codebook_file);
 
-    const uint32_t base_num = (uint32_t)std::min<uint64_t>((uint64_t)fl.num("chunksize"), DataReader.num());
+    // The database size is what tool_createdb wrote, i.e. the length of .dbIdx (the reference
+    // takes DataReader.num(); --chunksize is not the DB size).  Every file must agree with it.
+    const std::string idx_file = pre + ".dbIdx", lines_file = pre + "_" + std::to_string(LP) + ".lines";
+    if (stat(idx_file.c_str(), &sb) != 0) throw std::runtime_error("cannot stat " + idx_file);
+    if (sb.st_size == 0 || sb.st_size % 4) throw std::runtime_error(idx_file + ": size is not a multiple of 4");
+    if ((uint64_t)sb.st_size / 4 > 0xFFFFFFFFull) throw std::runtime_error(idx_file + ": too many vectors");
+    const uint32_t base_num = (uint32_t)(sb.st_size / 4);
+    if (base_num > DataReader.num())
+      throw std::runtime_error("the database holds " + std::to_string(base_num) + " vectors, the dataset only " +
+                               std::to_string(DataReader.num()));
+    if (stat(lines_file.c_str(), &sb) != 0) throw std::runtime_error("cannot stat " + lines_file);
+    if ((uint64_t)sb.st_size != (uint64_t)base_num * LP * 4)
+      throw std::runtime_error(lines_file + ": size does not match " + std::to_string(base_num) + " vectors x " +
+                               std::to_string(LP) + " line parts");
     std::vector<pqt::uint> binPrefix = slurp<pqt::uint>(pre + ".prefix", hashsize);
     std::vector<pqt::uint> binCounts = slurp<pqt::uint>(pre + ".count", hashsize);
     std::vector<pqt::uint> dbIdx = slurp<pqt::uint>(pre + ".dbIdx", base_num);
-    std::vector<float> hLines = slurp<float>(pre + "_" + std::to_string(LP) + ".lines", (size_t)base_num * LP);
+    std::vector<float> hLines = slurp<float>(lines_file, (size_t)base_num * LP);
 
     ppt.setDB(base_num, binPrefix.data(), binCounts.data(), dbIdx.data());
     ppt.setLines(hLines.data(), base_num, LP);

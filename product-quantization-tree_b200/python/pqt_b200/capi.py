@@ -26,7 +26,11 @@ EXPORTS = [
     "pqt_shard_codes_handle", "pqt_shard_codes_open", "pqt_shard_codes_set_peers", "pqt_shard_codes_ptr",
     "pqt_shard_candidates", "pqt_shard_scan_p2p", "pqt_shard_rank", "pqt_profile_enable", "pqt_get_stats", "pqt_reset_stats",
     "pqt_debug_enable", "pqt_debug_stage",
+    "pqt_assign_bins", "pqt_set_db_from_bins", "pqt_line_dist_begin", "pqt_line_dist_chunk",
+    "pqt_line_dist_end", "pqt_get_codes_binorder",
 ]
+
+X_F32, X_U8 = 0, 1
 
 STAGES = dict(assign=0, lut=1, assign_val=2, assign_idx=3, bins=4, n_bins=5, select_idx=6,
               n_vec=7, cb_dist=8, dist_seq=9, dist_seq_2d=10, big_bins=11, big_n_bins=12, rerank_phases=13)
@@ -97,6 +101,14 @@ def lib():
         L.pqt_query_big_knn_rerank2.argtypes = L.pqt_query_knn.argtypes
         L.pqt_build_kbest_db.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]
         L.pqt_line_dist.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32]
+        L.pqt_assign_bins.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32,
+                                      C.c_void_p, C.c_int]
+        L.pqt_set_db_from_bins.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]
+        L.pqt_line_dist_begin.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        L.pqt_line_dist_chunk.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32,
+                                          C.c_uint32, C.c_void_p]
+        L.pqt_line_dist_end.argtypes = [C.c_void_p]
+        L.pqt_get_codes_binorder.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
         L.pqt_get_db.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pqt_get_lines.argtypes = [C.c_void_p, C.c_void_p]
         L.pqt_get_db_size.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
@@ -228,6 +240,53 @@ class PerturbationProTree:
     def lineDist(self, DB, N, line_parts=16):
         ptr, dev = _ptr(DB)
         self._chk(self._L.pqt_line_dist(self._h, ptr, dev, N, line_parts))
+
+    # ---- chunked build (test/test1B.cpp:783-871: the base set in 10-M-vector chunks)
+    @staticmethod
+    def _rows(X):
+        """rows as float32 or uint8 (numpy host array or torch tensor) -> (ptr, kind, on_device)"""
+        if isinstance(X, np.ndarray):
+            if X.dtype != np.uint8:
+                X = np.ascontiguousarray(X, np.float32)
+            kind = X_U8 if X.dtype == np.uint8 else X_F32
+            assert X.flags["C_CONTIGUOUS"]
+            return X, X.ctypes.data, kind, 0
+        kind = X_U8 if str(X.dtype) == "torch.uint8" else X_F32
+        assert X.is_contiguous() and str(X.dtype) in ("torch.uint8", "torch.float32")
+        return X, X.data_ptr(), kind, 1 if X.is_cuda else 0
+
+    def assignBins(self, X, n, bin_out=None):
+        """bins of n vectors; bin_out: torch CUDA int32 tensor / numpy uint32 array (returned)"""
+        keep, xp, kind, dev = self._rows(X)
+        if bin_out is None:
+            bin_out = np.zeros(n, np.uint32)
+        bp, bdev = _ptr(bin_out)
+        self._chk(self._L.pqt_assign_bins(self._h, xp, kind, dev, n, bp, bdev))
+        return bin_out
+
+    def setDBFromBins(self, bin_of, N):
+        bp, bdev = _ptr(bin_of)
+        self._chk(self._L.pqt_set_db_from_bins(self._h, bp, bdev, N))
+
+    def lineDistBegin(self, N, line_parts):
+        self._chk(self._L.pqt_line_dist_begin(self._h, N, line_parts))
+
+    def lineDistChunk(self, X, id0, n, lines_out=None):
+        keep, xp, kind, dev = self._rows(X)
+        lp = lines_out.ctypes.data if lines_out is not None else None
+        self._chk(self._L.pqt_line_dist_chunk(self._h, xp, kind, dev, id0, n, lp))
+
+    def lineDistEnd(self):
+        self._chk(self._L.pqt_line_dist_end(self._h))
+
+    def getCodesBinOrder(self, pos0=0, n=None, out=None):
+        N, lp = self.dbSize()
+        if n is None:
+            n = N - pos0
+        if out is None:
+            out = np.zeros((n, lp), np.uint32)
+        self._chk(self._L.pqt_get_codes_binorder(self._h, pos0, n, out.ctypes.data))
+        return out
 
     def dbSize(self):
         n, lp = C.c_uint32(), C.c_uint32()

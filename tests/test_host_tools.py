@@ -57,7 +57,7 @@ def test_createdb_then_query_end_to_end(tmp_path):
     formats.write_mem(str(tmp_path / "query.umem"), Q)
     base = str(tmp_path / "tmp")
     common = ["--c1", str(c1), "--c2", str(c2), "--p", str(p), "--dim", str(dim), "--lineparts",
-              str(LP), "--hashsize", str(hs), "--chunksize", str(N), "--basename", base,
+              str(LP), "--hashsize", str(hs), "--chunksize", "3000", "--basename", base,
               "--dataset", str(tmp_path / "base.umem")]
     r = subprocess.run([TOOL_CREATEDB] + common, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr

@@ -16,12 +16,13 @@ import bench  # noqa: E402
 def main():
     sys.argv = [sys.argv[0]] + sys.argv[1:]
     a = bench.parse()
-    if a.clusters <= 0:
-        a.clusters = max(4096, a.n // 256)
-    X8, Q8, src, cb1, cb2 = bench.build_inputs(a, "cuda:0")
-    t, _ = bench.build_index_gpu(a, X8, cb1, cb2, 0)
-    del X8
-    Qd = Q8.to(torch.float32).contiguous()
+    import pqt_b200
+    inp = bench.build_inputs(a, "cuda:0")
+    t = pqt_b200.PerturbationProTree(a.dim, a.p, a.p, 0)
+    t.set_params(hash_size=a.hashsize, k1_build=min(16, a.c1))
+    t.setTree(inp["cb1"], inp["cb2"])
+    bench.build_index_chunked(a, t, inp, 0, 1, "cuda:0")
+    Qd = inp["Q8"].to(torch.float32).contiguous()
     oi = torch.empty((a.qn, a.k), dtype=torch.int32, device="cuda")
     od = torch.empty((a.qn, a.k), dtype=torch.float32, device="cuda")
     for _ in range(2):
