@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--variants", default="knn,big", help="comma list of knn, big")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-version", action="store_true",
+                    help="skip the cpu_version/ (CPU twin, config C1) leg (~2 min of host time, cached per box)")
     ap.add_argument("--cache-dir", default="/dev/shm/pqt_b200_bench",
                     help="where the index files for the CPU arms live (tmpfs: 136 GB at 1B)")
     ap.add_argument("--rm-files", action="store_true",
@@ -240,6 +242,53 @@ def load_host_index(paths, a):
 def remove_index_files(a):
     import shutil
     shutil.rmtree(cache_paths(a)["dir"], ignore_errors=True)
+
+
+def cpu_version_baseline(a, device):
+    """BASELINE config 1: the reference's CPU twin (cpu_version/, compiled unmodified against the
+    Eigen stand-in into oracle/_ref/cpu_version_bench) as treequantizer<float,128,16,8,4,4,32>
+    on 1M x 128-d synthetic vectors, query(20000, 500) over 1k queries
+    (cpu_version/tools/query.cpp:42,133-138): single thread as the reference runs it, and one
+    index replica per host core.  Cached per box (the CPU numbers do not depend on the arm)."""
+    import subprocess
+    import torch
+    import synthdb
+    from pqt_b200 import formats
+    exe = os.path.join(ROOT, "oracle", "_ref", "cpu_version_bench")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/cpu_version_bench is not built (the reference tree was absent at build time)"}
+    d = os.path.join(a.cache_dir, "c1_cpu_version")
+    cache = os.path.join(d, "result.json")
+    if os.path.exists(cache):
+        return json.load(open(cache))
+    os.makedirs(d, exist_ok=True)
+    n, qn, ncl, dim = 1000000, 1000, 4096, 128
+    mu = synthdb.centres_u8(ncl, dim, DB_SEED, device)
+    X = synthdb.db_u8(torch.empty((n, dim), dtype=torch.uint8, device=device), 0, n, mu, DB_SEED)
+    Q8, _ = synthdb.queries_u8(qn, n, mu, DB_SEED, QUERY_SEED)
+    _, gt = synthdb.exact_1nn(Q8, n, mu, DB_SEED)
+    formats.write_mem(os.path.join(d, "base.umem"), X.cpu().numpy())
+    formats.write_mem(os.path.join(d, "query.umem"), Q8.cpu().numpy())
+    formats.write_mem(os.path.join(d, "gt.imem"), gt.cpu().numpy().astype(np.int32)[:, None])
+    del X
+    threads = os.cpu_count() or 1
+    out = {"kind": "cpu_version", "config": "BASELINE configs[0]: 1M x 128-d synthetic, p=4 c1=16 c2=8 "
+           "(W=4, LP=32), 1k queries, query(20000, 500)", "host_cores": threads}
+    for label, nt in (("single_thread", 1), ("all_cores", threads)):
+        r = subprocess.run([exe, os.path.join(d, "base.umem"), os.path.join(d, "query.umem"),
+                            os.path.join(d, "gt.imem"), "100000", str(qn), str(nt)],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            return {"unavailable": "cpu_version_bench failed: " + (r.stderr or r.stdout)[-300:]}
+        out[label] = json.loads(r.stdout.strip().splitlines()[-1])
+    out["value"] = out["all_cores"]["queries_per_s"]
+    out["unit"] = "queries/s"
+    out["cores"] = threads
+    out["recall_at_1"] = out["single_thread"]["recall_at_1"]
+    for f in ("base.umem", "query.umem", "gt.imem"):
+        os.remove(os.path.join(d, f))
+    json.dump(out, open(cache, "w"))
+    return out
 
 
 def oracle_handles():
@@ -571,14 +620,16 @@ def run_b200(a, rank, world, local_rank):
         return
 
     peak, peak_src = measured_peak_hbm()
-    bytes_per_cand = 4 * a.lineparts + 4
-
     def summarise(r):
         st = r["st"]
         scan_ms = st.ms_scan / max(1, st.scan_launches)
         cand_per_launch = st.candidates / max(1, st.scan_launches)
         if sharded:
             cand_per_launch /= world
+        # split pipeline: the scan kernel reads the code rows only (ids are implicit in the
+        # bin-ordered layout and read by the ranking kernel); fused: codes + the 4-byte id
+        split = st.stream_scan_launches > 0
+        bytes_per_cand = 4 * a.lineparts + (0 if split else 4)
         achieved = cand_per_launch * bytes_per_cand / (scan_ms * 1e-3) / 1e9
         gtu = gt.astype(np.uint32)
         return {
@@ -588,7 +639,9 @@ def run_b200(a, rank, world, local_rank):
                     "d2h_bytes_per_step": int(QN * k * 8), "ms_per_step": r["e2e_ms"] / a.steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None,
-                         "kernel": "adc_scan_p2p_kernel" if sharded else "rerank_kernel (ADC scan + ranking fused)",
+                         "kernel": "adc_scan_p2p_kernel" if sharded else
+                         ("adc_stream_kernel (ADC scan; ranking = rank2_kernel, stage 'sort')" if split
+                          else "rerank_kernel (ADC scan + ranking fused)"),
                          "peak_source": peak_src, "ms_per_launch": scan_ms,
                          "candidates_per_launch": cand_per_launch,
                          "bytes_per_candidate": bytes_per_cand,
@@ -638,6 +691,12 @@ def run_b200(a, rank, world, local_rank):
             if a.rm_files:
                 remove_index_files(a)
 
+    cpuv = None
+    if world == 1 and not a.no_cpu_baseline and not a.no_cpu_version:
+        try:
+            cpuv = cpu_version_baseline(a, device)
+        except Exception as e:  # noqa: BLE001
+            cpuv = {"unavailable": repr(e)}
     head = summ.get("knn") or next(iter(summ.values()))
     par = ("bin-range shards x%d, scan fused with peer-memory exchange (NVLink), NCCL all-gather of candidate lists" % world) if sharded \
         else ("bin-range shards x%d, batch split over the ranks, line codes of the other shards read over NVLink inside the fused scan kernel, no collective" % world) if pull \
@@ -653,6 +712,7 @@ def run_b200(a, rank, world, local_rank):
         "l2": "flushed between steps (256 MiB write)",
         "roofline": head["roofline"],
         "cpu_baseline": cpu,
+        "cpu_version_baseline": cpuv,
         "e2e": head["e2e"],
         "e2e_k100": e2e_k100,
         "gpu_launches": head["gpu_launches"],

@@ -90,7 +90,9 @@ typedef struct pqt_stats {
                                   (tied or >= 1e7 distances); all others use the fast sort */
   uint64_t tie_resolved_queries; /* queries whose groups of bit-equal distances were put into
                                     the network's order by the bit-plane simulation */
-  uint64_t reserved[5];
+  uint64_t stream_scan_launches; /* of scan_launches: launches of the streaming scan kernel
+                                    (split pipeline: ms_scan = ADC scan alone, ms_sort = ranking) */
+  uint64_t reserved[4];
 } pqt_stats;
 
 /* ---- lifetime ------------------------------------------------------------- */

@@ -52,7 +52,10 @@ struct BinsBigArgs {
 };
 
 // dynamic smem: l_val[512] | l_idx[512] | r_dist[1024] | r_bin[1024] | in_val[128] | in_idx[128]
-//               | list[list_cap] | warp_sums[32] | misc[4]
+//               | list[list_cap] | warp_sums[32] | misc[4] | pay u16[1024]
+// The rounds' 1024-wide and the merges' 256-wide sorts are the reference's network (ties between
+// equal summed distances follow it), run by grp_sort_dispatch: same compare-exchanges in
+// registers / shuffles, shared memory and a barrier only for the cross-warp distances.
 __global__ void __launch_bounds__(kBigThreads) bins_big_kernel(BinsBigArgs a) {
   extern __shared__ float smem_f[];
   float* l_val = smem_f;
@@ -64,7 +67,9 @@ __global__ void __launch_bounds__(kBigThreads) bins_big_kernel(BinsBigArgs a) {
   uint32_t* list = in_idx + 2 * kBigKMax;
   uint32_t* warp_sums = list + a.list_cap;
   uint32_t* misc = warp_sums + 32;
+  uint16_t* pay = reinterpret_cast<uint16_t*>(misc + 4);
   const uint32_t tid = threadIdx.x;
+  const Grp G{tid, (uint32_t)kBigThreads, 0};
   const uint32_t K = a.c1c2;
   const uint32_t factor = K * K;  // uint32 wrap (:3101)
   const size_t seq_total = (size_t)kNumAnisoDir * kNumDistSeq;
@@ -93,11 +98,14 @@ __global__ void __launch_bounds__(kBigThreads) bins_big_kernel(BinsBigArgs a) {
           b = in_idx[x] * K + in_idx[kBigKMax + y];
         }
         l_val[pi * kBigInter + tid] = d;
-        l_idx[pi * kBigInter + tid] = b;
+        r_bin[tid] = b;
+        pay[tid] = (uint16_t)tid;
       }
       __syncthreads();
-      bitonic_smem(l_val + pi * kBigInter, l_idx + pi * kBigInter, kBigInter, 1);
+      grp_sort_dispatch(G, l_val + pi * kBigInter, pay, kBigInter);  // bitonic3 over 256 (:2985)
+      if (tid < kBigInter) l_idx[pi * kBigInter + tid] = r_bin[pay[tid]];
     }
+    __syncthreads();
     // ---- selectBinKernel2DFinal
     if (tid == 0) misc[0] = slope_index(l_val, l_val + kBigInter, 1024);
     __syncthreads();
@@ -117,10 +125,11 @@ __global__ void __launch_bounds__(kBigThreads) bins_big_kernel(BinsBigArgs a) {
         }
         r_dist[tid] = d;
         r_bin[tid] = magicmod(b, a.hash);
+        pay[tid] = (uint16_t)tid;
       }
       __syncthreads();
-      bitonic_smem(r_dist, r_bin, kBigThreads, 1);  // bitonic3(dist, outIdx, blockDim.x) :3106
-      const uint32_t mybin = r_bin[tid];
+      grp_sort_dispatch(G, r_dist, pay, kBigThreads);  // bitonic3(dist, outIdx, blockDim.x) :3106
+      const uint32_t mybin = r_bin[pay[tid]];
       uint32_t start, cnt;
       dir_lookup(a.dir, mybin, start, cnt);
       const uint32_t e = cnt < 2 ? cnt : 2;  // maxVecPB = 2 (:3114)

@@ -96,6 +96,7 @@ struct pqt_index {
   DevBuf g_bigbins, g_bignbins, g_phases;
   uint32_t dbg_big_QN = 0, dbg_big_cap = 0;
   DevBuf d_seqsorted;  // per 4096-batch, sorted by the ranks of all parts but the last (bins3)
+  DevBuf d_seqfine;    // the same per 1024-batch (bins3 on dense indexes: finer early stop)
   DevBuf d_seqmega, d_seqplain;  // the same per 16384 codes + plain nibble codes (bins4)
   std::vector<uint32_t> h_distseq;
   uint32_t seq_m = 0, seq_p = 0;
@@ -127,6 +128,7 @@ struct pqt_index {
   // multi-GPU exchange (fused scan + peer stores)
   DevBuf x_val, x_idx;  // own [q_per_rank][max_vec] candidate arrays, written by peers
   uint32_t x_q_per_rank = 0, x_max_vec = 0, x_world = 0;
+  uint32_t x_lut_QN = 0;  // queries whose LUT the last pqt_shard_candidates call left in s_lut
   float* x_peer_val[8] = {nullptr};
   uint32_t* x_peer_idx[8] = {nullptr};
   bool x_ipc_opened[8] = {false};
@@ -138,6 +140,7 @@ struct pqt_index {
   DevBuf d_exact;  // two uint64: queries ranked by the exact-network fallback, queries with re-ordered ties
 
   // profiling
+  bool split_ranked = false;  // the last run_scan_chain ran the split pipeline (scan kernel + ranking kernel)
   bool profile = false;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   pqt_stats stats{};
@@ -195,6 +198,10 @@ int ensure_dist_seq(pqt_index* h, uint32_t max_cluster) {
   if (h->d_distseq.p && h->seq_m == m && h->seq_p == h->p) return PQT_OK;
   uint64_t n64 = 1;
   for (uint32_t j = 0; j < h->p; j++) n64 *= m;
+  // the reference computes uint nVec = pow(m, p) (pqt/ProTree.cu:139): it wraps for p = 8 and the
+  // host sort of m^p pairs is impractical long before that
+  if (n64 > (1ull << 24))
+    return fail(h, PQT_ERR_INVALID, "traversal table of %u^%u codes is too large (p <= 6 at k1*c2 >= 16)", m, h->p);
   uint32_t nvec = (uint32_t)n64;
   std::vector<std::pair<float, uint32_t>> d(nvec);
   std::vector<uint32_t> den(h->p);
@@ -224,25 +231,28 @@ int ensure_dist_seq(pqt_index* h, uint32_t max_cluster) {
   if (h->p <= 4) {
     // bins3_kernel: inside each batch visit the probes sorted by (ranks of parts 0..p-2,
     // rank of the last part); entry = (rank inside the batch << 16) | nibble code
-    std::vector<uint32_t> sorted(kNumDistSeq, 0u);
-    const uint32_t batch = kBins3Batch;
     const uint32_t last_shift = 4 * (h->p - 1);
-    std::vector<std::pair<uint32_t, uint32_t>> key(batch);
-    for (uint32_t b = 0; b < kNumDistSeq / batch; b++) {
-      for (uint32_t u = 0; u < batch; u++) {
-        uint32_t code = h->h_distseq[b * batch + u], v = 0;
-        for (uint32_t j = 0; j < h->p; j++) v |= ((code / den[j]) % m) << (4 * j);
-        uint32_t prefix = v & ((1u << last_shift) - 1u), last = v >> last_shift;
-        key[u] = std::make_pair((prefix << 4) | last, (u << 16) | v);
+    for (int pass = 0; pass < 2; pass++) {
+      std::vector<uint32_t> sorted(kNumDistSeq, 0u);
+      const uint32_t batch = pass == 0 ? (uint32_t)kBins3Batch : (uint32_t)kBins3FineBatch;
+      std::vector<std::pair<uint32_t, uint32_t>> key(batch);
+      for (uint32_t b = 0; b < kNumDistSeq / batch; b++) {
+        for (uint32_t u = 0; u < batch; u++) {
+          uint32_t code = h->h_distseq[b * batch + u], v = 0;
+          for (uint32_t j = 0; j < h->p; j++) v |= ((code / den[j]) % m) << (4 * j);
+          uint32_t prefix = v & ((1u << last_shift) - 1u), last = v >> last_shift;
+          key[u] = std::make_pair((prefix << 4) | last, (u << 16) | v);
+        }
+        std::sort(key.begin(), key.end());
+        // thread-major storage [r][thread]: lane-consecutive reads hit consecutive entries
+        for (uint32_t e = 0; e < batch; e++) sorted[b * batch + e] = key[e].second;
       }
-      std::sort(key.begin(), key.end());
-      // thread-major storage [r][thread]: lane-consecutive reads hit consecutive entries
-      for (uint32_t e = 0; e < batch; e++) sorted[b * batch + e] = key[e].second;
+      DevBuf& dst = pass == 0 ? h->d_seqsorted : h->d_seqfine;
+      CU_TRY(h, dst.ensure(kNumDistSeq * sizeof(uint32_t)));
+      CU_TRY(h, cudaMemcpyAsync(dst.p, sorted.data(), kNumDistSeq * sizeof(uint32_t),
+                                cudaMemcpyHostToDevice, h->stream));
+      CU_TRY(h, cudaStreamSynchronize(h->stream));
     }
-    CU_TRY(h, h->d_seqsorted.ensure(kNumDistSeq * sizeof(uint32_t)));
-    CU_TRY(h, cudaMemcpyAsync(h->d_seqsorted.p, sorted.data(), kNumDistSeq * sizeof(uint32_t),
-                              cudaMemcpyHostToDevice, h->stream));
-    CU_TRY(h, cudaStreamSynchronize(h->stream));
     // bins4_kernel: the same order over mega-batches of 16384 codes, plus the nibble codes
     // in plain traversal order (for the few kept probes)
     std::vector<uint32_t> mega(kNumDistSeq, 0u), plain(kNumDistSeq, 0u);
@@ -412,7 +422,10 @@ int launch_bins_p4(pqt_index* h, const pqt_params& P, uint32_t max_vec, uint32_t
                    uint32_t* dbg_nbins) {
   const uint32_t n_probes = P.max_trials * P.bin_threads;
   const double density = (double)h->n_nonempty / (double)std::max<uint32_t>(1u, h->db_hash_size);
-  const bool early_stop_likely = density * kBins3Batch * 2.0 >= (double)P.max_bins;
+  // the walk ends after max_bins kept bins or max_vec listed candidates, whichever comes first
+  const double vec_per_probe = (double)h->N / (double)std::max<uint32_t>(1u, h->db_hash_size);
+  const bool early_stop_likely = density * kBins3Batch * 2.0 >= (double)P.max_bins ||
+                                 (!dbg_bins && vec_per_probe * kBins3Batch * 2.0 >= (double)max_vec);
   static const int force = getenv("PQT_BINS_KERNEL") ? atoi(getenv("PQT_BINS_KERNEL")) : 0;  // 3 / 4: A/B runs
   const bool use4 = force == 4 || (force != 3 && !early_stop_likely && n_probes > kBins3Batch);
   uint32_t grid = std::min<uint32_t>(nq, (uint32_t)h->num_sms * 6);
@@ -451,16 +464,23 @@ int launch_bins_p4(pqt_index* h, const pqt_params& P, uint32_t max_vec, uint32_t
     a.n_probes = n_probes;
     a.max_bins = P.max_bins; a.max_vec_per_bin = P.max_vec_per_bin; a.max_vec = max_vec;
     a.cand_pos = cand_pos; a.n_vec = n_vec; a.dbg_bins = dbg_bins; a.dbg_nbins = dbg_nbins;
-    const size_t smem = (size_t)(P.max_bins + kBins3Batch + 2 * 256 + kBins3Batch / 32 + 32) * 4;
+    // dense index: a 1024-code batch already lists a good part of the max_vec candidates, so
+    // the candidate-count stop is checked after every 1024 codes; otherwise 4096-code batches
+    const bool fine = vec_per_probe * kBins3FineBatch * 8.0 >= (double)max_vec && !dbg_bins;
+    if (fine) a.seq_sorted = h->d_seqfine.as<uint32_t>();
+    const size_t smem = bins3_smem_bytes(P.max_bins, fine ? kBins3FineProbes : kProbesPerThread);
+#define LAUNCH_BINS3(NP, PPTV)                                                                       \
+  do {                                                                                               \
+    if (smem > 48 * 1024)                                                                            \
+      CU_TRY(h, cudaFuncSetAttribute(bins3_kernel<NP, PPTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    bins3_kernel<NP, PPTV><<<grid, kBins2Threads, smem, h->stream>>>(a);                             \
+  } while (0)
     if (h->p <= 2) {
-      if (smem > 48 * 1024)
-        CU_TRY(h, cudaFuncSetAttribute(bins3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      bins3_kernel<1><<<grid, kBins2Threads, smem, h->stream>>>(a);
+      if (fine) LAUNCH_BINS3(1, kBins3FineProbes); else LAUNCH_BINS3(1, kProbesPerThread);
     } else {
-      if (smem > 48 * 1024)
-        CU_TRY(h, cudaFuncSetAttribute(bins3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      bins3_kernel<2><<<grid, kBins2Threads, smem, h->stream>>>(a);
+      if (fine) LAUNCH_BINS3(2, kBins3FineProbes); else LAUNCH_BINS3(2, kProbesPerThread);
     }
+#undef LAUNCH_BINS3
   }
   CU_TRY(h, cudaGetLastError());
   h->stats.kernel_launches++;
@@ -582,7 +602,7 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
       h->dbg_big_QN = QN;
       h->dbg_big_cap = a.list_cap;
     }
-    size_t smem = (size_t)(4 * kBigInter + 2 * kBigThreads + 4 * kBigKMax + a.list_cap + 32 + 4) * 4;
+    size_t smem = (size_t)(4 * kBigInter + 2 * kBigThreads + 4 * kBigKMax + a.list_cap + 32 + 4) * 4 + 2 * kBigThreads;
     if (smem > 48 * 1024)
       CU_TRY(h, cudaFuncSetAttribute(bins_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 2);
@@ -638,9 +658,85 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
     // fused scan + rank: 4 thread groups per CTA over the canonical c^2 table when that fits
     // (LP <= 16), else 2 groups over the replicated table
     const size_t kSmemMax = 227 * 1024;
-    const bool four = h->LP <= 16 && rerank_smem_bytes(h->c1, h->LP, max_vec, 4, false) <= kSmemMax;
+    // cp.async.bulk moves multiples of 16 bytes: the canonical c^2 table (c1*c1*LP floats) must
+    // be one, else the replicated layout (32-float rows) is used
+    const bool four = h->LP <= 16 && ((h->c1 * h->c1 * h->LP) % 4u) == 0 &&
+                      rerank_smem_bytes(h->c1, h->LP, max_vec, 4, false) <= kSmemMax;
     const size_t smem_fused = four ? rerank_smem_bytes(h->c1, h->LP, max_vec, 4, false)
                                    : rerank_smem_bytes(h->c1, h->LP, max_vec, 2, true);
+    // Split pipeline (lineparts 16 / 32, unsharded): a pure streaming scan kernel writes the
+    // distances, the ranking kernel (4 CTAs per SM) sorts and emits.  The scan is the HBM-bound
+    // part and runs without any ranking state in its way; PQT_SCAN_MODE=fused selects the fused
+    // kernel instead (A/B runs).
+    const char* env_mode = getenv("PQT_SCAN_MODE");
+    const bool want_split = env_mode ? (strcmp(env_mode, "split") == 0) : true;
+    h->split_ranked = false;
+    const bool pull_split = h->world > 1;
+    if (fused_out_dist && want_split && (h->LP == 16 || h->LP == 32) && max_vec >= 256 &&
+        max_vec <= 4096 && stream_scan_smem_bytes(h->c1, h->LP, h->LP == 32) <= kSmemMax) {
+      CU_TRY(h, h->s_val.ensure((size_t)QN * max_vec * 4));
+      StreamScanArgs sa{};
+      sa.codes = h->d_codes.as<uint32_t>();
+      sa.cand_pos = h->s_cand.as<uint32_t>();
+      sa.n_vec = h->s_nvec.as<uint32_t>();
+      sa.lut_dup = h->s_lut.as<float>();
+      sa.cbd = h->LP == 32 ? h->d_cbd_dup.as<float>() : h->d_cbd.as<float>();
+      sa.QN = QN; sa.c1 = h->c1; sa.max_vec = max_vec;
+      sa.out_val = h->s_val.as<float>();
+      if (pull_split) {
+        if (h->c_world != h->world) return fail(h, PQT_ERR_STATE, "code slices of the other shards are not connected");
+        sa.n_shards = h->world;
+        for (uint32_t r = 0; r <= h->world; r++) sa.shard_lo[r] = (uint32_t)((uint64_t)h->N * r / h->world);
+        for (uint32_t r = 0; r < h->world; r++) sa.codes_adj[r] = h->c_peer[r] - (size_t)sa.shard_lo[r] * h->LP;
+      }
+      const size_t ssmem = stream_scan_smem_bytes(h->c1, h->LP, h->LP == 32);
+      const uint32_t sgrid = std::min<uint32_t>(QN, (uint32_t)h->num_sms);
+#define LAUNCH_STREAM(LPV, CREPV, PULLV)                                                            \
+  do {                                                                                              \
+    CU_TRY(h, cudaFuncSetAttribute(adc_stream_kernel<LPV, CREPV, 512, PULLV>,                       \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));        \
+    adc_stream_kernel<LPV, CREPV, 512, PULLV><<<sgrid, 512, ssmem, h->stream>>>(sa);                 \
+  } while (0)
+      if (h->LP == 32) {
+        if (pull_split) LAUNCH_STREAM(32, true, true); else LAUNCH_STREAM(32, true, false);
+      } else {
+        if (pull_split) LAUNCH_STREAM(16, false, true); else LAUNCH_STREAM(16, false, false);
+      }
+#undef LAUNCH_STREAM
+      h->stats.stream_scan_launches++;
+      CU_TRY(h, cudaGetLastError());
+      h->stats.kernel_launches++;
+      h->stats.scan_launches++;
+      if (h->profile) {
+        CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+        CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
+      }
+      Rank2Args ra{};
+      ra.val = h->s_val.as<float>();
+      ra.idx = h->s_cand.as<uint32_t>();
+      ra.ids = h->d_dbidx.as<uint32_t>() + (pull_split ? 0u : h->pos_lo);  // pull: global positions
+      ra.QN = QN; ra.max_vec = max_vec; ra.k = k;
+      ra.out_dist = fused_out_dist; ra.out_idx = fused_out_idx;
+      ra.exact_counter = h->d_exact.as<unsigned long long>();
+      ra.tie_counter = h->d_exact.as<unsigned long long>() + 1;
+      ra.n_vec = h->s_nvec.as<uint32_t>();
+      ra.fast_rank = (P.rank_mode == 0) ? 1u : 0u;
+      const size_t rsmem = rank2_smem_bytes(max_vec);
+      if (rsmem > 48 * 1024)
+        CU_TRY(h, cudaFuncSetAttribute(rank2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+      rank2_kernel<false><<<std::min<uint32_t>(QN, (uint32_t)h->num_sms * 4), kRank2Threads, rsmem, h->stream>>>(ra);
+      CU_TRY(h, cudaGetLastError());
+      h->stats.kernel_launches++;
+      if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+      h->split_ranked = true;
+      if (h->debug && h->world == 1) {
+        gather_select_idx_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(
+            h->s_cand.as<uint32_t>(), h->s_nvec.as<uint32_t>(), h->d_dbidx.as<uint32_t>(), QN, max_vec,
+            h->g_sel.as<uint32_t>());
+        CU_TRY(h, cudaGetLastError());
+      }
+      return PQT_OK;
+    }
     if (fused_out_dist && smem_fused <= kSmemMax) {
       RerankArgs g{};
       g.s = a;
@@ -651,6 +747,9 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
       g.exact_counter = h->d_exact.as<unsigned long long>();
       g.tie_counter = h->d_exact.as<unsigned long long>() + 1;
       g.fast_rank = (P.rank_mode == 0) ? 1u : 0u;
+      const int env_dedupe = getenv("PQT_RERANK_DEDUPE") ? atoi(getenv("PQT_RERANK_DEDUPE")) : 1;  // A/B runs
+      const int env_tpb = getenv("PQT_RERANK_TPB") ? atoi(getenv("PQT_RERANK_TPB")) : 512;
+      g.dedupe = env_dedupe ? 1u : 0u;
       CU_TRY(h, h->d_sched.ensure(4));
       CU_TRY(h, cudaMemsetAsync(h->d_sched.p, 0, 4, h->stream));
       g.next_query = h->d_sched.as<uint32_t>();
@@ -675,6 +774,13 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused)); \
     rerank_kernel<LPV, NGV, CREPV><<<grid, kScanThreads, smem_fused, h->stream>>>(g);            \
   } while (0)
+      // lineparts = 32: two groups of 256 threads with 128 registers each (pipelined scan)
+#define LAUNCH_RERANK_512(PULLV)                                                                 \
+  do {                                                                                           \
+    CU_TRY(h, cudaFuncSetAttribute(rerank_kernel<32, 2, true, PULLV, 512>,                       \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused)); \
+    rerank_kernel<32, 2, true, PULLV, 512><<<grid, 512, smem_fused, h->stream>>>(g);             \
+  } while (0)
       if (pull) {
         if (four) {
           CU_TRY(h, cudaFuncSetAttribute(rerank_kernel<16, 4, false, true>,
@@ -684,6 +790,8 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
           CU_TRY(h, cudaFuncSetAttribute(rerank_kernel<16, 2, true, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused));
           rerank_kernel<16, 2, true, true><<<grid, kScanThreads, smem_fused, h->stream>>>(g);
+        } else if (env_tpb == 512) {
+          LAUNCH_RERANK_512(true);
         } else {
           CU_TRY(h, cudaFuncSetAttribute(rerank_kernel<32, 2, true, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused));
@@ -704,9 +812,12 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
           case 4: LAUNCH_RERANK(4, 2, true); break;
           case 8: LAUNCH_RERANK(8, 2, true); break;
           case 16: LAUNCH_RERANK(16, 2, true); break;
-          default: LAUNCH_RERANK(32, 2, true); break;
+          default:
+            if (env_tpb == 512) LAUNCH_RERANK_512(false); else LAUNCH_RERANK(32, 2, true);
+            break;
         }
       }
+#undef LAUNCH_RERANK_512
 #undef LAUNCH_RERANK
     } else if (smem <= 220 * 1024) {
       uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms);
@@ -756,9 +867,9 @@ int run_rank(pqt_index* h, const float* d_val, const uint32_t* d_idx, uint32_t Q
   a.fast_rank = (h->prm.rank_mode == 0) ? 1u : 0u;
   size_t smem = rank2_smem_bytes(max_vec);
   if (smem > 48 * 1024)
-    CU_TRY(h, cudaFuncSetAttribute(rank2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(h, cudaFuncSetAttribute(rank2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 4);
-  rank2_kernel<<<grid, kRank2Threads, smem, h->stream>>>(a);
+  rank2_kernel<true><<<grid, kRank2Threads, smem, h->stream>>>(a);
   CU_TRY(h, cudaGetLastError());
   h->stats.kernel_launches++;
   return PQT_OK;
@@ -874,7 +985,7 @@ int pqt_destroy(pqt_index* h) {
   if (!h) return PQT_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  for (DevBuf* b : {&h->d_cb1, &h->d_cb2, &h->d_cb1T, &h->d_cb2T, &h->d_distseq, &h->d_seqnib, &h->d_seqsorted, &h->d_seqmega, &h->d_seqplain, &h->d_seq2d, &h->s_topv, &h->s_topi, &h->g_bigbins, &h->g_bignbins, &h->d_bitmap, &h->d_rank_base, &h->d_cprefix,
+  for (DevBuf* b : {&h->d_cb1, &h->d_cb2, &h->d_cb1T, &h->d_cb2T, &h->d_distseq, &h->d_seqnib, &h->d_seqsorted, &h->d_seqfine, &h->d_seqmega, &h->d_seqplain, &h->d_seq2d, &h->s_topv, &h->s_topi, &h->g_bigbins, &h->g_bignbins, &h->d_bitmap, &h->d_rank_base, &h->d_cprefix,
                     &h->d_dbidx, &h->d_codes, &h->d_cbd, &h->d_cbd_dup, &h->s_q, &h->s_lut, &h->s_idx16,
                     &h->s_cand, &h->s_nvec, &h->s_val, &h->s_idx, &h->s_outd, &h->s_outi, &h->g_assign,
                     &h->g_lut, &h->g_aval, &h->g_aidx, &h->g_bins, &h->g_nbins, &h->g_sel, &h->d_exact, &h->x_val, &h->x_idx})
@@ -1520,7 +1631,7 @@ static int query_common(pqt_index* h, const float* Q, int q_on_device, uint32_t 
     uint32_t* oi = d_out_idx + (size_t)q0 * k;
     if (fused) {
       PQ_TRY(run_scan_chain(h, q, n, k, nullptr, nullptr, od, oi, big));
-      if (h->profile) {
+      if (h->profile && !h->split_ranked) {
         CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
         CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
       }
@@ -1761,6 +1872,7 @@ int pqt_shard_candidates(pqt_index* h, const float* Q, int q_on_device, uint32_t
     CU_TRY(h, cudaGetLastError());
   }
   if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[1], h->stream));
+  h->x_lut_QN = QN;
   PQ_TRY(launch_bins_p4(h, P, max_vec, nq, h->s_idx16.as<uint32_t>(), cand_pos + (size_t)q_lo * max_vec,
                         n_vec + q_lo, nullptr, nullptr));
   if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
@@ -1786,6 +1898,7 @@ int pqt_shard_scan_p2p(pqt_index* h, uint32_t QN, uint32_t k, const uint32_t* ca
   if (!h->x_world || h->x_world != h->world) return fail(h, PQT_ERR_STATE, "exchange buffers are not connected (pqt_shard_exchange_open / _set_peers)");
   if (max_vec != h->x_max_vec) return fail(h, PQT_ERR_INVALID, "candidate width %u differs from the exchange buffers' %u", max_vec, h->x_max_vec);
   if ((uint64_t)h->x_q_per_rank * h->world < QN) return fail(h, PQT_ERR_INVALID, "QN exceeds q_per_rank * world");
+  if (h->x_lut_QN != QN) return fail(h, PQT_ERR_STATE, "pqt_shard_scan_p2p needs the LUTs of the same %u queries (pqt_shard_candidates was called for %u)", QN, h->x_lut_QN);
   ScanArgs a{};
   a.codes = h->d_codes.as<uint32_t>();
   a.ids = h->d_dbidx.as<uint32_t>() + h->pos_lo;
@@ -1858,7 +1971,7 @@ int pqt_shard_rank(pqt_index* h, const uint32_t* n_vec_own, uint32_t q_own, uint
   if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
   size_t smem = rank2_smem_bytes(max_vec);
   if (smem > 48 * 1024)
-    CU_TRY(h, cudaFuncSetAttribute(rank2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(h, cudaFuncSetAttribute(rank2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // host outputs: rank in slabs so that the device->host copy of one slab overlaps the
   // ranking of the next (same scheme as pqt_query_knn)
   const uint32_t slab = out_on_device ? q_own : std::min<uint32_t>(q_own, kSlabQueries);
@@ -1890,7 +2003,7 @@ int pqt_shard_rank(pqt_index* h, const uint32_t* n_vec_own, uint32_t q_own, uint
     a.exact_counter = h->d_exact.as<unsigned long long>();
     a.fast_rank = (h->prm.rank_mode == 0) ? 1u : 0u;
     a.n_vec = n_vec_own + q0;
-    rank2_kernel<<<std::min<uint32_t>(n, (uint32_t)h->num_sms * 4), kRank2Threads, smem, h->stream>>>(a);
+    rank2_kernel<true><<<std::min<uint32_t>(n, (uint32_t)h->num_sms * 4), kRank2Threads, smem, h->stream>>>(a);
     CU_TRY(h, cudaGetLastError());
     h->stats.kernel_launches++;
     if (!out_on_device) {

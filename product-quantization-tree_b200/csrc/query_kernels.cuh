@@ -419,59 +419,94 @@ __global__ void __launch_bounds__(kBinsThreads) bins_kernel(BinsArgs a) {
 // ROWS: the code rows of the candidates may live in different allocations (shards mapped
 // from peer GPUs): `row` = this lane's candidate's code row and the 64-bit pointer is
 // shuffled instead of the position.
+// Split in two so that a caller can issue the loads of the next step before it evaluates the
+// current one (software pipelining, rerank_kernel):
+//   adc_load_rows   the LP code words of this lane (line part lp of the LP candidates of its lane
+//                   group), one coalesced row read per candidate
+//   adc_eval_rows   table look-ups, dist(), summation butterfly -> distance of the lane's candidate
+template <int LP, bool ROWS>
+__device__ __forceinline__ void adc_load_rows(uint32_t (&w)[LP], uint32_t pos,
+                                              const uint32_t* __restrict__ codes_lp, uint32_t lp,
+                                              const uint32_t* row) {
+#pragma unroll
+  for (int s = 0; s < LP; s++) {
+    if (ROWS) {
+      const unsigned long long rp =
+          __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)row, s, LP);
+      w[s] = __ldg(reinterpret_cast<const uint32_t*>((uintptr_t)rp) + lp);
+    } else {
+      // position of candidate s of this lane group (shuffle inside the LP-lane segment)
+      const uint32_t cpos = __shfl_sync(0xffffffffu, pos, s, LP);
+      w[s] = __ldg(codes_lp + (size_t)cpos * LP);
+    }
+  }
+}
+
+// partial distance of one line code (Step E2, :5295-5310)
+template <uint32_t CROW>
+__device__ __forceinline__ float adc_code_dist(uint32_t w, uint32_t lut_b, uint32_t cbd_b, uint32_t c1,
+                                               uint32_t sel) {
+  // lineDescr {p1, p2, lambda} (pqt/PerturbationProTree.hh:21-25); one multiply-add per
+  // table address: column base + row * row bytes
+  const uint32_t p1 = w & 0xFFu;
+  const uint32_t p2 = __byte_perm(w, 0u, 0x4441u);
+  uint32_t aa, ab, ac, pr;
+  asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(aa) : "r"(p1), "r"(lut_b));
+  asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(ab) : "r"(p2), "r"(lut_b));
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(pr) : "r"(p2), "r"(c1), "r"(p1));
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ac) : "r"(pr), "n"(CROW * 4u), "r"(cbd_b));
+  // toFloat (pqt/triangle.cuh:14-18): u16 dropped into the mantissa of 2^23, one FFMA
+  const float lam = __fmaf_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, sel)), 1.220703125e-4f, -1028.f);
+  const float a2 = lds_f32(aa);
+  const float b2 = lds_f32(ab);
+  const float c2 = lds_f32(ac);
+  return tri_dist(a2, b2, c2, lam);
+}
+
+template <int LP, uint32_t CROW>
+__device__ __forceinline__ float adc_eval_rows(const uint32_t (&w)[LP], uint32_t lut_b, uint32_t cbd_b,
+                                               uint32_t c1, uint32_t lp) {
+  // byte selector of the lambda conversion, pinned in a register for the whole step (the
+  // compiler would otherwise re-create it next to every use)
+  uint32_t sel;
+  asm volatile("mov.u32 %0, 0x7632;" : "=r"(sel));
+  if constexpr (LP == 1) {
+    return adc_code_dist<CROW>(w[0], lut_b, cbd_b, c1, sel);
+  } else {
+    // The first butterfly stage (distance LP/2) is applied as soon as the two partial distances
+    // it pairs exist, so only LP/2 sums stay live (same operand pairs as the reference's tree).
+    constexpr int HF = LP / 2;
+    float d[HF];
+    const bool up0 = (lp & (uint32_t)HF) != 0u;
+#pragma unroll
+    for (int s = 0; s < HF; s++) {
+      const float d0 = adc_code_dist<CROW>(w[s], lut_b, cbd_b, c1, sel);
+      const float d1 = adc_code_dist<CROW>(w[s + HF], lut_b, cbd_b, c1, sel);
+      const float send = up0 ? d0 : d1;
+      const float keep = up0 ? d1 : d0;
+      d[s] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, HF));
+    }
+#pragma unroll
+    for (int st = HF >> 1; st > 0; st >>= 1) {
+      const bool up = (lp & (uint32_t)st) != 0u;
+#pragma unroll
+      for (int s = 0; s < st; s++) {
+        const float send = up ? d[s] : d[s + st];
+        const float keep = up ? d[s + st] : d[s];
+        d[s] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, st));
+      }
+    }
+    return d[0];
+  }
+}
+
 template <int LP, uint32_t CROW, bool ROWS = false>
 __device__ __forceinline__ float adc_warp_step(uint32_t pos, const uint32_t* __restrict__ codes_lp,
                                                uint32_t lut_b, uint32_t cbd_b, uint32_t c1, uint32_t lp,
                                                const uint32_t* row = nullptr) {
-  float d[LP];
-  {
-    uint32_t w[LP];
-#pragma unroll
-    for (int s = 0; s < LP; s++) {
-      if (ROWS) {
-        const unsigned long long rp =
-            __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)row, s, LP);
-        w[s] = __ldg(reinterpret_cast<const uint32_t*>((uintptr_t)rp) + lp);
-      } else {
-        // position of candidate s of this lane group (shuffle inside the LP-lane segment)
-        const uint32_t cpos = __shfl_sync(0xffffffffu, pos, s, LP);
-        w[s] = __ldg(codes_lp + (size_t)cpos * LP);
-      }
-    }
-    // byte selector of the lambda conversion, pinned in a register for the whole step (the
-    // compiler would otherwise re-create it next to every use)
-    uint32_t sel;
-    asm volatile("mov.u32 %0, 0x7632;" : "=r"(sel));
-#pragma unroll
-    for (int s = 0; s < LP; s++) {
-      // lineDescr {p1, p2, lambda} (pqt/PerturbationProTree.hh:21-25); one multiply-add per
-      // table address: column base + row * row bytes
-      const uint32_t p1 = w[s] & 0xFFu;
-      const uint32_t p2 = __byte_perm(w[s], 0u, 0x4441u);
-      uint32_t aa, ab, ac, pr;
-      asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(aa) : "r"(p1), "r"(lut_b));
-      asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(ab) : "r"(p2), "r"(lut_b));
-      asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(pr) : "r"(p2), "r"(c1), "r"(p1));
-      asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ac) : "r"(pr), "n"(CROW * 4u), "r"(cbd_b));
-      // toFloat (pqt/triangle.cuh:14-18): u16 dropped into the mantissa of 2^23, one FFMA
-      const float lam = __fmaf_rn(__uint_as_float(__byte_perm(w[s], 0x4B000000u, sel)), 1.220703125e-4f, -1028.f);
-      const float a2 = lds_f32(aa);
-      const float b2 = lds_f32(ab);
-      const float c2 = lds_f32(ac);
-      d[s] = tri_dist(a2, b2, c2, lam);
-    }
-  }
-#pragma unroll
-  for (int st = LP >> 1; st > 0; st >>= 1) {
-    const bool up = (lp & (uint32_t)st) != 0u;
-#pragma unroll
-    for (int s = 0; s < st; s++) {
-      const float send = up ? d[s] : d[s + st];
-      const float keep = up ? d[s + st] : d[s];
-      d[s] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, st));
-    }
-  }
-  return d[0];
+  uint32_t w[LP];
+  adc_load_rows<LP, ROWS>(w, pos, codes_lp, lp, row);
+  return adc_eval_rows<LP, CROW>(w, lut_b, cbd_b, c1, lp);
 }
 
 struct ScanArgs {
@@ -1084,6 +1119,7 @@ __global__ void __launch_bounds__(kTablesWarps * 32) tables_warp_kernel(TablesWa
           case 64: warp_sort_regs<2>(sv, si, lane); break;
           case 128: warp_sort_regs<4>(sv, si, lane); break;
           case 256: warp_sort_regs<8>(sv, si, lane); break;
+          case 512: warp_sort_regs<16>(sv, si, lane); break;  // k1 = 16 cells (the 1-B variant)
           default: bitonic_warp_smem(sv, si, a.npC, lane); break;
         }
         if (lane < 16) a.idx16[((size_t)qi * a.p + part) * 16 + lane] = (lane < a.m) ? si[lane] : 0u;

@@ -182,18 +182,26 @@ __global__ void __launch_bounds__(kBins2Threads) bins2_kernel(Bins2Args a) {
 }
 
 // ============================================================================
-// Steps D + E1, v3 (p <= 4): same walk as bins2_kernel, but inside every batch of 4096
-// traversal codes the probes are visited in a STATIC order sorted by the ranks of all
-// parts but the last.  Probes that share those ranks differ only in the last Horner
-// digit (< c1*c2), so their bins fall into one 128-byte line of the bitmap when
+// Steps D + E1, v3 (p <= 4): same walk as bins2_kernel, but inside every batch of
+// kBins2Threads * PPT traversal codes the probes are visited in a STATIC order sorted by the
+// ranks of all parts but the last.  Probes that share those ranks differ only in the last
+// Horner digit (< c1*c2), so their bins fall into one 128-byte line of the bitmap when
 // c1*c2 <= 1024: neighbouring lanes then share L1 wavefronts instead of touching 32
 // different lines per load (bins2: 77-92 % of the L1 tag bandwidth).  Kept probes are
 // put back into traversal order through a per-batch bit array before the ordered
 // compaction, so the bin list is identical.
+//
+// Step E1 runs after every batch over the bins that became final, and the walk stops as soon
+// as max_vec candidates are listed: nothing behind that point can reach cand_pos / n_vec (the
+// reference's E1 loop ends there, :4339-4417), so the remaining probes -- random sector reads
+// of a bitmap that a 1-B index's code traffic keeps evicting from L2 -- are skipped.  On a
+// dense index (1 B vectors: most probed bins are occupied) PPT = 4 visits ~2 k of the 8 k
+// codes the bin-count stop (max_bins kept) would need.  The debug bin list disables the early
+// stop (it wants every kept bin).
 // ============================================================================
 struct Bins3Args {
   const uint32_t* idx16;       // [QN][p][16]
-  const uint32_t* seq_sorted;  // [16 batches][4096]: (rank inside the batch << 16) | nibble code
+  const uint32_t* seq_sorted;  // [65536 / batch][batch]: (rank inside the batch << 16) | nibble code
   BinDir dir;
   MagicMod hash;
   uint32_t QN, p, c1c2;
@@ -206,16 +214,25 @@ struct Bins3Args {
 };
 
 constexpr int kBins3Batch = kBins2Threads * kProbesPerThread;  // 4096
+constexpr int kBins3FineProbes = 4;                            // probes per thread of the dense-index variant
+constexpr int kBins3FineBatch = kBins2Threads * kBins3FineProbes;  // 1024
 
-// dynamic smem: list[max_bins] | binbuf[4096] | pairs[2][256] | bits[128] | warp_sums[32]
-template <int NPAIRS>
+inline size_t bins3_smem_bytes(uint32_t max_bins, int ppt) {
+  const size_t batch = (size_t)kBins2Threads * ppt;
+  return (max_bins + std::max<size_t>(batch, 2 * kBins2Threads) + 2 * 256 + batch / 32 + 32) * 4;
+}
+
+// dynamic smem: list[max_bins] | binbuf[max(batch, 512)] | pairs[2][256] | bits[batch/32] | warp_sums[32]
+template <int NPAIRS, int PPT>
 __global__ void __launch_bounds__(kBins2Threads, 6) bins3_kernel(Bins3Args a) {
+  constexpr uint32_t kBatch = kBins2Threads * PPT;
+  constexpr uint32_t kBuf = kBatch > 2u * kBins2Threads ? kBatch : 2u * kBins2Threads;
   extern __shared__ uint32_t smem_u[];
   uint32_t* list = smem_u;
   uint32_t* binbuf = list + a.max_bins;
-  uint32_t* pairs = binbuf + kBins3Batch;
+  uint32_t* pairs = binbuf + kBuf;
   uint32_t* bits = pairs + 2 * 256;
-  uint32_t* warp_sums = bits + kBins3Batch / 32;
+  uint32_t* warp_sums = bits + kBatch / 32;
   const uint32_t K = a.c1c2;
   const uint32_t p = a.p;
   // multiplier that moves the first pair past the second pair (or single last part)
@@ -238,18 +255,56 @@ __global__ void __launch_bounds__(kBins2Threads, 6) bins3_kernel(Bins3Args a) {
     __syncthreads();
 
     uint32_t n_out = 0;
-    for (uint32_t b0 = 0; b0 < n_probes && n_out < max_bins; b0 += kBins3Batch) {
-      if (threadIdx.x < kBins3Batch / 32) bits[threadIdx.x] = 0;
+    uint32_t offset = 0;     // candidates listed so far (unclipped, as the reference's scan offset)
+    uint32_t done_bins = 0;  // list entries Step E1 has consumed
+    uint32_t* cand = a.cand_pos + (size_t)qi * a.max_vec;
+    uint32_t* s_pos = binbuf;  // E1 staging: the probe buffer is free between batches
+    uint32_t* s_start = binbuf + kBins2Threads;
+    // ---- Step E1 (:4339-4417) over list entries [done_bins, upto).  The candidate slots of a
+    // chunk of bins are written by the whole CTA (slot -> bin by binary search over the chunk's
+    // exclusive scan): coalesced stores, and a bin with hundreds of vectors does not serialise
+    // one thread.
+    auto step_e1 = [&](uint32_t upto) {
+      for (uint32_t c0 = done_bins; c0 < upto && offset < a.max_vec; c0 += blockDim.x) {
+        uint32_t b = c0 + threadIdx.x;
+        uint32_t start = 0, nv = 0;
+        if (b < upto) {
+          uint32_t cnt;
+          dir_lookup(a.dir, list[b], start, cnt);
+          nv = cnt < a.max_vec_per_bin ? cnt : a.max_vec_per_bin;
+        }
+        uint32_t total;
+        const uint32_t pos = offset + block_exscan(nv, warp_sums, total);
+        s_pos[threadIdx.x] = pos;
+        s_start[threadIdx.x] = start;
+        __syncthreads();
+        const uint32_t hi = offset + total < a.max_vec ? offset + total : a.max_vec;
+        for (uint32_t slot = offset + threadIdx.x; slot < hi; slot += blockDim.x) {
+          // the bin that holds this slot = the last one whose first slot is <= slot
+          uint32_t j = 0;
+#pragma unroll
+          for (uint32_t step = kBins2Threads >> 1; step > 0; step >>= 1)
+            if (s_pos[j + step] <= slot) j += step;
+          cand[slot] = s_start[j] + (slot - s_pos[j]);
+        }
+        offset += total;
+        __syncthreads();
+      }
+      done_bins = upto;
+    };
+
+    for (uint32_t b0 = 0; b0 < n_probes && n_out < max_bins; b0 += kBatch) {
+      if (threadIdx.x < kBatch / 32) bits[threadIdx.x] = 0;
       __syncthreads();
       // only the loaded bitmap words (and the bit position inside them, 5 bits each) stay in
-      // registers while the 16 probes are in flight; bins of the few kept probes are
+      // registers while the probes are in flight; bins of the few kept probes are
       // recomputed -- keeps the kernel at 6 CTAs per SM
-      uint32_t words[kProbesPerThread];
-      uint32_t sh[kProbesPerThread / 4];
+      uint32_t words[PPT];
+      uint32_t sh[(PPT + 3) / 4];
 #pragma unroll
-      for (int r = 0; r < kProbesPerThread / 4; r++) sh[r] = 0;
+      for (int r = 0; r < (PPT + 3) / 4; r++) sh[r] = 0;
 #pragma unroll
-      for (int r = 0; r < kProbesPerThread; r++) {
+      for (int r = 0; r < PPT; r++) {
         const uint32_t ent = __ldg(a.seq_sorted + b0 + r * kBins2Threads + threadIdx.x);
         uint32_t o = pairs[ent & 0xFF];
         if (NPAIRS == 2) o = o * mul1 + pairs[256 + ((ent >> 8) & 0xFF)];
@@ -258,7 +313,7 @@ __global__ void __launch_bounds__(kBins2Threads, 6) bins3_kernel(Bins3Args a) {
         words[r] = (b0 + (ent >> 16) < n_probes) ? __ldg(bitmap + (bin >> 5)) : 0u;
       }
 #pragma unroll
-      for (int r = 0; r < kProbesPerThread; r++) {
+      for (int r = 0; r < PPT; r++) {
         if ((words[r] >> ((sh[r >> 2] >> (8 * (r & 3))) & 31u)) & 1u) {
           const uint32_t ent = __ldg(a.seq_sorted + b0 + r * kBins2Threads + threadIdx.x);
           const uint32_t u = ent >> 16;
@@ -270,7 +325,7 @@ __global__ void __launch_bounds__(kBins2Threads, 6) bins3_kernel(Bins3Args a) {
       }
       __syncthreads();
       // ordered compaction in traversal order: thread i owns 32 consecutive probes
-      uint32_t w = (threadIdx.x < kBins3Batch / 32) ? bits[threadIdx.x] : 0u;
+      uint32_t w = (threadIdx.x < kBatch / 32) ? bits[threadIdx.x] : 0u;
       uint32_t total;
       uint32_t pos = n_out + block_exscan(__popc(w), warp_sums, total);
       while (w) {
@@ -280,6 +335,12 @@ __global__ void __launch_bounds__(kBins2Threads, 6) bins3_kernel(Bins3Args a) {
         if (pos < max_bins) list[pos] = binbuf[threadIdx.x * 32 + bit];
       }
       n_out += total;
+      __syncthreads();
+      if (!a.dbg_bins) {
+        // entries below min(n_out, max_bins) are final whatever the rest of the walk keeps
+        step_e1(n_out < max_bins ? n_out : max_bins);
+        if (offset >= a.max_vec) break;
+      }
     }
     __syncthreads();
     const uint32_t nb = n_out < max_bins ? n_out : max_bins;
@@ -289,39 +350,7 @@ __global__ void __launch_bounds__(kBins2Threads, 6) bins3_kernel(Bins3Args a) {
             (e == 0) ? 0u : ((e <= n_out && e < max_bins) ? list[e] : 0u);
       if (threadIdx.x == 0) a.dbg_nbins[qi] = nb;
     }
-
-    // ---- Step E1 (:4339-4417).  The candidate slots of a chunk of bins are written by the
-    // whole CTA (slot -> bin by binary search over the chunk's exclusive scan): coalesced
-    // stores, and a bin with hundreds of vectors does not serialise one thread.
-    uint32_t offset = 0;
-    uint32_t* cand = a.cand_pos + (size_t)qi * a.max_vec;
-    uint32_t* s_pos = binbuf;                  // the probe buffer is free now
-    uint32_t* s_start = binbuf + kBins2Threads;
-    for (uint32_t c0 = 0; c0 < nb && offset < a.max_vec; c0 += blockDim.x) {
-      uint32_t b = c0 + threadIdx.x;
-      uint32_t start = 0, nv = 0;
-      if (b < nb) {
-        uint32_t cnt;
-        dir_lookup(a.dir, list[b], start, cnt);
-        nv = cnt < a.max_vec_per_bin ? cnt : a.max_vec_per_bin;
-      }
-      uint32_t total;
-      const uint32_t pos = offset + block_exscan(nv, warp_sums, total);
-      s_pos[threadIdx.x] = pos;
-      s_start[threadIdx.x] = start;
-      __syncthreads();
-      const uint32_t hi = offset + total < a.max_vec ? offset + total : a.max_vec;
-      for (uint32_t slot = offset + threadIdx.x; slot < hi; slot += blockDim.x) {
-        // the bin that holds this slot = the last one whose first slot is <= slot
-        uint32_t j = 0;
-#pragma unroll
-        for (uint32_t step = kBins2Threads >> 1; step > 0; step >>= 1)
-          if (s_pos[j + step] <= slot) j += step;
-        cand[slot] = s_start[j] + (slot - s_pos[j]);
-      }
-      offset += total;
-      __syncthreads();
-    }
+    step_e1(nb);
     if (threadIdx.x == 0) a.n_vec[qi] = offset < a.max_vec ? offset : a.max_vec;
   }
 }
@@ -605,6 +634,9 @@ __device__ __forceinline__ void rank_and_emit(const Grp& g, float* s_val, uint16
   uint32_t n2 = pow2ceil(nv < 32 ? 32 : nv);
   if (n2 > max_vec) n2 = max_vec;  // max_vec < 32: tiny widths
   const bool full = (n2 == max_vec);
+  // callers arrive here right after reading *s_flag (the verdict of the fast path): nobody may
+  // clear it before every thread of the group has read it
+  g.sync();
   if (t == 0) *s_flag = 0;
   g.sync();
   // payload = candidate position
@@ -697,6 +729,7 @@ struct RerankArgs {
   unsigned long long* exact_counter;  // queries ranked by the exact network (may be null)
   unsigned long long* tie_counter;    // queries whose ties were re-ordered by tie_resolve (may be null)
   uint32_t fast_rank;                 // 1: composite-key sort first (fast_rank.cuh); 0: network only
+  uint32_t dedupe;                    // 1: evaluate repeated candidates once (see rerank_kernel)
   unsigned long long* phase_dbg;      // optional [QN][8] clock64 stamps per query (debug)
   uint32_t* next_query;               // work counter (zeroed before the launch): the thread groups
                                       // draw queries from it, so a slow query does not hold up a
@@ -719,15 +752,19 @@ constexpr int kRerankGroupThreads = kScanThreads / kRerankGroups;  // 512
 // layout, c1*c1*LP*4 bytes; the 32/LP candidates of a warp step may collide on a bank).
 inline size_t rerank_smem_bytes(uint32_t c1, uint32_t LP, uint32_t max_vec, int NG, bool crep) {
   return ((size_t)c1 * c1 * (crep ? 32 : LP) + (size_t)NG * 2 * c1 * 32) * 4 +
-         (size_t)NG * ((size_t)8 * max_vec + 512 + 4 + 16 + 16) + 64;
+         (size_t)NG * ((size_t)8 * max_vec + 512 + 4 + 32 + 16) + 64 + 16;
 }
 
-template <int LP, int NG, bool CREP, bool PULL = false>
-__global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
+// TPB threads per CTA = NG groups of TPB / NG threads.  1024 threads leave 64 registers per
+// thread; the lineparts = 32 configuration runs 512 (two groups of 256 = the 256 sorter threads
+// of a 4096-wide ranking) so that a warp can hold the code rows of TWO warp steps: the loads of
+// the next step are in flight while the current one is evaluated.
+template <int LP, int NG, bool CREP, bool PULL = false, int TPB = kScanThreads>
+__global__ void __launch_bounds__(TPB, 1) rerank_kernel(RerankArgs g) {
   const ScanArgs& a = g.s;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr uint32_t kRerankGroups = NG;
-  constexpr uint32_t kRerankGroupThreads = kScanThreads / NG;
+  constexpr uint32_t kRerankGroupThreads = TPB / NG;
   constexpr uint32_t CROW = CREP ? 32u : (uint32_t)LP;  // floats per row of the c^2 table
   const uint32_t lut_floats = a.c1 * 32;
   const uint32_t cbd_floats = a.c1 * a.c1 * CROW;
@@ -738,19 +775,21 @@ __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
   float* s_luts = s_cbd + cbd_floats;                                  // [groups][2][lut_floats]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_luts + kRerankGroups * 2 * lut_floats);  // [groups][2] + cbd
   uint32_t* s_flags = reinterpret_cast<uint32_t*>(bars + 2 * kRerankGroups + 2);
-  uint32_t* s_red = s_flags + kRerankGroups;                           // [groups][4]: umin, umax, bad, next query
-  uint32_t* s_fixes = s_red + 4 * kRerankGroups;                       // [groups][128]: emit bitmap
-  float* s_arr = reinterpret_cast<float*>(s_fixes + 128 * kRerankGroups);  // [groups][2][max_vec]
+  uint32_t* s_red = s_flags + kRerankGroups;                           // [groups][8]: umin, umax, bad, next query, roots
+  uint32_t* s_fixes = s_red + 8 * kRerankGroups;                       // [groups][128]: emit bitmap
+  float* s_arr = reinterpret_cast<float*>(                               // [groups][2][max_vec], 16-byte aligned
+      (reinterpret_cast<uintptr_t>(s_fixes + 128 * kRerankGroups) + 15u) & ~(uintptr_t)15u);
   float* s_lut0 = s_luts + grp * 2 * lut_floats;
   float* s_lut1 = s_lut0 + lut_floats;
   uint64_t* gbar = bars + 2 * grp;
   uint64_t* cbar = bars + 2 * kRerankGroups;
   uint32_t* s_flag = s_flags + grp;
-  uint32_t* s_min = s_red + 4 * grp;
+  uint32_t* s_min = s_red + 8 * grp;
   uint32_t* s_max = s_min + 1;
   uint32_t* s_bad = s_min + 2;
   uint32_t* s_fix = s_fixes + 128 * grp;
-  uint32_t* s_q = s_min + 3;  // next query of this group
+  uint32_t* s_q = s_min + 3;    // next query of this group
+  uint32_t* s_cnt = s_min + 4;  // first occurrences among the candidates of the current query
   // per group: val f32[max_vec] | scratch u32[max_vec] (composite sort words; the (u16) payload
   // array of the exact network aliases it).  Vector ids are not staged: they are read once,
   // when a result is emitted.
@@ -823,37 +862,158 @@ __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
     if (ph && G.t == 0) ph[1] = clock64();
     G.sync();
     const uint32_t q_next = *s_q;
-    // ---- scan: only chunks that hold real candidates
     const uint32_t lut_b = smem_u32(s_lut) + lane * 4u;
     uint32_t umin = 0xFFFFFFFFu, umax = 0u, bad = 0u;
-    uint32_t pos_next = (warp * 32 + lane < nv) ? __ldg(cand + warp * 32 + lane) : 0u;
-    for (uint32_t base = warp * 32; base < nv; base += nwarps * 32) {
-      const uint32_t ca = base + lane;
-      const bool valid = ca < nv;
-      const uint32_t pos = pos_next;  // 0 for lanes past the end: a valid code row, result unused
-      // the id is read when the result is emitted: pull its sector into L2 now
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ids + pos));
-      {
-        const uint32_t cn = ca + nwarps * 32;
-        pos_next = cn < nv ? __ldg(cand + cn) : 0u;
+    auto note = [&](float v) {
+      const uint32_t u = sortable_key(v);
+      umin = min(umin, u);
+      umax = max(umax, u);
+      // the fast path needs finite distances below the pad value
+      if (!(v < kPadDist) || !(v > -__int_as_float(0x7f800000))) bad = 1u;
+    };
+    // Evaluates the candidates slot_of(0) .. slot_of(M-1), 32 per warp step, software pipelined:
+    // the code rows of step k+1 are requested before step k is evaluated (two register sets),
+    // and the positions are fetched two steps ahead.  Lanes past the end work on element 0 (a
+    // valid row, result unused).
+    auto run_scan = [&](uint32_t M, auto slot_of) {
+      const uint32_t stride = nwarps * 32;
+      auto fetch = [&](uint32_t e, uint32_t& ca, uint32_t& pos) {
+        ca = slot_of(e < M ? e : 0u);
+        pos = __ldg(cand + ca);
+      };
+      auto load = [&](uint32_t (&w)[LP], uint32_t pos) {
+        // the id is read when the result is emitted: pull its sector into L2 now
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ids + pos));
+        if (PULL) {
+          uint32_t r = 0;
+          for (uint32_t i = 1; i < g.n_shards; i++) r += (pos >= g.shard_lo[i]) ? 1u : 0u;
+          adc_load_rows<LP, true>(w, 0u, nullptr, lp, g.codes_adj[r] + (size_t)pos * LP);
+        } else {
+          adc_load_rows<LP, false>(w, pos, codes_lp, lp, nullptr);
+        }
+      };
+      uint32_t e0 = warp * 32 + lane;
+      if (warp * 32 >= M) return;  // warp-uniform
+      uint32_t wA[LP], wB[LP];
+      uint32_t ca0, pos0, ca1, pos1, ca2, pos2;
+      fetch(e0, ca0, pos0);
+      fetch(e0 + stride, ca1, pos1);
+      load(wA, pos0);
+      for (uint32_t base = warp * 32; base < M; base += 2 * stride) {
+        const bool has1 = base + stride < M, has2 = base + 2 * stride < M;
+        if (has1) load(wB, pos1);
+        fetch(e0 + 2 * stride, ca2, pos2);
+        {
+          const float v = adc_eval_rows<LP, CROW>(wA, lut_b, cbd_b, a.c1, lp);
+          if (e0 < M) s_val[ca0] = v;
+        }
+        if (!has1) break;
+        if (has2) load(wA, pos2);
+        uint32_t ca3, pos3;
+        fetch(e0 + 3 * stride, ca3, pos3);
+        {
+          const float v = adc_eval_rows<LP, CROW>(wB, lut_b, cbd_b, a.c1, lp);
+          if (e0 + stride < M) s_val[ca1] = v;
+        }
+        e0 += 2 * stride;
+        ca0 = ca2;
+        pos0 = pos2;
+        ca1 = ca3;
+        pos1 = pos3;
       }
-      float myval;
-      if (PULL) {
-        uint32_t r = 0;
-        for (uint32_t i = 1; i < g.n_shards; i++) r += (pos >= g.shard_lo[i]) ? 1u : 0u;
-        const uint32_t* row = g.codes_adj[r] + (size_t)pos * LP;
-        myval = adc_warp_step<LP, CROW, true>(0u, nullptr, lut_b, cbd_b, a.c1, lp, row);
-      } else {
-        myval = adc_warp_step<LP, CROW>(pos, codes_lp, lut_b, cbd_b, a.c1, lp);
+    };
+    // The same bin can be listed several times (the uint32 Horner hash keeps only idx_0 mod 4
+    // of the first part), so about a third of the candidates of a dense list repeat a code row
+    // that is already in the list.  Repeats are found with a small hash table over the
+    // positions (the sort scratch is free during the scan), only the first occurrences are
+    // evaluated, and the repeats copy their distance -- the same bits the evaluation would
+    // give.  Detection may miss repeats (two table slots per position, no chaining): they are
+    // simply evaluated again.
+    constexpr uint32_t CPT = 4096u / kRerankGroupThreads;  // candidates per thread (max_vec <= 4096)
+    if (g.dedupe && a.max_vec >= 256u && nv >= 128u) {
+      constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+      const uint32_t tbits = 31u - (uint32_t)__clz((int)a.max_vec);
+      for (uint32_t e = G.t; e < a.max_vec; e += G.n) s_cmp[e] = kEmpty;
+      if (G.t == 0) *s_cnt = 0u;
+      G.sync();
+      // every stage for a chunk of the thread's candidates at once: the loads of a stage overlap
+      uint32_t src[CPT];
+      constexpr uint32_t CH = CPT < 8u ? CPT : 8u;
+#pragma unroll
+      for (uint32_t c0 = 0; c0 < CPT; c0 += CH) {
+        uint32_t pos[CH], chk[CH];  // chk: slot whose position has to be compared (key match), or kEmpty
+        uint2 ent[CH];
+#pragma unroll
+        for (uint32_t i = 0; i < CH; i++) {
+          const uint32_t ca = G.t + (c0 + i) * G.n;
+          pos[i] = ca < nv ? __ldg(cand + ca) : 0u;
+        }
+#pragma unroll
+        for (uint32_t i = 0; i < CH; i++) {
+          const uint32_t h = ((pos[i] * 2654435761u) >> (32u - tbits)) & ~1u;  // an aligned pair of slots
+          ent[i] = *reinterpret_cast<const uint2*>(s_cmp + h);
+        }
+#pragma unroll
+        for (uint32_t i = 0; i < CH; i++) {
+          const uint32_t ca = G.t + (c0 + i) * G.n;
+          const uint32_t mix = pos[i] * 2654435761u;
+          const uint32_t key = mix & 0xFFFF0000u;
+          const uint32_t h = (mix >> (32u - tbits)) & ~1u;
+          src[c0 + i] = ca;
+          chk[i] = kEmpty;
+          if (ca < nv) {
+            uint32_t e0 = ent[i].x, e1 = ent[i].y;
+            // register as a first occurrence in the first free slot of the pair
+            if (e0 == kEmpty) e0 = atomicCAS(&s_cmp[h], kEmpty, key | ca);
+            if (e0 != kEmpty) {
+              if (((e0 ^ key) >> 16) == 0u) {
+                chk[i] = e0 & 0xFFFFu;
+              } else {
+                if (e1 == kEmpty) e1 = atomicCAS(&s_cmp[h + 1u], kEmpty, key | ca);
+                if (e1 != kEmpty && ((e1 ^ key) >> 16) == 0u) chk[i] = e1 & 0xFFFFu;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (uint32_t i = 0; i < CH; i++) {
+          if (chk[i] != kEmpty && __ldg(cand + chk[i]) == pos[i]) src[c0 + i] = chk[i];
+        }
       }
-      if (valid) {
-        s_val[ca] = myval;
-        const uint32_t u = sortable_key(myval);
-        umin = min(umin, u);
-        umax = max(umax, u);
-        // the fast path needs finite distances below the pad value
-        if (!(myval < kPadDist) || !(myval > -__int_as_float(0x7f800000))) bad = 1u;
+      G.sync();  // the table is dead: its words now hold src u16[max_vec] | roots u16[max_vec]
+      uint16_t* s_src = reinterpret_cast<uint16_t*>(s_cmp);
+      uint16_t* s_root = s_src + a.max_vec;
+#pragma unroll
+      for (uint32_t i = 0; i < CPT; i++) {
+        const uint32_t ca = G.t + i * G.n;
+        const bool real = ca < nv;
+        const bool root = real && src[i] == ca;
+        if (real) s_src[ca] = (uint16_t)src[i];
+        const uint32_t mask = __ballot_sync(0xffffffffu, root);
+        if (mask) {
+          uint32_t off = 0;
+          if (lane == 0) off = atomicAdd(s_cnt, __popc(mask));
+          off = __shfl_sync(0xffffffffu, off, 0) + __popc(mask & ((1u << lane) - 1u));
+          if (root) s_root[off] = (uint16_t)ca;
+        }
       }
+      G.sync();
+      run_scan(*s_cnt, [&](uint32_t e) { return (uint32_t)s_root[e]; });
+      G.sync();
+#pragma unroll
+      for (uint32_t i = 0; i < CPT; i++) {
+        const uint32_t ca = G.t + i * G.n;
+        if (ca < nv) {
+          const uint32_t sc = s_src[ca];
+          const float v = s_val[sc];
+          if (sc != ca) s_val[ca] = v;
+          note(v);
+        }
+      }
+    } else {
+      run_scan(nv, [&](uint32_t e) { return e; });
+      G.sync();
+      for (uint32_t ca = G.t; ca < nv; ca += G.n) note(s_val[ca]);
     }
     umin = __reduce_min_sync(0xffffffffu, umin);
     umax = __reduce_max_sync(0xffffffffu, umax);
@@ -897,14 +1057,142 @@ __global__ void __launch_bounds__(kScanThreads, 1) rerank_kernel(RerankArgs g) {
   }
 }
 
-// ranking only: candidates already assembled in global memory (multi-GPU path)
+// ============================================================================
+// Step E2, distance part, as a pure streaming kernel (the split pipeline): no ranking state in
+// shared memory, so every warp of the SM streams code rows all the time.  One persistent CTA
+// per SM; all warps work on the same query (its LUT is double-buffered with TMA bulk copies)
+// and every warp keeps the rows of its NEXT 32 candidates in flight while it evaluates the
+// current ones (two register sets).  Writes the distance of candidate slot a to
+// out_val[q][a] (a < nVec); ids are not touched (the ranking kernel reads them when it emits).
+// ============================================================================
+struct StreamScanArgs {
+  const uint32_t* codes;     // [N][LP] line codes in bin order
+  const uint32_t* cand_pos;  // [QN][max_vec]
+  const uint32_t* n_vec;     // [QN]
+  const float* lut_dup;      // [QN][c1][32]
+  const float* cbd;          // [c1*c1][CROW] (replicated rows when CREP)
+  uint32_t QN, c1, max_vec;
+  float* out_val;            // [QN][max_vec]
+  // PULL (multi-GPU, index sharded by bin range): candidate positions are global; the code rows
+  // of shard r live at codes_adj[r] + pos * LP (mapped slice - shard_lo[r] * LP), local or peer
+  // memory read over NVLink
+  uint32_t n_shards;
+  uint32_t shard_lo[9];
+  const uint32_t* codes_adj[8];
+};
+
+inline size_t stream_scan_smem_bytes(uint32_t c1, uint32_t LP, bool crep) {
+  return ((size_t)c1 * c1 * (crep ? 32 : LP) + 2 * (size_t)c1 * 32) * 4 + 64;
+}
+
+template <int LP, bool CREP, int TPB, bool PULL = false>
+__global__ void __launch_bounds__(TPB, 1) adc_stream_kernel(StreamScanArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr uint32_t CROW = CREP ? 32u : (uint32_t)LP;
+  const uint32_t lut_floats = a.c1 * 32;
+  const uint32_t cbd_floats = a.c1 * a.c1 * CROW;
+  float* s_cbd = reinterpret_cast<float*>(smem_raw);
+  float* s_lut0 = s_cbd + cbd_floats;
+  float* s_lut1 = s_lut0 + lut_floats;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lut1 + lut_floats);  // [0],[1]: lut, [2]: cbd
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = TPB >> 5;
+  const uint32_t lp = lane & (LP - 1);
+  const uint32_t cbd_b = smem_u32(s_cbd) + (CREP ? lane : lp) * 4u;
+  const uint32_t* __restrict__ codes_lp = a.codes + lp;
+  if (blockIdx.x >= a.QN) return;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t cbd_bytes = cbd_floats * 4;
+    mbar_expect_tx(&bars[2], cbd_bytes);
+    for (uint32_t off = 0; off < cbd_bytes; off += 32768) {
+      uint32_t n = cbd_bytes - off < 32768 ? cbd_bytes - off : 32768;
+      tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_cbd) + off,
+                   reinterpret_cast<const unsigned char*>(a.cbd) + off, n, &bars[2]);
+    }
+    mbar_expect_tx(&bars[0], lut_floats * 4);
+    tma_bulk_g2s(s_lut0, a.lut_dup + (size_t)blockIdx.x * lut_floats, lut_floats * 4, &bars[0]);
+  }
+  mbar_wait(&bars[2], 0);
+
+  const uint32_t stride = nwarps * 32;
+  uint32_t buf = 0, phase0 = 0, phase1 = 0;
+  for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
+    const uint32_t qn = qi + gridDim.x;
+    if (threadIdx.x == 0 && qn < a.QN) {  // the other buffer's readers passed the barrier below
+      uint64_t* nb = &bars[buf ^ 1];
+      mbar_expect_tx(nb, lut_floats * 4);
+      tma_bulk_g2s(buf ? s_lut0 : s_lut1, a.lut_dup + (size_t)qn * lut_floats, lut_floats * 4, nb);
+    }
+    const uint32_t nv = min(__ldg(a.n_vec + qi), a.max_vec);
+    const uint32_t* cand = a.cand_pos + (size_t)qi * a.max_vec;
+    float* out = a.out_val + (size_t)qi * a.max_vec;
+    // the first two positions of this warp are requested before the LUT wait
+    uint32_t e0 = warp * 32 + lane;
+    uint32_t pos0 = e0 < nv ? __ldg(cand + e0) : 0u;
+    uint32_t pos1 = e0 + stride < nv ? __ldg(cand + e0 + stride) : 0u;
+    const float* s_lut = buf ? s_lut1 : s_lut0;
+    const uint32_t lut_b = smem_u32(s_lut) + lane * 4u;
+    auto load = [&](uint32_t (&w)[LP], uint32_t pos) {
+      if (PULL) {
+        uint32_t r = 0;
+        for (uint32_t i = 1; i < a.n_shards; i++) r += (pos >= a.shard_lo[i]) ? 1u : 0u;
+        adc_load_rows<LP, true>(w, 0u, nullptr, lp, a.codes_adj[r] + (size_t)pos * LP);
+      } else {
+        adc_load_rows<LP, false>(w, pos, codes_lp, lp, nullptr);
+      }
+    };
+    if (warp * 32 < nv) {  // warp-uniform
+      uint32_t wA[LP], wB[LP];
+      load(wA, pos0);
+      mbar_wait(&bars[buf], buf ? phase1 : phase0);
+      for (uint32_t base = warp * 32; base < nv; base += 2 * stride) {
+        const bool has1 = base + stride < nv, has2 = base + 2 * stride < nv;
+        if (has1) load(wB, pos1);
+        const uint32_t pos2 = e0 + 2 * stride < nv ? __ldg(cand + e0 + 2 * stride) : 0u;
+        {
+          const float v = adc_eval_rows<LP, CROW>(wA, lut_b, cbd_b, a.c1, lp);
+          if (e0 < nv) out[e0] = v;
+        }
+        if (!has1) break;
+        if (has2) load(wA, pos2);
+        const uint32_t pos3 = e0 + 3 * stride < nv ? __ldg(cand + e0 + 3 * stride) : 0u;
+        {
+          const float v = adc_eval_rows<LP, CROW>(wB, lut_b, cbd_b, a.c1, lp);
+          if (e0 + stride < nv) out[e0 + stride] = v;
+        }
+        e0 += 2 * stride;
+        pos1 = pos3;
+      }
+    } else {
+      mbar_wait(&bars[buf], buf ? phase1 : phase0);
+    }
+    if (buf)
+      phase1 ^= 1;
+    else
+      phase0 ^= 1;
+    __syncthreads();  // everyone is done with s_lut[buf] before it is refilled
+    buf ^= 1;
+  }
+}
+
+// ranking only: candidates already in global memory (the split pipeline and the multi-GPU
+// paths).  DIRECT: idx[q][slot] is the vector id itself (assembled from shards); otherwise
+// idx = cand_pos (bin-order positions) and ids[pos] is the id, read when a result is emitted.
 struct Rank2Args {
   const float* val;     // [QN][max_vec]
-  const uint32_t* idx;  // [QN][max_vec]
+  const uint32_t* idx;  // [QN][max_vec]: ids (DIRECT) or bin-order positions
+  const uint32_t* ids;  // !DIRECT: id of each bin-order position
   uint32_t QN, max_vec, k;
   float* out_dist;
   uint32_t* out_idx;
   unsigned long long* exact_counter;
+  unsigned long long* tie_counter;
   const uint32_t* n_vec;  // optional [QN]: number of real candidates; slots beyond are padding
                           // and are NOT read (peer-store mode leaves them unwritten)
   uint32_t fast_rank;     // 1: composite-key sort first; 0: the network only
@@ -913,6 +1201,7 @@ struct Rank2Args {
 inline size_t rank2_smem_bytes(uint32_t max_vec) { return (size_t)max_vec * 8 + 512 + 64; }
 constexpr int kRank2Threads = 256;  // one query per CTA, 4 CTAs per SM
 
+template <bool DIRECT>
 __global__ void __launch_bounds__(kRank2Threads, 4) rank2_kernel(Rank2Args a) {
   extern __shared__ float smem_f[];
   float* s_val = smem_f;
@@ -969,15 +1258,19 @@ __global__ void __launch_bounds__(kRank2Threads, 4) rank2_kernel(Rank2Args a) {
     const uint32_t nv = a.n_vec ? limit : *s_nv;
     float* od = a.out_dist + (size_t)qi * a.k;
     uint32_t* oi = a.out_idx + (size_t)qi * a.k;
-    auto id_of = [&](uint32_t slot) { return __ldg(idx_row + slot); };
+    const uint32_t* cand = DIRECT ? nullptr : idx_row;
+    const uint32_t* ids = DIRECT ? idx_row : a.ids;
+    auto id_of = [&](uint32_t slot) { return DIRECT ? __ldg(idx_row + slot) : __ldg(a.ids + __ldg(idx_row + slot)); };
     const uint32_t n2 = nv ? pow2ceil(nv) : 0u;
     bool done = false;
     if (a.fast_rank && n2 >= kFastMinN2 && *s_bad == 0u) {
       FastRankState st{*s_min, *s_max};
-      uint32_t f = fast_rank_emit<true>(G, 1, s_val, s_cmp, s_fix, s_flag, nv, n2, a.k, st, od, oi, nullptr,
-                                        idx_row, nullptr);
-      if (f == 1u && a.k >= nv && tie_resolve<true>(G, s_val, s_cmp, s_flag, nv, a.max_vec, od, oi, nullptr, idx_row))
+      uint32_t f = fast_rank_emit<DIRECT>(G, 1, s_val, s_cmp, s_fix, s_flag, nv, n2, a.k, st, od, oi, cand, ids,
+                                          nullptr);
+      if (f == 1u && a.k >= nv && tie_resolve<DIRECT>(G, s_val, s_cmp, s_flag, nv, a.max_vec, od, oi, cand, ids)) {
         f = 0u;
+        if (threadIdx.x == 0 && a.tie_counter) atomicAdd(a.tie_counter, 1ull);
+      }
       done = (f == 0u);
     }
     if (!done)

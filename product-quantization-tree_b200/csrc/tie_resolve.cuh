@@ -8,8 +8,9 @@
 // every comparator outcome that matters is decided by three classes: Lower (< v), Equal,
 // Higher (> v, pads included) -- a monotone image of the input, and the network commutes with
 // monotone maps.  The classes of all max_vec input positions are held as bit planes (one
-// 32-bit word per 32 positions, one thread per word) and the whole network is run on the
-// planes with bitwise operations: 32 comparators per instruction instead of one.  A third
+// 32-bit word per 32 positions, four words per lane of ONE warp) and the whole network is run
+// on the planes with bitwise operations in registers and shuffles: 32 comparators per
+// instruction instead of one, no shared memory, no barrier.  A third
 // plane carries which of the (two) different vectors an Equal position holds; it is moved by
 // the same swaps.  When the network is done the Equal positions are the group's output slots
 // and the label plane says which vector goes where.
@@ -76,10 +77,8 @@ __device__ __forceinline__ uint32_t tie_resolve(const Grp& g, const float* s_val
   uint32_t* s_gm = s_gr + 8;         // length
   uint32_t* s_ga = s_gm + 8;         // first vector's id
   uint32_t* s_gb = s_ga + 8;         // the other vector's id
-  uint32_t* s_planes = s_scr + 64;   // [teams][2][3][nW]: class planes / exchange buffer
-  const uint32_t teams = g.n >> 7;
   const uint32_t nW = max_vec >> 5;  // words per plane
-  if (nW == 0u || 64u + 6u * teams * nW > max_vec) return 0u;  // scratch too small (uniform)
+  if (nW == 0u || nW > 128u || max_vec < 64u) return 0u;  // planes do not fit a warp / scratch (uniform)
   if (t == 0) *s_cnt = 0;
   g.sync();
   // ---- A. find the groups: slot e starts a tie when it repeats the distance of e-1 with a
@@ -147,102 +146,128 @@ __device__ __forceinline__ uint32_t tie_resolve(const Grp& g, const float* s_val
   if (*s_flag & 8u) return 0u;
   if (cnt == 0u) return 1u;  // only duplicates of one vector shared a distance: nothing to do
 
-  // ---- B. one team of 128 threads per group; thread x of a team owns word x of the planes
-  const uint32_t team = t >> 7, x = t & 127u, lane = t & 31u, wteam = x >> 5;
-  uint32_t* pl = s_planes + team * (6u * nW);
-  uint32_t* xb = pl + 3u * nW;
-  for (uint32_t g0 = 0; g0 < cnt; g0 += teams) {
-    const uint32_t gi = g0 + team;
-    const bool act = gi < cnt;
-    const uint32_t r = act ? s_gr[gi] : 0u, m = act ? s_gm[gi] : 0u;
-    const uint32_t idA = act ? s_ga[gi] : 0u, idB = act ? s_gb[gi] : 0u;
-    if (act) {
-      const float v = out_dist[r];
-      for (uint32_t w = wteam; w < nW; w += 4u) {
-        const uint32_t a = (w << 5) + lane;
-        const float val = a < nv ? s_val[a] : kPadDist;
-        const bool isL = val < v, isH = val > v;
-        bool isB = false;
-        if (!isL && !isH) isB = ident_id<DIRECT>(ids, slot_ident<DIRECT>(cand, ids, a)) != idA;
-        const uint32_t bl = __ballot_sync(0xffffffffu, isL);
-        const uint32_t bh = __ballot_sync(0xffffffffu, isH);
-        const uint32_t bb = __ballot_sync(0xffffffffu, isB);
-        if (lane == 0) {
-          pl[w] = bl;
-          pl[nW + w] = bh;
-          pl[2u * nW + w] = bb;
+  // ---- B. one WARP per group: lane l owns words 4l .. 4l+3 of the three planes (max_vec <=
+  // 4096 positions = 128 words), so the whole network runs in registers and shuffles -- no
+  // shared memory, no barrier, and the warps without a group stay out of the issue slots.
+  const uint32_t lane = t & 31u, warp = t >> 5, nwarps = g.n >> 5;
+  for (uint32_t g0 = 0; g0 < cnt; g0 += nwarps) {
+    const uint32_t gi = g0 + warp;
+    if (gi >= cnt) break;  // warp-uniform
+    const uint32_t r = s_gr[gi], m = s_gm[gi];
+    const uint32_t idA = s_ga[gi], idB = s_gb[gi];
+    const float v = out_dist[r];
+    uint32_t L[4] = {0u, 0u, 0u, 0u}, H[4] = {~0u, ~0u, ~0u, ~0u}, B[4] = {0u, 0u, 0u, 0u};
+    // classes of the input positions (candidate order, pads = Higher); word w goes to lane w / 4
+    for (uint32_t w0 = 0; w0 < nW; w0 += 4u) {
+#pragma unroll
+      for (uint32_t i = 0; i < 4u; i++) {
+        const uint32_t w = w0 + i;
+        if (w < nW) {  // warp-uniform
+          const uint32_t a = (w << 5) + lane;
+          const float val = a < nv ? s_val[a] : kPadDist;
+          const bool isL = val < v, isH = val > v;
+          bool isB = false;
+          if (!isL && !isH) isB = ident_id<DIRECT>(ids, slot_ident<DIRECT>(cand, ids, a)) != idA;
+          const uint32_t bl = __ballot_sync(0xffffffffu, isL);
+          const uint32_t bh = __ballot_sync(0xffffffffu, isH);
+          const uint32_t bb = __ballot_sync(0xffffffffu, isB);
+          if (lane == (w0 >> 2)) {
+            L[i] = bl;
+            H[i] = bh;
+            B[i] = bb;
+          }
         }
       }
     }
-    g.sync();
-    uint32_t L = 0, H = 0, B = 0;
-    if (act && x < nW) {
-      L = pl[x];
-      H = pl[nW + x];
-      B = pl[2u * nW + x];
-    }
     // the network of pqt/bitonicSort.cuh:16-44 / :47-78: for k = 2..n, for j = k/2..1:
-    // pairs (i, i^j), ascending iff (i & k) == 0
+    // pairs (i, i^j), ascending iff (i & k) == 0.  x = 4*lane + i is the word index.
     for (uint32_t kk = 2u; kk <= max_vec; kk <<= 1) {
       for (uint32_t j = kk >> 1; j > 0u; j >>= 1) {
         if (j < 32u) {
           const uint32_t M = j == 1u ? 0x55555555u : j == 2u ? 0x33333333u : j == 4u ? 0x0F0F0F0Fu
                              : j == 8u ? 0x00FF00FFu : 0x0000FFFFu;
-          uint32_t D;
           if (kk < 32u) {
             const uint32_t Mk = kk == 2u ? 0x33333333u : kk == 4u ? 0x0F0F0F0Fu
                                 : kk == 8u ? 0x00FF00FFu : 0x0000FFFFu;
-            D = ~Mk & M;  // positions with (pos & kk) != 0
+            const uint32_t D = ~Mk & M;  // positions with (pos & kk) != 0
+#pragma unroll
+            for (uint32_t i = 0; i < 4u; i++) tie_substage_inword(L[i], H[i], B[i], j, M, D);
           } else {
-            D = (x & (kk >> 5)) ? M : 0u;
+            const uint32_t kw = kk >> 5;
+#pragma unroll
+            for (uint32_t i = 0; i < 4u; i++)
+              tie_substage_inword(L[i], H[i], B[i], j, M, (((lane << 2) + i) & kw) ? M : 0u);
           }
-          tie_substage_inword(L, H, B, j, M, D);
         } else {
-          const uint32_t wd = j >> 5;
-          uint32_t oL, oH, oB;
-          if (wd < 32u) {
-            oL = __shfl_xor_sync(0xffffffffu, L, wd);
-            oH = __shfl_xor_sync(0xffffffffu, H, wd);
-            oB = __shfl_xor_sync(0xffffffffu, B, wd);
+          const uint32_t wd = j >> 5, kw = kk >> 5;
+          if (wd < 4u) {
+            // partner word in the same lane: i ^ wd
+#pragma unroll
+            for (uint32_t i = 0; i < 4u; i++) {
+              if ((i & wd) == 0u) {
+                const uint32_t q = i ^ wd;  // wd is 1 or 2: compile-time after unrolling on both
+                const bool desc = (((lane << 2) + i) & kw) != 0u;
+                uint32_t L0 = L[i], H0 = H[i], B0 = B[i];
+                uint32_t L1 = wd == 1u ? L[i ^ 1u] : L[i ^ 2u];
+                uint32_t H1 = wd == 1u ? H[i ^ 1u] : H[i ^ 2u];
+                uint32_t B1 = wd == 1u ? B[i ^ 1u] : B[i ^ 2u];
+                const uint32_t gt = (H0 & ~H1) | (~L0 & L1);
+                const uint32_t lt = (H1 & ~H0) | (~L1 & L0);
+                const uint32_t sw = desc ? lt : gt;
+                const uint32_t dL = (L0 ^ L1) & sw, dH = (H0 ^ H1) & sw, dB = (B0 ^ B1) & sw;
+                L[i] = L0 ^ dL;
+                H[i] = H0 ^ dH;
+                B[i] = B0 ^ dB;
+                if (wd == 1u) {
+                  L[i ^ 1u] = L1 ^ dL;
+                  H[i ^ 1u] = H1 ^ dH;
+                  B[i ^ 1u] = B1 ^ dB;
+                } else {
+                  L[i ^ 2u] = L1 ^ dL;
+                  H[i ^ 2u] = H1 ^ dH;
+                  B[i ^ 2u] = B1 ^ dB;
+                }
+                (void)q;
+              }
+            }
           } else {
-            if (x < nW) {
-              xb[x] = L;
-              xb[nW + x] = H;
-              xb[2u * nW + x] = B;
+            const uint32_t ld = wd >> 2;  // lane distance
+            const bool lo = (lane & ld) == 0u;
+#pragma unroll
+            for (uint32_t i = 0; i < 4u; i++) {
+              const uint32_t oL = __shfl_xor_sync(0xffffffffu, L[i], ld);
+              const uint32_t oH = __shfl_xor_sync(0xffffffffu, H[i], ld);
+              const uint32_t oB = __shfl_xor_sync(0xffffffffu, B[i], ld);
+              tie_substage_xword(L[i], H[i], B[i], oL, oH, oB, lo, (((lane << 2) + i) & kw) != 0u);
             }
-            g.sync();
-            oL = oH = oB = 0u;
-            if (x < nW) {
-              oL = xb[x ^ wd];
-              oH = xb[nW + (x ^ wd)];
-              oB = xb[2u * nW + (x ^ wd)];
-            }
-            g.sync();
           }
-          tie_substage_xword(L, H, B, oL, oH, oB, (x & wd) == 0u, (x & (kk >> 5)) != 0u);
         }
       }
     }
     // ---- the Equal positions are now the group's output slots r .. r+m-1
-    if (act && x < nW) {
-      const uint32_t base = x << 5;
-      uint32_t want = 0;
-      if (base < r + m && base + 32u > r) {
-        const uint32_t lo = r > base ? r - base : 0u;
-        const uint32_t hi = min(32u, r + m - base);
-        want = (hi >= 32u ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-      }
-      const uint32_t eq = ~(L | H);
-      if (eq != want) atomicOr(s_flag, 8u);  // cannot happen for a sorted result; be safe
-      uint32_t todo = want;
-      while (todo) {
-        const uint32_t b = __ffs(todo) - 1u;
-        todo &= todo - 1u;
-        out_idx[base + b] = ((B >> b) & 1u) ? idB : idA;
+#pragma unroll
+    for (uint32_t i = 0; i < 4u; i++) {
+      const uint32_t x = (lane << 2) + i;
+      if (x < nW) {
+        const uint32_t base = x << 5;
+        uint32_t want = 0;
+        if (base < r + m && base + 32u > r) {
+          const uint32_t lo = r > base ? r - base : 0u;
+          const uint32_t hi = min(32u, r + m - base);
+          want = (hi >= 32u ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+        }
+        const uint32_t eq = ~(L[i] | H[i]);
+        if (eq != want) atomicOr(s_flag, 8u);  // cannot happen for a sorted result; be safe
+        uint32_t todo = want;
+        while (todo) {
+          const uint32_t b = __ffs(todo) - 1u;
+          todo &= todo - 1u;
+          out_idx[base + b] = ((B[i] >> b) & 1u) ? idB : idA;
+        }
       }
     }
-    g.sync();
   }
+  g.sync();
   return (*s_flag & 8u) ? 0u : 1u;
 }
 

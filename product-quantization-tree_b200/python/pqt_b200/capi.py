@@ -49,7 +49,7 @@ class Stats(C.Structure):
                 ("ms_bins", C.c_double), ("ms_scan", C.c_double), ("ms_sort", C.c_double),
                 ("ms_total", C.c_double), ("scan_launches", C.c_uint64),
                 ("exact_rank_queries", C.c_uint64), ("tie_resolved_queries", C.c_uint64),
-                ("reserved", C.c_uint64 * 5)]
+                ("stream_scan_launches", C.c_uint64), ("reserved", C.c_uint64 * 4)]
 
 
 class PqtError(RuntimeError):
