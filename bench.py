@@ -54,12 +54,11 @@ def parse():
                     help="cluster centres of the synthetic data (0 = max(4096, n // 256))")
     ap.add_argument("--train", type=int, default=300000)
     ap.add_argument("--chunk", type=int, default=10000000, help="vectors per build chunk (test/test1B.cpp:623)")
-    ap.add_argument("--mode", default="pull", choices=["pull", "shard", "replica"],
-                    help="N>1: 'pull' = index sharded by bin range, every rank answers its slice of "
-                         "the batch and reads the other shards' line codes over NVLink (no "
-                         "collective on the data path); 'shard' = same shards, candidate lists "
-                         "all-gathered and the scan results pushed to the query's owner; 'replica' "
-                         "= a full index per GPU")
+    ap.add_argument("--mode", default="shard", choices=["shard", "replica"],
+                    help="N>1: 'shard' = index sharded by bin range (BASELINE configs[3]): every rank "
+                         "owns a slice of the batch and a slice of the line codes; candidates are "
+                         "dispatched to the shard that holds them and the scan results stored into "
+                         "the owner's arrays over NVLink; 'replica' = a full index per GPU")
     ap.add_argument("--variants", default="knn,big", help="comma list of knn, big")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -460,12 +459,11 @@ def run_b200(a, rank, world, local_rank):
     gt_s = time.perf_counter() - t_setup0
 
     sharded = world > 1 and a.mode == "shard"
-    pull = world > 1 and a.mode == "pull"
     replica = world > 1 and a.mode == "replica"
     t = pqt_b200.PerturbationProTree(a.dim, a.p, a.p, local_rank)
     t.set_params(hash_size=a.hashsize, k1_build=min(16, a.c1))
     t.setTree(inp["cb1"], inp["cb2"])
-    if sharded or pull:
+    if sharded:
         assert a.qn % world == 0, "qn must be divisible by the number of ranks"
         t.setShard(rank, world)
     build = build_index_chunked(a, t, inp, 0 if replica else rank, 1 if replica else world, device)
@@ -474,22 +472,6 @@ def run_b200(a, rank, world, local_rank):
     QN, k = a.qn, a.k
     Qd = inp["Q8"].to(torch.float32).contiguous()
     Qh = Qd.cpu().pin_memory()
-    if pull:
-        # every rank maps the code slices of the others (CUDA IPC); queries then run through the
-        # ordinary public call on each rank's slice of the batch.  If the mapping fails on any
-        # rank (peer access unavailable), all ranks fall back to the push pipeline.
-        ok = torch.ones(1, dtype=torch.int32, device=device)
-        try:
-            handles = [None] * world
-            dist.all_gather_object(handles, t.shardCodesHandle())
-            t.shardCodesOpen(handles)
-        except Exception as e:  # noqa: BLE001
-            print("rank %d: pull-mode setup failed (%r); falling back to --mode shard" % (rank, e),
-                  file=sys.stderr, flush=True)
-            ok.zero_()
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 0:
-            pull, sharded = False, True
     mv = t.candidateWidth(k)
     q_lo, q_hi = 0, QN
     if world > 1:
@@ -507,18 +489,18 @@ def run_b200(a, rank, world, local_rank):
         handles = [None] * world
         dist.all_gather_object(handles, t.shardExchangeHandle())
         t.shardExchangeOpen(handles)
-        cand = torch.zeros((QN, mv), dtype=torch.int32, device=device)
-        nvec = torch.zeros((QN,), dtype=torch.int32, device=device)
         token = torch.zeros(1, dtype=torch.int32, device=device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
 
     def shard_step(Qdev, oi, od):
-        t.shardCandidates(Qdev, QN, k, q_lo, q_hi, cand, nvec)
-        dist.all_gather_into_tensor(cand, cand[q_lo:q_hi])
-        dist.all_gather_into_tensor(nvec, nvec[q_lo:q_hi])
-        t.shardScanP2P(QN, k, cand, nvec)
-        dist.all_reduce(token)
-        t.shardRank(nvec[q_lo:q_hi], nq_out, k, oi, od)
+        # 1. Steps A-E1 for the own queries, the LUT of every query, and the dispatch of the own
+        #    candidates to the shards that hold them (peer stores over NVLink)
+        t.shardDispatch(Qdev, QN, k, q_lo, q_hi)
+        dist.all_reduce(token)  # 2. stream-ordered cross-rank barrier: every inbox is complete
+        # 3. scan the own inbox; distances go straight into the owners' arrays (peer stores)
+        t.shardScanP2P(QN, k)
+        dist.all_reduce(token)  # 4. barrier: every distance has arrived
+        t.shardRank(nq_out, k, oi, od)  # 5. rank the own queries
 
     def barrier():
         torch.cuda.synchronize()
@@ -598,7 +580,7 @@ def run_b200(a, rank, world, local_rank):
         results[v] = measure(v == "big")
     # second end-to-end operating point: same 4096-candidate scan, k = 100 results returned
     e2e_k100 = None
-    if "knn" in results and not sharded and k > 100 and mv <= 4096:
+    if "knn" in results and world == 1 and k > 100 and mv <= 4096:
         t.set_params(max_vec=mv)
         pi = torch.empty((nq_out, 100), dtype=torch.int32).pin_memory()
         pd = torch.empty((nq_out, 100), dtype=torch.float32).pin_memory()
@@ -623,9 +605,9 @@ def run_b200(a, rank, world, local_rank):
     def summarise(r):
         st = r["st"]
         scan_ms = st.ms_scan / max(1, st.scan_launches)
+        # sharded: rank 0 counts the candidates of its own queries (1/world of the batch), which
+        # is also what its shard scans on average (1/world of every query's candidates)
         cand_per_launch = st.candidates / max(1, st.scan_launches)
-        if sharded:
-            cand_per_launch /= world
         # split pipeline: the scan kernel reads the code rows only (ids are implicit in the
         # bin-ordered layout and read by the ranking kernel); fused: codes + the 4-byte id
         split = st.stream_scan_launches > 0
@@ -639,7 +621,7 @@ def run_b200(a, rank, world, local_rank):
                     "d2h_bytes_per_step": int(QN * k * 8), "ms_per_step": r["e2e_ms"] / a.steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None,
-                         "kernel": "adc_scan_p2p_kernel" if sharded else
+                         "kernel": "adc_stream_kernel<INBOX> (ADC scan of the own shard, results stored to the owners over NVLink)" if sharded else
                          ("adc_stream_kernel (ADC scan; ranking = rank2_kernel, stage 'sort')" if split
                           else "rerank_kernel (ADC scan + ranking fused)"),
                          "peak_source": peak_src, "ms_per_launch": scan_ms,
@@ -698,8 +680,8 @@ def run_b200(a, rank, world, local_rank):
         except Exception as e:  # noqa: BLE001
             cpuv = {"unavailable": repr(e)}
     head = summ.get("knn") or next(iter(summ.values()))
-    par = ("bin-range shards x%d, scan fused with peer-memory exchange (NVLink), NCCL all-gather of candidate lists" % world) if sharded \
-        else ("bin-range shards x%d, batch split over the ranks, line codes of the other shards read over NVLink inside the fused scan kernel, no collective" % world) if pull \
+    par = ("bin-range shards x%d: candidates dispatched to the shard that holds them, scan fused with the "
+           "exchange of its results over peer memory (NVLink), two stream-ordered NCCL barriers per batch" % world) if sharded \
         else ("replicas x%d, batch split over the ranks" % world) if replica else "single GPU"
     out = {
         "metric": "queries/sec", "value": head["value"], "unit": "queries/s",

@@ -205,66 +205,52 @@ int pqt_get_lines(const pqt_index *h, uint32_t *lines);
 int pqt_get_codes_binorder(const pqt_index *h, uint64_t pos0, uint64_t n, uint32_t *codes);
 int pqt_get_db_size(const pqt_index *h, uint32_t *N, uint32_t *line_parts);
 
-/* ---- multi-GPU: bin-range shards ---------------------------------------------- */
-
-/* Keep only the line codes whose position in the bin-ordered list lies in this
- * rank's slice [rank*N/world, (rank+1)*N/world) -- contiguous bin ranges with equal
- * vector counts.  Either before pqt_set_db (the slice is all that is uploaded) or
- * after the index is complete (the resident codes are trimmed in place). */
-int pqt_set_shard(pqt_index *h, uint32_t rank, uint32_t world);
-/* Per-shard half of queryKNN: Steps A-E2 over this rank's candidates only.
- * val/idx: DEVICE [QN][max_vec]; slots owned by other ranks hold +inf / INT32_MIN
- * (0x80000000) so that an element-wise float MIN / signed-int32 MAX across ranks
- * (one reduce-scatter or all-reduce each) assembles exactly the single-GPU
- * candidate arrays (vector ids must stay below 2^31 in sharded mode). */
-int pqt_query_scan_shard(pqt_index *h, const float *Q, int q_on_device, uint32_t QN, uint32_t k,
-                         float *val, uint32_t *idx);
-/* Ranking half: bitonic network over assembled val/idx (DEVICE [QN][max_vec]) and
- * emit the first k per query, exactly like the tail of rerankKernelFast :5331-5346 */
-int pqt_rank_candidates(pqt_index *h, float *val, uint32_t *idx, uint32_t QN, uint32_t max_vec,
-                        uint32_t k, uint32_t *out_idx, float *out_dist, int out_on_device);
-/* ---- multi-GPU, fused scan + exchange over peer memory ----------------------------------
- * Rank r owns queries [r*q_per_rank, (r+1)*q_per_rank) (Steps A, C, D, E1 and the ranking)
- * and a slice of the bin-ordered codes (pqt_set_shard).  Per batch:
- *   1. pqt_shard_candidates   Steps A-E1 for the own queries -> rows of cand_pos / n_vec;
- *                             Step B (the LUT) for ALL queries (cheaper than shipping it)
- *   2. all-gather of cand_pos / n_vec (NCCL, caller)
- *   3. pqt_shard_scan_p2p     ADC scan of the own shard's candidates of ALL queries; every
- *                             result is stored directly into the candidate arrays of the
- *                             rank that owns the query (peer memory over NVLink)
- *   4. a cross-rank barrier on the stream (caller: any tiny NCCL collective)
- *   5. pqt_shard_rank         bitonic ranking of the own queries
- * The exchange buffers (val/idx [q_per_rank][max_vec]) are owned by the handle; peers map
+/* ---- multi-GPU: bin-range shards ----------------------------------------------
+ * The reference is single-GPU; its 1-B mode keeps the line codes in pinned host memory
+ * (test/test1B.cpp:1121-1192).  Here the bin-ordered code array is cut into `world` contiguous
+ * slices of equal vector counts, one per GPU (one process per GPU); the bin directory, the ids
+ * and the codebooks are replicated.  Rank r owns the queries [r*q_per_rank, (r+1)*q_per_rank)
+ * of a batch (Steps A-E1 and the ranking) and its slice of the codes (the ADC scan of every
+ * query's candidates that live there).  Per batch, on every rank:
+ *   1. pqt_shard_dispatch   Steps A-E1 for the own queries; Step B (the LUT) for ALL queries
+ *                           (cheaper than shipping 4 KB per query); then every shard is sent
+ *                           the own queries' candidates that live in its slice: (position,
+ *                           entry) pairs stored into the shard's inbox -- peer memory over
+ *                           NVLink, 8 bytes per candidate, repeats of a code row sent once
+ *   2. a cross-rank barrier on the stream (caller: any tiny NCCL collective)
+ *   3. pqt_shard_scan_p2p   streaming ADC scan of the own inbox; every distance is stored
+ *                           straight into the distance array of the rank that owns the query
+ *                           (peer memory, 4 bytes per candidate): the scan and the all-to-all
+ *                           of its results are one kernel
+ *   4. a cross-rank barrier
+ *   5. pqt_shard_rank       ranking + first-k emit of the own queries
+ * The result is bit-identical to pqt_query_knn on the unsharded index (every candidate has
+ * exactly one evaluator and one slot).  The exchange buffers are owned by the handle; peers map
  * them through CUDA IPC handles (or raw pointers inside one process). */
+
+/* Keep only the line codes whose position in the bin-ordered list lies in this rank's slice
+ * [rank*N/world, (rank+1)*N/world).  Either before the DB is installed (pqt_set_db /
+ * pqt_set_db_from_bins: the slice is all that is uploaded / encoded) or after the index is
+ * complete (the resident codes are trimmed in place). */
+int pqt_set_shard(pqt_index *h, uint32_t rank, uint32_t world);
+/* own buffers: distances [q_per_rank][max_vec], inbox [q_per_rank*world][max_vec] x 8 bytes,
+ * inbox row lengths [q_per_rank*world]; call after pqt_set_shard */
 int pqt_shard_exchange_alloc(pqt_index *h, uint32_t q_per_rank, uint32_t max_vec);
-/* 128 bytes: cudaIpcMemHandle_t of the val buffer, then of the idx buffer */
-int pqt_shard_exchange_handle(pqt_index *h, void *handle128);
-/* handles: world * 128 bytes, entry r from rank r (the own entry is ignored) */
+/* 192 bytes: cudaIpcMemHandle_t of the distance buffer, of the inbox, of the row lengths */
+int pqt_shard_exchange_handle(pqt_index *h, void *handle192);
+/* handles: world * 192 bytes, entry r from rank r (the own entry is ignored) */
 int pqt_shard_exchange_open(pqt_index *h, uint32_t world, const void *handles);
 /* same-process alternative (tests): raw device pointers of every rank's buffers */
 int pqt_shard_exchange_set_peers(pqt_index *h, uint32_t world, void *const *val_ptrs,
-                                 void *const *idx_ptrs);
-int pqt_shard_exchange_ptrs(pqt_index *h, void **val_ptr, void **idx_ptr);
-/* Q: all QN queries (device or host); cand_pos [QN][max_vec] / n_vec [QN]: DEVICE arrays,
- * rows [q_lo, q_hi) are written */
-/* Pull mode: the index stays sharded by bin range (pqt_set_shard), every rank answers its own
- * slice of the query batch with pqt_query_knn and reads the line codes of the other shards from
- * their memory (CUDA IPC mapping, NVLink loads inside the fused scan kernel).  No collective on
- * the data path.  handle64 = 64-byte cudaIpcMemHandle_t of this rank's code slice; handles =
- * world * 64 bytes in rank order; _set_peers / _ptr: the same with plain device pointers
- * (several handles in one process). */
-int pqt_shard_codes_handle(pqt_index *h, void *handle64);
-int pqt_shard_codes_open(pqt_index *h, uint32_t world, const void *handles);
-int pqt_shard_codes_set_peers(pqt_index *h, uint32_t world, void *const *codes_ptrs);
-int pqt_shard_codes_ptr(pqt_index *h, void **codes_ptr);
-
-int pqt_shard_candidates(pqt_index *h, const float *Q, int q_on_device, uint32_t QN, uint32_t k,
-                         uint32_t q_lo, uint32_t q_hi, uint32_t *cand_pos, uint32_t *n_vec);
-int pqt_shard_scan_p2p(pqt_index *h, uint32_t QN, uint32_t k, const uint32_t *cand_pos,
-                       const uint32_t *n_vec);
-/* n_vec_own: DEVICE [q_per_rank] (the own rows of n_vec); idx/dist: [q_per_rank][k] */
-int pqt_shard_rank(pqt_index *h, const uint32_t *n_vec_own, uint32_t q_own, uint32_t k,
-                   uint32_t *idx, float *dist, int out_on_device);
+                                 void *const *inbox_ptrs, void *const *cnt_ptrs);
+int pqt_shard_exchange_ptrs(pqt_index *h, void **val_ptr, void **inbox_ptr, void **cnt_ptr);
+/* Q: all QN queries of the batch (device or host); the own queries are [q_lo, q_hi) */
+int pqt_shard_dispatch(pqt_index *h, const float *Q, int q_on_device, uint32_t QN, uint32_t k,
+                       uint32_t q_lo, uint32_t q_hi);
+int pqt_shard_scan_p2p(pqt_index *h, uint32_t QN, uint32_t k);
+/* idx/dist: [q_own][k] results of the own queries, device or host */
+int pqt_shard_rank(pqt_index *h, uint32_t q_own, uint32_t k, uint32_t *idx, float *dist,
+                   int out_on_device);
 
 /* pow2ceil(k) or params.max_vec: row length of the candidate arrays */
 int pqt_candidate_width(const pqt_index *h, uint32_t k, uint32_t *max_vec);

@@ -77,6 +77,8 @@ struct pqt_index {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // device->host result copies, overlapped with the next slab
+  cudaStream_t aux_stream = nullptr;   // multi-GPU: the LUTs of the other ranks' queries, beside Steps A-E1
+  cudaEvent_t aux_ev[2] = {nullptr, nullptr};
   std::vector<cudaEvent_t> slab_ev;
   mutable std::string err;
   pqt_params prm{};
@@ -121,21 +123,23 @@ struct pqt_index {
 
   // per-batch scratch
   DevBuf s_q, s_lut, s_idx16, s_cand, s_nvec, s_val, s_idx, s_outd, s_outi;
+  DevBuf s_rootpos, s_ridx, s_nroot;  // candidates without repeats (bins3_kernel -> scan / rank kernels)
+  bool have_roots = false;            // the last bin walk filled them
   // debug
   bool debug = false;
   uint32_t dbg_QN = 0, dbg_k = 0, dbg_maxvec = 0;
   DevBuf g_assign, g_lut, g_aval, g_aidx, g_bins, g_nbins, g_sel;
   // multi-GPU exchange (fused scan + peer stores)
-  DevBuf x_val, x_idx;  // own [q_per_rank][max_vec] candidate arrays, written by peers
+  DevBuf x_val;    // own [q_per_rank][max_vec] distances, written by the shards (peers)
+  DevBuf x_inbox;  // [q_per_rank * world][max_vec] (local position, entry number): this shard's
+                   // candidates of every query of the batch, written by the queries' owners
+  DevBuf x_cnt;    // [q_per_rank * world] length of every inbox row
   uint32_t x_q_per_rank = 0, x_max_vec = 0, x_world = 0;
-  uint32_t x_lut_QN = 0;  // queries whose LUT the last pqt_shard_candidates call left in s_lut
+  uint32_t x_lut_QN = 0;  // queries whose LUT the last pqt_shard_dispatch call left in s_lut
   float* x_peer_val[8] = {nullptr};
-  uint32_t* x_peer_idx[8] = {nullptr};
+  uint2* x_peer_inbox[8] = {nullptr};
+  uint32_t* x_peer_cnt[8] = {nullptr};
   bool x_ipc_opened[8] = {false};
-  // pull mode: the code slices of all shards (own slice + peers' slices mapped through CUDA IPC)
-  const uint32_t* c_peer[8] = {nullptr};
-  bool c_ipc_opened[8] = {false};
-  uint32_t c_world = 0;
   DevBuf d_sched;  // one uint32: work counter of the fused scan+rank kernel
   DevBuf d_exact;  // two uint64: queries ranked by the exact-network fallback, queries with re-ordered ties
 
@@ -419,7 +423,8 @@ struct QueryPlan {
 // (early stop every 4096 codes) does less work.  Same output either way.
 int launch_bins_p4(pqt_index* h, const pqt_params& P, uint32_t max_vec, uint32_t nq,
                    const uint32_t* idx16, uint32_t* cand_pos, uint32_t* n_vec, uint32_t* dbg_bins,
-                   uint32_t* dbg_nbins) {
+                   uint32_t* dbg_nbins, bool want_roots = false) {
+  h->have_roots = false;
   const uint32_t n_probes = P.max_trials * P.bin_threads;
   const double density = (double)h->n_nonempty / (double)std::max<uint32_t>(1u, h->db_hash_size);
   // the walk ends after max_bins kept bins or max_vec listed candidates, whichever comes first
@@ -468,7 +473,18 @@ int launch_bins_p4(pqt_index* h, const pqt_params& P, uint32_t max_vec, uint32_t
     // the candidate-count stop is checked after every 1024 codes; otherwise 4096-code batches
     const bool fine = vec_per_probe * kBins3FineBatch * 8.0 >= (double)max_vec && !dbg_bins;
     if (fine) a.seq_sorted = h->d_seqfine.as<uint32_t>();
-    const size_t smem = bins3_smem_bytes(P.max_bins, fine ? kBins3FineProbes : kProbesPerThread);
+    if (want_roots && max_vec <= 65536) {
+      CU_TRY(h, h->s_rootpos.ensure((size_t)nq * max_vec * 4));
+      CU_TRY(h, h->s_ridx.ensure((size_t)nq * max_vec * 2));
+      CU_TRY(h, h->s_nroot.ensure((size_t)nq * 4));
+      a.root_pos = h->s_rootpos.as<uint32_t>();
+      a.ridx = h->s_ridx.as<uint16_t>();
+      a.n_root = h->s_nroot.as<uint32_t>();
+      h->have_roots = true;
+    }
+    const size_t smem = bins3_smem_bytes(P.max_bins, fine ? kBins3FineProbes : kProbesPerThread, h->have_roots);
+    // static query assignment: never launch more CTAs than are resident at once
+    grid = std::min<uint32_t>(grid, (uint32_t)h->num_sms * std::max<uint32_t>(1u, std::min<uint32_t>(6u, (uint32_t)((227 * 1024) / (smem + 1024)))));
 #define LAUNCH_BINS3(NP, PPTV)                                                                       \
   do {                                                                                               \
     if (smem > 48 * 1024)                                                                            \
@@ -576,6 +592,20 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
     h->stats.kernel_launches++;
   }
   if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[1], h->stream));
+  // Split pipeline (lineparts 16 / 32): a pure streaming scan kernel writes the distances, the
+  // ranking kernel (4 CTAs per SM) sorts and emits.  The scan is the HBM-bound part and runs
+  // without any ranking state in its way; PQT_SCAN_MODE=fused selects the fused kernel instead
+  // (A/B runs).
+  const char* env_mode = getenv("PQT_SCAN_MODE");
+  const bool want_split = env_mode ? (strcmp(env_mode, "split") == 0) : true;
+  const bool will_split = fused_out_dist && want_split && (h->LP == 16 || h->LP == 32) && max_vec >= 256 &&
+                          max_vec <= 4096 &&
+                          stream_scan_smem_bytes(h->c1, h->LP, h->LP == 32) <= (size_t)227 * 1024;
+  // Listing the first occurrences in the bin walk costs that kernel about what the scan kernel
+  // saves on one GPU (profiles/r02c_ab_bins_dedupe_1b.log), so it is off here by default; the
+  // multi-GPU path, where it also cuts the NVLink traffic by a third, turns it on.
+  const bool want_roots = will_split && !h->debug && getenv("PQT_BINS_DEDUPE") && atoi(getenv("PQT_BINS_DEDUPE")) == 1;
+  h->have_roots = false;
   // ---- Steps D+E1
   if (big) {
     PQ_TRY(ensure_dist_seq_2d(h));
@@ -612,7 +642,7 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
   } else if (h->p <= 4) {
     PQ_TRY(launch_bins_p4(h, P, max_vec, QN, h->s_idx16.as<uint32_t>(), h->s_cand.as<uint32_t>(),
                           h->s_nvec.as<uint32_t>(), h->debug ? h->g_bins.as<uint32_t>() : nullptr,
-                          h->debug ? h->g_nbins.as<uint32_t>() : nullptr));
+                          h->debug ? h->g_nbins.as<uint32_t>() : nullptr, want_roots));
   } else {
     Bins2Args a{};
     a.idx16 = h->s_idx16.as<uint32_t>();
@@ -664,44 +694,27 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
                       rerank_smem_bytes(h->c1, h->LP, max_vec, 4, false) <= kSmemMax;
     const size_t smem_fused = four ? rerank_smem_bytes(h->c1, h->LP, max_vec, 4, false)
                                    : rerank_smem_bytes(h->c1, h->LP, max_vec, 2, true);
-    // Split pipeline (lineparts 16 / 32, unsharded): a pure streaming scan kernel writes the
-    // distances, the ranking kernel (4 CTAs per SM) sorts and emits.  The scan is the HBM-bound
-    // part and runs without any ranking state in its way; PQT_SCAN_MODE=fused selects the fused
-    // kernel instead (A/B runs).
-    const char* env_mode = getenv("PQT_SCAN_MODE");
-    const bool want_split = env_mode ? (strcmp(env_mode, "split") == 0) : true;
     h->split_ranked = false;
-    const bool pull_split = h->world > 1;
-    if (fused_out_dist && want_split && (h->LP == 16 || h->LP == 32) && max_vec >= 256 &&
-        max_vec <= 4096 && stream_scan_smem_bytes(h->c1, h->LP, h->LP == 32) <= kSmemMax) {
+    if (will_split) {
       CU_TRY(h, h->s_val.ensure((size_t)QN * max_vec * 4));
       StreamScanArgs sa{};
       sa.codes = h->d_codes.as<uint32_t>();
-      sa.cand_pos = h->s_cand.as<uint32_t>();
-      sa.n_vec = h->s_nvec.as<uint32_t>();
+      // repeated candidates are evaluated once: the bin walk left the first occurrences
+      sa.cand_pos = h->have_roots ? h->s_rootpos.as<uint32_t>() : h->s_cand.as<uint32_t>();
+      sa.n_vec = h->have_roots ? h->s_nroot.as<uint32_t>() : h->s_nvec.as<uint32_t>();
       sa.lut_dup = h->s_lut.as<float>();
       sa.cbd = h->LP == 32 ? h->d_cbd_dup.as<float>() : h->d_cbd.as<float>();
       sa.QN = QN; sa.c1 = h->c1; sa.max_vec = max_vec;
       sa.out_val = h->s_val.as<float>();
-      if (pull_split) {
-        if (h->c_world != h->world) return fail(h, PQT_ERR_STATE, "code slices of the other shards are not connected");
-        sa.n_shards = h->world;
-        for (uint32_t r = 0; r <= h->world; r++) sa.shard_lo[r] = (uint32_t)((uint64_t)h->N * r / h->world);
-        for (uint32_t r = 0; r < h->world; r++) sa.codes_adj[r] = h->c_peer[r] - (size_t)sa.shard_lo[r] * h->LP;
-      }
       const size_t ssmem = stream_scan_smem_bytes(h->c1, h->LP, h->LP == 32);
       const uint32_t sgrid = std::min<uint32_t>(QN, (uint32_t)h->num_sms);
-#define LAUNCH_STREAM(LPV, CREPV, PULLV)                                                            \
+#define LAUNCH_STREAM(LPV, CREPV)                                                                   \
   do {                                                                                              \
-    CU_TRY(h, cudaFuncSetAttribute(adc_stream_kernel<LPV, CREPV, 512, PULLV>,                       \
+    CU_TRY(h, cudaFuncSetAttribute(adc_stream_kernel<LPV, CREPV, 512, false>,                       \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));        \
-    adc_stream_kernel<LPV, CREPV, 512, PULLV><<<sgrid, 512, ssmem, h->stream>>>(sa);                 \
+    adc_stream_kernel<LPV, CREPV, 512, false><<<sgrid, 512, ssmem, h->stream>>>(sa);                 \
   } while (0)
-      if (h->LP == 32) {
-        if (pull_split) LAUNCH_STREAM(32, true, true); else LAUNCH_STREAM(32, true, false);
-      } else {
-        if (pull_split) LAUNCH_STREAM(16, false, true); else LAUNCH_STREAM(16, false, false);
-      }
+      if (h->LP == 32) LAUNCH_STREAM(32, true); else LAUNCH_STREAM(16, false);
 #undef LAUNCH_STREAM
       h->stats.stream_scan_launches++;
       CU_TRY(h, cudaGetLastError());
@@ -714,12 +727,13 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
       Rank2Args ra{};
       ra.val = h->s_val.as<float>();
       ra.idx = h->s_cand.as<uint32_t>();
-      ra.ids = h->d_dbidx.as<uint32_t>() + (pull_split ? 0u : h->pos_lo);  // pull: global positions
+      ra.ids = h->d_dbidx.as<uint32_t>() + h->pos_lo;
       ra.QN = QN; ra.max_vec = max_vec; ra.k = k;
       ra.out_dist = fused_out_dist; ra.out_idx = fused_out_idx;
       ra.exact_counter = h->d_exact.as<unsigned long long>();
       ra.tie_counter = h->d_exact.as<unsigned long long>() + 1;
       ra.n_vec = h->s_nvec.as<uint32_t>();
+      ra.ridx = h->have_roots ? h->s_ridx.as<uint16_t>() : nullptr;
       ra.fast_rank = (P.rank_mode == 0) ? 1u : 0u;
       const size_t rsmem = rank2_smem_bytes(max_vec);
       if (rsmem > 48 * 1024)
@@ -757,15 +771,6 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
         CU_TRY(h, h->g_phases.ensure((size_t)QN * 8 * 8));
         g.phase_dbg = h->g_phases.as<unsigned long long>();
       }
-      const bool pull = h->world > 1;
-      if (pull) {
-        if (h->c_world != h->world) return fail(h, PQT_ERR_STATE, "code slices of the other shards are not connected");
-        if (h->LP != 16 && h->LP != 32) return fail(h, PQT_ERR_INVALID, "pull mode is built for lineparts 16 and 32");
-        g.n_shards = h->world;
-        for (uint32_t r = 0; r <= h->world; r++) g.shard_lo[r] = (uint32_t)((uint64_t)h->N * r / h->world);
-        for (uint32_t r = 0; r < h->world; r++) g.codes_adj[r] = h->c_peer[r] - (size_t)g.shard_lo[r] * h->LP;
-        g.s.ids = h->d_dbidx.as<uint32_t>();  // global positions
-      }
       const uint32_t ng = four ? 4u : 2u;
       uint32_t grid = std::min<uint32_t>((QN + ng - 1) / ng, (uint32_t)h->num_sms);
 #define LAUNCH_RERANK(LPV, NGV, CREPV)                                                           \
@@ -775,29 +780,13 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
     rerank_kernel<LPV, NGV, CREPV><<<grid, kScanThreads, smem_fused, h->stream>>>(g);            \
   } while (0)
       // lineparts = 32: two groups of 256 threads with 128 registers each (pipelined scan)
-#define LAUNCH_RERANK_512(PULLV)                                                                 \
+#define LAUNCH_RERANK_512()                                                                      \
   do {                                                                                           \
-    CU_TRY(h, cudaFuncSetAttribute(rerank_kernel<32, 2, true, PULLV, 512>,                       \
+    CU_TRY(h, cudaFuncSetAttribute(rerank_kernel<32, 2, true, 512>,                              \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused)); \
-    rerank_kernel<32, 2, true, PULLV, 512><<<grid, 512, smem_fused, h->stream>>>(g);             \
+    rerank_kernel<32, 2, true, 512><<<grid, 512, smem_fused, h->stream>>>(g);                    \
   } while (0)
-      if (pull) {
-        if (four) {
-          CU_TRY(h, cudaFuncSetAttribute(rerank_kernel<16, 4, false, true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused));
-          rerank_kernel<16, 4, false, true><<<grid, kScanThreads, smem_fused, h->stream>>>(g);
-        } else if (h->LP == 16) {
-          CU_TRY(h, cudaFuncSetAttribute(rerank_kernel<16, 2, true, true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused));
-          rerank_kernel<16, 2, true, true><<<grid, kScanThreads, smem_fused, h->stream>>>(g);
-        } else if (env_tpb == 512) {
-          LAUNCH_RERANK_512(true);
-        } else {
-          CU_TRY(h, cudaFuncSetAttribute(rerank_kernel<32, 2, true, true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused));
-          rerank_kernel<32, 2, true, true><<<grid, kScanThreads, smem_fused, h->stream>>>(g);
-        }
-      } else if (four) {
+      if (four) {
         switch (h->LP) {
           case 1: LAUNCH_RERANK(1, 4, false); break;
           case 2: LAUNCH_RERANK(2, 4, false); break;
@@ -813,7 +802,7 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
           case 8: LAUNCH_RERANK(8, 2, true); break;
           case 16: LAUNCH_RERANK(16, 2, true); break;
           default:
-            if (env_tpb == 512) LAUNCH_RERANK_512(false); else LAUNCH_RERANK(32, 2, true);
+            if (env_tpb == 512) LAUNCH_RERANK_512(); else LAUNCH_RERANK(32, 2, true);
             break;
         }
       }
@@ -973,6 +962,8 @@ int pqt_create(uint32_t dim, uint32_t p, uint32_t p2, int device, pqt_index** ou
     return PQT_ERR_CUDA;
   }
   for (auto& e : h->ev) cudaEventCreate(&e);
+  cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
+  for (auto& e : h->aux_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   if (h->d_exact.ensure(16) != cudaSuccess || cudaMemset(h->d_exact.p, 0, 16) != cudaSuccess) {
     pqt_destroy(h);
     return PQT_ERR_CUDA;
@@ -988,19 +979,22 @@ int pqt_destroy(pqt_index* h) {
   for (DevBuf* b : {&h->d_cb1, &h->d_cb2, &h->d_cb1T, &h->d_cb2T, &h->d_distseq, &h->d_seqnib, &h->d_seqsorted, &h->d_seqfine, &h->d_seqmega, &h->d_seqplain, &h->d_seq2d, &h->s_topv, &h->s_topi, &h->g_bigbins, &h->g_bignbins, &h->d_bitmap, &h->d_rank_base, &h->d_cprefix,
                     &h->d_dbidx, &h->d_codes, &h->d_cbd, &h->d_cbd_dup, &h->s_q, &h->s_lut, &h->s_idx16,
                     &h->s_cand, &h->s_nvec, &h->s_val, &h->s_idx, &h->s_outd, &h->s_outi, &h->g_assign,
-                    &h->g_lut, &h->g_aval, &h->g_aidx, &h->g_bins, &h->g_nbins, &h->g_sel, &h->d_exact, &h->x_val, &h->x_idx})
+                    &h->g_lut, &h->g_aval, &h->g_aidx, &h->g_bins, &h->g_nbins, &h->g_sel, &h->d_exact, &h->x_val, &h->x_inbox, &h->x_cnt})
     b->release();
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   for (uint32_t r = 0; r < 8; r++) {
-    if (h->c_ipc_opened[r]) cudaIpcCloseMemHandle(const_cast<uint32_t*>(h->c_peer[r]));
     if (h->x_ipc_opened[r]) {
       cudaIpcCloseMemHandle(h->x_peer_val[r]);
-      cudaIpcCloseMemHandle(h->x_peer_idx[r]);
+      cudaIpcCloseMemHandle(h->x_peer_inbox[r]);
+      cudaIpcCloseMemHandle(h->x_peer_cnt[r]);
     }
   }
   for (auto& e : h->slab_ev) cudaEventDestroy(e);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+  for (auto& e : h->aux_ev)
+    if (e) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return PQT_OK;
@@ -1582,8 +1576,8 @@ static int query_common(pqt_index* h, const float* Q, int q_on_device, uint32_t 
     if (h->prm.big_k1 * h->c2 < kBigKMax) return fail(h, PQT_ERR_INVALID, "big_k1*c2 < 64: the 2-D merge reads 64 sorted entries per part (:3729)");
     if (pow2ceil(h->prm.big_k1 * h->c2) > 1024) return fail(h, PQT_ERR_INVALID, "big_k1*c2 > 1024");
   }
-  if (h->world != 1 && (h->c_world != h->world || big))
-    return fail(h, PQT_ERR_STATE, "sharded handle: connect the code slices (pqt_shard_codes_open) for pqt_query_knn, or use pqt_shard_candidates / pqt_shard_scan_p2p / pqt_shard_rank");
+  if (h->world != 1)
+    return fail(h, PQT_ERR_STATE, "sharded handle: a shard answers queries together with the others through pqt_shard_dispatch / pqt_shard_scan_p2p / pqt_shard_rank");
   const uint32_t max_vec = candidate_width(h, k);
   const float* dQ = Q;
   if (!q_on_device) {
@@ -1669,47 +1663,36 @@ int pqt_query_big_knn_rerank2(pqt_index* h, const float* Q, int q_on_device, uin
   return query_common(h, Q, q_on_device, QN, k, idx, dist, out_on_device, true);
 }
 
-int pqt_query_scan_shard(pqt_index* h, const float* Q, int q_on_device, uint32_t QN, uint32_t k,
-                         float* val, uint32_t* idx) {
-  if (!h || !Q || !val || !idx) return PQT_ERR_INVALID;
-  CU_TRY(h, cudaSetDevice(h->device));
-  PQ_TRY(check_query_state(h, QN, k));
-  const float* dQ = Q;
-  if (!q_on_device) {
-    CU_TRY(h, h->s_q.ensure((size_t)QN * h->dim * 4));
-    CU_TRY(h, cudaMemcpyAsync(h->s_q.p, Q, (size_t)QN * h->dim * 4, cudaMemcpyHostToDevice, h->stream));
-    dQ = h->s_q.as<float>();
-  }
-  PQ_TRY(run_scan_chain(h, dQ, QN, k, val, idx));
-  CU_TRY(h, cudaStreamSynchronize(h->stream));
-  if (h->profile) accumulate_profile(h, QN, false);
-  return PQT_OK;
-}
-
-// ---- multi-GPU: fused scan + exchange over peer memory ---------------------------------
+// ---- multi-GPU: bin-range shards, dispatch + scan fused with the exchange over peer memory ---
 int pqt_shard_exchange_alloc(pqt_index* h, uint32_t q_per_rank, uint32_t max_vec) {
   if (!h || !q_per_rank || !max_vec) return PQT_ERR_INVALID;
   CU_TRY(h, cudaSetDevice(h->device));
-  // cudaIpcGetMemHandle needs a plain cudaMalloc allocation
+  const size_t qn = (size_t)q_per_rank * h->world;
+  // cudaIpcGetMemHandle needs plain cudaMalloc allocations
   h->x_val.release();
-  h->x_idx.release();
+  h->x_inbox.release();
+  h->x_cnt.release();
   CU_TRY(h, h->x_val.ensure((size_t)q_per_rank * max_vec * 4));
-  CU_TRY(h, h->x_idx.ensure((size_t)q_per_rank * max_vec * 4));
+  CU_TRY(h, h->x_inbox.ensure(qn * max_vec * 8));
+  CU_TRY(h, h->x_cnt.ensure(qn * 4));
+  CU_TRY(h, cudaMemset(h->x_cnt.p, 0, qn * 4));
   h->x_q_per_rank = q_per_rank;
   h->x_max_vec = max_vec;
   return PQT_OK;
 }
 
-int pqt_shard_exchange_handle(pqt_index* h, void* handle128) {
-  if (!h || !handle128) return PQT_ERR_INVALID;
+int pqt_shard_exchange_handle(pqt_index* h, void* handle192) {
+  if (!h || !handle192) return PQT_ERR_INVALID;
   if (!h->x_val.p) return fail(h, PQT_ERR_STATE, "pqt_shard_exchange_alloc first");
   CU_TRY(h, cudaSetDevice(h->device));
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
-  cudaIpcMemHandle_t hv, hi;
+  cudaIpcMemHandle_t hv, hi, hc;
   CU_TRY(h, cudaIpcGetMemHandle(&hv, h->x_val.p));
-  CU_TRY(h, cudaIpcGetMemHandle(&hi, h->x_idx.p));
-  std::memcpy(handle128, &hv, 64);
-  std::memcpy(static_cast<char*>(handle128) + 64, &hi, 64);
+  CU_TRY(h, cudaIpcGetMemHandle(&hi, h->x_inbox.p));
+  CU_TRY(h, cudaIpcGetMemHandle(&hc, h->x_cnt.p));
+  std::memcpy(handle192, &hv, 64);
+  std::memcpy(static_cast<char*>(handle192) + 64, &hi, 64);
+  std::memcpy(static_cast<char*>(handle192) + 128, &hc, 64);
   return PQT_OK;
 }
 
@@ -1721,17 +1704,17 @@ int pqt_shard_exchange_open(pqt_index* h, uint32_t world, const void* handles) {
   for (uint32_t r = 0; r < world; r++) {
     if (r == h->rank) {
       h->x_peer_val[r] = h->x_val.as<float>();
-      h->x_peer_idx[r] = h->x_idx.as<uint32_t>();
+      h->x_peer_inbox[r] = h->x_inbox.as<uint2>();
+      h->x_peer_cnt[r] = h->x_cnt.as<uint32_t>();
       continue;
     }
-    cudaIpcMemHandle_t hv, hi;
-    std::memcpy(&hv, static_cast<const char*>(handles) + (size_t)r * 128, 64);
-    std::memcpy(&hi, static_cast<const char*>(handles) + (size_t)r * 128 + 64, 64);
-    void *pv = nullptr, *pi = nullptr;
-    CU_TRY(h, cudaIpcOpenMemHandle(&pv, hv, cudaIpcMemLazyEnablePeerAccess));
-    CU_TRY(h, cudaIpcOpenMemHandle(&pi, hi, cudaIpcMemLazyEnablePeerAccess));
-    h->x_peer_val[r] = static_cast<float*>(pv);
-    h->x_peer_idx[r] = static_cast<uint32_t*>(pi);
+    cudaIpcMemHandle_t hd[3];
+    std::memcpy(hd, static_cast<const char*>(handles) + (size_t)r * 192, 192);
+    void* pp[3] = {nullptr, nullptr, nullptr};
+    for (int j = 0; j < 3; j++) CU_TRY(h, cudaIpcOpenMemHandle(&pp[j], hd[j], cudaIpcMemLazyEnablePeerAccess));
+    h->x_peer_val[r] = static_cast<float*>(pp[0]);
+    h->x_peer_inbox[r] = static_cast<uint2*>(pp[1]);
+    h->x_peer_cnt[r] = static_cast<uint32_t*>(pp[2]);
     h->x_ipc_opened[r] = true;
   }
   h->x_world = world;
@@ -1739,76 +1722,32 @@ int pqt_shard_exchange_open(pqt_index* h, uint32_t world, const void* handles) {
 }
 
 int pqt_shard_exchange_set_peers(pqt_index* h, uint32_t world, void* const* val_ptrs,
-                                 void* const* idx_ptrs) {
-  if (!h || !val_ptrs || !idx_ptrs || world == 0 || world > 8) return PQT_ERR_INVALID;
+                                 void* const* inbox_ptrs, void* const* cnt_ptrs) {
+  if (!h || !val_ptrs || !inbox_ptrs || !cnt_ptrs || world == 0 || world > 8) return PQT_ERR_INVALID;
   if (world != h->world) return fail(h, PQT_ERR_STATE, "world differs from pqt_set_shard");
   for (uint32_t r = 0; r < world; r++) {
     h->x_peer_val[r] = static_cast<float*>(val_ptrs[r]);
-    h->x_peer_idx[r] = static_cast<uint32_t*>(idx_ptrs[r]);
+    h->x_peer_inbox[r] = static_cast<uint2*>(inbox_ptrs[r]);
+    h->x_peer_cnt[r] = static_cast<uint32_t*>(cnt_ptrs[r]);
   }
   h->x_world = world;
   return PQT_OK;
 }
 
-int pqt_shard_exchange_ptrs(pqt_index* h, void** val_ptr, void** idx_ptr) {
-  if (!h || !val_ptr || !idx_ptr) return PQT_ERR_INVALID;
+int pqt_shard_exchange_ptrs(pqt_index* h, void** val_ptr, void** inbox_ptr, void** cnt_ptr) {
+  if (!h || !val_ptr || !inbox_ptr || !cnt_ptr) return PQT_ERR_INVALID;
   if (!h->x_val.p) return fail(h, PQT_ERR_STATE, "pqt_shard_exchange_alloc first");
   *val_ptr = h->x_val.p;
-  *idx_ptr = h->x_idx.p;
+  *inbox_ptr = h->x_inbox.p;
+  *cnt_ptr = h->x_cnt.p;
   return PQT_OK;
 }
 
-// ---- multi-GPU, pull mode: every rank ranks its own queries and reads the line codes of the
-// other shards straight from their memory (NVLink); no collective on the data path -----------
-int pqt_shard_codes_handle(pqt_index* h, void* handle64) {
-  if (!h || !handle64) return PQT_ERR_INVALID;
-  if (!h->has_lines || !h->d_codes.p) return fail(h, PQT_ERR_STATE, "no line codes");
-  CU_TRY(h, cudaSetDevice(h->device));
-  cudaIpcMemHandle_t hc;
-  CU_TRY(h, cudaIpcGetMemHandle(&hc, h->d_codes.p));
-  std::memcpy(handle64, &hc, 64);
-  return PQT_OK;
-}
-
-int pqt_shard_codes_ptr(pqt_index* h, void** codes_ptr) {
-  if (!h || !codes_ptr) return PQT_ERR_INVALID;
-  if (!h->has_lines || !h->d_codes.p) return fail(h, PQT_ERR_STATE, "no line codes");
-  *codes_ptr = h->d_codes.p;
-  return PQT_OK;
-}
-
-int pqt_shard_codes_open(pqt_index* h, uint32_t world, const void* handles) {
-  if (!h || !handles || world == 0 || world > 8) return PQT_ERR_INVALID;
-  if (world != h->world) return fail(h, PQT_ERR_STATE, "world differs from pqt_set_shard");
-  if (!h->has_lines) return fail(h, PQT_ERR_STATE, "no line codes");
-  CU_TRY(h, cudaSetDevice(h->device));
-  for (uint32_t r = 0; r < world; r++) {
-    if (r == h->rank) {
-      h->c_peer[r] = h->d_codes.as<uint32_t>();
-      continue;
-    }
-    cudaIpcMemHandle_t hc;
-    std::memcpy(&hc, static_cast<const char*>(handles) + (size_t)r * 64, 64);
-    void* pc = nullptr;
-    CU_TRY(h, cudaIpcOpenMemHandle(&pc, hc, cudaIpcMemLazyEnablePeerAccess));
-    h->c_peer[r] = static_cast<const uint32_t*>(pc);
-    h->c_ipc_opened[r] = true;
-  }
-  h->c_world = world;
-  return PQT_OK;
-}
-
-int pqt_shard_codes_set_peers(pqt_index* h, uint32_t world, void* const* codes_ptrs) {
-  if (!h || !codes_ptrs || world == 0 || world > 8) return PQT_ERR_INVALID;
-  if (world != h->world) return fail(h, PQT_ERR_STATE, "world differs from pqt_set_shard");
-  for (uint32_t r = 0; r < world; r++) h->c_peer[r] = static_cast<const uint32_t*>(codes_ptrs[r]);
-  h->c_world = world;
-  return PQT_OK;
-}
-
-int pqt_shard_candidates(pqt_index* h, const float* Q, int q_on_device, uint32_t QN, uint32_t k,
-                         uint32_t q_lo, uint32_t q_hi, uint32_t* cand_pos, uint32_t* n_vec) {
-  if (!h || !Q || !cand_pos || !n_vec || q_lo >= q_hi || q_hi > QN) return PQT_ERR_INVALID;
+// Steps A-E1 for the own queries, Step B for everybody else's, then the dispatch of the own
+// queries' candidates to the shards that hold them
+int pqt_shard_dispatch(pqt_index* h, const float* Q, int q_on_device, uint32_t QN, uint32_t k,
+                       uint32_t q_lo, uint32_t q_hi) {
+  if (!h || !Q || q_lo >= q_hi || q_hi > QN) return PQT_ERR_INVALID;
   CU_TRY(h, cudaSetDevice(h->device));
   PQ_TRY(check_query_state(h, QN, k));
   const pqt_params& P = h->prm;
@@ -1816,8 +1755,12 @@ int pqt_shard_candidates(pqt_index* h, const float* Q, int q_on_device, uint32_t
   const uint32_t n = P.k1 * h->c2, npC = pow2ceil(n);
   const bool warp_path = h->c1 <= 32 && P.k1 <= 32 && (h->LP % h->p) == 0 &&
                          (h->vl == 8 || h->vl == 16 || h->vl == 32) && (h->dim % 4) == 0;
-  if (!warp_path || h->p > 4)
-    return fail(h, PQT_ERR_INVALID, "the peer-store multi-GPU path supports c1 <= 32, p <= 4, dim/p in {8,16,32}");
+  if (!warp_path || h->p > 4 || (h->LP != 16 && h->LP != 32))
+    return fail(h, PQT_ERR_INVALID, "the multi-GPU path supports c1 <= 32, p <= 4, dim/p in {8,16,32}, lineparts 16 / 32");
+  if (!h->x_world || h->x_world != h->world) return fail(h, PQT_ERR_STATE, "exchange buffers are not connected (pqt_shard_exchange_open / _set_peers)");
+  if (max_vec != h->x_max_vec) return fail(h, PQT_ERR_INVALID, "candidate width %u differs from the exchange buffers' %u", max_vec, h->x_max_vec);
+  if ((uint64_t)h->x_q_per_rank * h->world < QN || q_hi - q_lo > h->x_q_per_rank || q_lo != h->rank * h->x_q_per_rank)
+    return fail(h, PQT_ERR_INVALID, "query slice [%u, %u) does not match rank %u of q_per_rank %u", q_lo, q_hi, h->rank, h->x_q_per_rank);
   const float* dQ = Q;
   if (!q_on_device) {
     CU_TRY(h, h->s_q.ensure((size_t)QN * h->dim * 4));
@@ -1828,6 +1771,8 @@ int pqt_shard_candidates(pqt_index* h, const float* Q, int q_on_device, uint32_t
   const uint32_t nq = q_hi - q_lo;
   CU_TRY(h, h->s_lut.ensure((size_t)QN * h->c1 * 32 * sizeof(float)));
   CU_TRY(h, h->s_idx16.ensure((size_t)nq * h->p * 16 * sizeof(uint32_t)));
+  CU_TRY(h, h->s_cand.ensure((size_t)nq * max_vec * sizeof(uint32_t)));
+  CU_TRY(h, h->s_nvec.ensure((size_t)nq * sizeof(uint32_t)));
   if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[0], h->stream));
   {
     TablesWarpArgs w{};
@@ -1857,27 +1802,48 @@ int pqt_shard_candidates(pqt_index* h, const float* Q, int q_on_device, uint32_t
     }
     CU_TRY(h, cudaGetLastError());
     h->stats.kernel_launches++;
-    // Step B for the queries owned by other ranks
+    // Step B for the queries owned by other ranks (every shard scans its own candidates of
+    // every query; recomputing c1*LP short segment distances is cheaper than shipping 4 KB),
+    // on a second stream beside Steps A-E1 and the dispatch of the own queries
     const size_t lsmem = (size_t)(h->dim + h->c1 * 32) * 4;
+    CU_TRY(h, cudaEventRecord(h->aux_ev[0], h->stream));  // the queries are on the device
+    CU_TRY(h, cudaStreamWaitEvent(h->aux_stream, h->aux_ev[0], 0));
     if (q_lo > 0) {
-      lut_kernel<<<std::min<uint32_t>(q_lo, (uint32_t)h->num_sms * 8), 128, lsmem, h->stream>>>(
+      lut_kernel<<<std::min<uint32_t>(q_lo, (uint32_t)h->num_sms * 8), 128, lsmem, h->aux_stream>>>(
           dQ, h->d_cb1T.as<float>(), 0, q_lo, h->dim, h->c1, h->LP, h->sl, h->s_lut.as<float>());
       h->stats.kernel_launches++;
     }
     if (q_hi < QN) {
-      lut_kernel<<<std::min<uint32_t>(QN - q_hi, (uint32_t)h->num_sms * 8), 128, lsmem, h->stream>>>(
+      lut_kernel<<<std::min<uint32_t>(QN - q_hi, (uint32_t)h->num_sms * 8), 128, lsmem, h->aux_stream>>>(
           dQ, h->d_cb1T.as<float>(), q_hi, QN, h->dim, h->c1, h->LP, h->sl, h->s_lut.as<float>());
       h->stats.kernel_launches++;
     }
     CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaEventRecord(h->aux_ev[1], h->aux_stream));
   }
   if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[1], h->stream));
+  const bool want_roots = !(getenv("PQT_BINS_DEDUPE") && atoi(getenv("PQT_BINS_DEDUPE")) == 0);
+  PQ_TRY(launch_bins_p4(h, P, max_vec, nq, h->s_idx16.as<uint32_t>(), h->s_cand.as<uint32_t>(),
+                        h->s_nvec.as<uint32_t>(), nullptr, nullptr, want_roots));
+  {
+    DispatchArgs d{};
+    d.list_pos = h->have_roots ? h->s_rootpos.as<uint32_t>() : h->s_cand.as<uint32_t>();
+    d.n_list = h->have_roots ? h->s_nroot.as<uint32_t>() : h->s_nvec.as<uint32_t>();
+    d.q_own = nq; d.q_first = q_lo; d.max_vec = max_vec; d.world = h->world;
+    for (uint32_t r = 0; r <= h->world; r++) d.shard_lo[r] = (uint32_t)((uint64_t)h->N * r / h->world);
+    for (uint32_t r = 0; r < h->world; r++) {
+      d.peer_inbox[r] = h->x_peer_inbox[r];
+      d.peer_cnt[r] = h->x_peer_cnt[r];
+    }
+    dispatch_kernel<<<std::min<uint32_t>(nq, (uint32_t)h->num_sms * 8), 256, 0, h->stream>>>(d);
+    CU_TRY(h, cudaGetLastError());
+    h->stats.kernel_launches++;
+  }
   h->x_lut_QN = QN;
-  PQ_TRY(launch_bins_p4(h, P, max_vec, nq, h->s_idx16.as<uint32_t>(), cand_pos + (size_t)q_lo * max_vec,
-                        n_vec + q_lo, nullptr, nullptr));
   if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaStreamWaitEvent(h->stream, h->aux_ev[1], 0));  // the LUTs are ready for the scan
   if (h->profile) {
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
     float t = 0;
     cudaEventElapsedTime(&t, h->ev[0], h->ev[1]);
     h->stats.ms_tables += t;
@@ -1885,66 +1851,8 @@ int pqt_shard_candidates(pqt_index* h, const float* Q, int q_on_device, uint32_t
     h->stats.ms_bins += t;
     h->stats.queries += nq;
     h->stats.calls++;
-  }
-  return PQT_OK;
-}
-
-int pqt_shard_scan_p2p(pqt_index* h, uint32_t QN, uint32_t k, const uint32_t* cand_pos,
-                       const uint32_t* n_vec) {
-  if (!h || !cand_pos || !n_vec) return PQT_ERR_INVALID;
-  CU_TRY(h, cudaSetDevice(h->device));
-  PQ_TRY(check_query_state(h, QN, k));
-  const uint32_t max_vec = candidate_width(h, k);
-  if (!h->x_world || h->x_world != h->world) return fail(h, PQT_ERR_STATE, "exchange buffers are not connected (pqt_shard_exchange_open / _set_peers)");
-  if (max_vec != h->x_max_vec) return fail(h, PQT_ERR_INVALID, "candidate width %u differs from the exchange buffers' %u", max_vec, h->x_max_vec);
-  if ((uint64_t)h->x_q_per_rank * h->world < QN) return fail(h, PQT_ERR_INVALID, "QN exceeds q_per_rank * world");
-  if (h->x_lut_QN != QN) return fail(h, PQT_ERR_STATE, "pqt_shard_scan_p2p needs the LUTs of the same %u queries (pqt_shard_candidates was called for %u)", QN, h->x_lut_QN);
-  ScanArgs a{};
-  a.codes = h->d_codes.as<uint32_t>();
-  a.ids = h->d_dbidx.as<uint32_t>() + h->pos_lo;
-  a.cand_pos = cand_pos;
-  a.n_vec = n_vec;
-  a.lut_dup = h->s_lut.as<float>();
-  a.cbd_dup = h->d_cbd_dup.as<float>();
-  a.QN = QN; a.c1 = h->c1; a.max_vec = max_vec;
-  a.pos_lo = h->pos_lo; a.pos_hi = h->pos_hi;
-  a.p2p = 1;
-  a.q_per_rank = h->x_q_per_rank;
-  for (uint32_t r = 0; r < h->world; r++) {
-    a.peer_val[r] = h->x_peer_val[r];
-    a.peer_idx[r] = h->x_peer_idx[r];
-  }
-  size_t smem = ((size_t)h->c1 * h->c1 * 32 + kP2PGroups * 2 * (size_t)h->c1 * 32 +
-                 kP2PGroups * 2 * (size_t)max_vec) * 4 + 128;
-  if (smem > 227 * 1024) return fail(h, PQT_ERR_INVALID, "c1 = %u > 32 is not supported by the ADC scan yet", h->c1);
-  uint32_t grid = std::min<uint32_t>((QN + kP2PGroups - 1) / kP2PGroups, (uint32_t)h->num_sms);
-  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-#define LAUNCH_SCAN_P2P(LPV)                                                                     \
-  do {                                                                                           \
-    CU_TRY(h, cudaFuncSetAttribute(adc_scan_p2p_kernel<LPV>,                                     \
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    adc_scan_p2p_kernel<LPV><<<grid, kScanThreads, smem, h->stream>>>(a);                        \
-  } while (0)
-  switch (h->LP) {
-    case 1: LAUNCH_SCAN_P2P(1); break;
-    case 2: LAUNCH_SCAN_P2P(2); break;
-    case 4: LAUNCH_SCAN_P2P(4); break;
-    case 8: LAUNCH_SCAN_P2P(8); break;
-    case 16: LAUNCH_SCAN_P2P(16); break;
-    default: LAUNCH_SCAN_P2P(32); break;
-  }
-#undef LAUNCH_SCAN_P2P
-  CU_TRY(h, cudaGetLastError());
-  h->stats.kernel_launches++;
-  h->stats.scan_launches++;
-  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
-  CU_TRY(h, cudaStreamSynchronize(h->stream));
-  if (h->profile) {
-    float t = 0;
-    cudaEventElapsedTime(&t, h->ev[2], h->ev[3]);
-    h->stats.ms_scan += t;
-    std::vector<uint32_t> nv(QN);
-    cudaMemcpy(nv.data(), n_vec, (size_t)QN * 4, cudaMemcpyDeviceToHost);
+    std::vector<uint32_t> nv(nq);
+    cudaMemcpy(nv.data(), h->s_nvec.p, (size_t)nq * 4, cudaMemcpyDeviceToHost);
     uint64_t sum = 0;
     for (uint32_t v : nv) sum += v;
     h->stats.candidates += sum;
@@ -1952,9 +1860,58 @@ int pqt_shard_scan_p2p(pqt_index* h, uint32_t QN, uint32_t k, const uint32_t* ca
   return PQT_OK;
 }
 
-int pqt_shard_rank(pqt_index* h, const uint32_t* n_vec_own, uint32_t q_own, uint32_t k, uint32_t* idx,
-                   float* dist, int out_on_device) {
-  if (!h || !n_vec_own || !idx || !dist || !q_own || !k) return PQT_ERR_INVALID;
+// ADC scan of this shard's inbox (its own candidates of ALL queries); every distance is stored
+// into the distance array of the rank that owns the query.  Call after a cross-rank barrier
+// that orders it behind every rank's pqt_shard_dispatch.
+int pqt_shard_scan_p2p(pqt_index* h, uint32_t QN, uint32_t k) {
+  if (!h) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  PQ_TRY(check_query_state(h, QN, k));
+  const uint32_t max_vec = candidate_width(h, k);
+  if (!h->x_world || h->x_world != h->world) return fail(h, PQT_ERR_STATE, "exchange buffers are not connected (pqt_shard_exchange_open / _set_peers)");
+  if (max_vec != h->x_max_vec) return fail(h, PQT_ERR_INVALID, "candidate width %u differs from the exchange buffers' %u", max_vec, h->x_max_vec);
+  if ((uint64_t)h->x_q_per_rank * h->world < QN) return fail(h, PQT_ERR_INVALID, "QN exceeds q_per_rank * world");
+  if (h->x_lut_QN != QN) return fail(h, PQT_ERR_STATE, "pqt_shard_scan_p2p needs the LUTs of the same %u queries (pqt_shard_dispatch was called for %u)", QN, h->x_lut_QN);
+  if (h->LP != 16 && h->LP != 32) return fail(h, PQT_ERR_INVALID, "the multi-GPU path is built for lineparts 16 and 32");
+  StreamScanArgs sa{};
+  sa.codes = h->d_codes.as<uint32_t>();
+  sa.cand_pos = nullptr;
+  sa.n_vec = h->x_cnt.as<uint32_t>();
+  sa.lut_dup = h->s_lut.as<float>();
+  sa.cbd = h->LP == 32 ? h->d_cbd_dup.as<float>() : h->d_cbd.as<float>();
+  sa.QN = QN; sa.c1 = h->c1; sa.max_vec = max_vec;
+  sa.inbox = h->x_inbox.as<uint2>();
+  sa.q_per_rank = h->x_q_per_rank;
+  for (uint32_t r = 0; r < h->world; r++) sa.peer_val[r] = h->x_peer_val[r];
+  const size_t ssmem = stream_scan_smem_bytes(h->c1, h->LP, h->LP == 32);
+  if (ssmem > (size_t)227 * 1024) return fail(h, PQT_ERR_INVALID, "c1 = %u > 32 is not supported by the ADC scan yet", h->c1);
+  const uint32_t sgrid = std::min<uint32_t>(QN, (uint32_t)h->num_sms);
+  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+  if (h->LP == 32) {
+    CU_TRY(h, cudaFuncSetAttribute(adc_stream_kernel<32, true, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+    adc_stream_kernel<32, true, 512, true><<<sgrid, 512, ssmem, h->stream>>>(sa);
+  } else {
+    CU_TRY(h, cudaFuncSetAttribute(adc_stream_kernel<16, false, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+    adc_stream_kernel<16, false, 512, true><<<sgrid, 512, ssmem, h->stream>>>(sa);
+  }
+  CU_TRY(h, cudaGetLastError());
+  h->stats.kernel_launches++;
+  h->stats.scan_launches++;
+  h->stats.stream_scan_launches++;
+  if (h->profile) {
+    CU_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    float t = 0;
+    cudaEventElapsedTime(&t, h->ev[2], h->ev[3]);
+    h->stats.ms_scan += t;
+  }
+  return PQT_OK;
+}
+
+// Ranking of the own queries (those of the last pqt_shard_dispatch).  Call after a cross-rank
+// barrier that orders it behind every rank's pqt_shard_scan_p2p.
+int pqt_shard_rank(pqt_index* h, uint32_t q_own, uint32_t k, uint32_t* idx, float* dist, int out_on_device) {
+  if (!h || !idx || !dist || !q_own || !k) return PQT_ERR_INVALID;
   CU_TRY(h, cudaSetDevice(h->device));
   if (!h->x_val.p) return fail(h, PQT_ERR_STATE, "pqt_shard_exchange_alloc first");
   if (q_own > h->x_q_per_rank) return fail(h, PQT_ERR_INVALID, "q_own exceeds the exchange buffers");
@@ -1971,10 +1928,10 @@ int pqt_shard_rank(pqt_index* h, const uint32_t* n_vec_own, uint32_t q_own, uint
   if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
   size_t smem = rank2_smem_bytes(max_vec);
   if (smem > 48 * 1024)
-    CU_TRY(h, cudaFuncSetAttribute(rank2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(h, cudaFuncSetAttribute(rank2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // host outputs: rank in slabs so that the device->host copy of one slab overlaps the
   // ranking of the next (same scheme as pqt_query_knn)
-  const uint32_t slab = out_on_device ? q_own : std::min<uint32_t>(q_own, kSlabQueries);
+  const uint32_t slab = out_on_device ? q_own : std::min<uint32_t>(q_own, std::max<uint32_t>(256u, (q_own + 3) / 4));
   const uint32_t nslabs = (q_own + slab - 1) / slab;
   if (!out_on_device) {
     while (h->slab_ev.size() < nslabs) {
@@ -1996,14 +1953,17 @@ int pqt_shard_rank(pqt_index* h, const uint32_t* n_vec_own, uint32_t q_own, uint
     const uint32_t q0 = sidx * slab, n = std::min(slab, q_own - q0);
     Rank2Args a{};
     a.val = h->x_val.as<float>() + (size_t)q0 * max_vec;
-    a.idx = h->x_idx.as<uint32_t>() + (size_t)q0 * max_vec;
+    a.idx = h->s_cand.as<uint32_t>() + (size_t)q0 * max_vec;  // global bin-order positions
+    a.ids = h->d_dbidx.as<uint32_t>();                          // replicated: id of every position
     a.QN = n; a.max_vec = max_vec; a.k = k;
     a.out_dist = d_out_dist + (size_t)q0 * k;
     a.out_idx = d_out_idx + (size_t)q0 * k;
     a.exact_counter = h->d_exact.as<unsigned long long>();
+    a.tie_counter = h->d_exact.as<unsigned long long>() + 1;
     a.fast_rank = (h->prm.rank_mode == 0) ? 1u : 0u;
-    a.n_vec = n_vec_own + q0;
-    rank2_kernel<true><<<std::min<uint32_t>(n, (uint32_t)h->num_sms * 4), kRank2Threads, smem, h->stream>>>(a);
+    a.n_vec = h->s_nvec.as<uint32_t>() + q0;
+    a.ridx = h->have_roots ? h->s_ridx.as<uint16_t>() + (size_t)q0 * max_vec : nullptr;
+    rank2_kernel<false><<<std::min<uint32_t>(n, (uint32_t)h->num_sms * 4), kRank2Threads, smem, h->stream>>>(a);
     CU_TRY(h, cudaGetLastError());
     h->stats.kernel_launches++;
     if (!out_on_device) {
@@ -2021,35 +1981,6 @@ int pqt_shard_rank(pqt_index* h, const uint32_t* n_vec_own, uint32_t q_own, uint
     float t = 0;
     cudaEventElapsedTime(&t, h->ev[4], h->ev[5]);
     h->stats.ms_sort += t;
-  }
-  return PQT_OK;
-}
-
-int pqt_rank_candidates(pqt_index* h, float* val, uint32_t* idx, uint32_t QN, uint32_t max_vec,
-                        uint32_t k, uint32_t* out_idx, float* out_dist, int out_on_device) {
-  if (!h || !val || !idx || !out_idx || !out_dist || !QN || !k) return PQT_ERR_INVALID;
-  CU_TRY(h, cudaSetDevice(h->device));
-  float* d_out_dist = out_dist;
-  uint32_t* d_out_idx = out_idx;
-  if (!out_on_device) {
-    CU_TRY(h, h->s_outd.ensure((size_t)QN * k * 4));
-    CU_TRY(h, h->s_outi.ensure((size_t)QN * k * 4));
-    d_out_dist = h->s_outd.as<float>();
-    d_out_idx = h->s_outi.as<uint32_t>();
-  }
-  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
-  PQ_TRY(run_rank(h, val, idx, QN, max_vec, k, d_out_dist, d_out_idx));
-  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
-  if (!out_on_device) {
-    CU_TRY(h, cudaMemcpyAsync(out_idx, d_out_idx, (size_t)QN * k * 4, cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(out_dist, d_out_dist, (size_t)QN * k * 4, cudaMemcpyDeviceToHost, h->stream));
-  }
-  CU_TRY(h, cudaStreamSynchronize(h->stream));
-  if (h->profile) {
-    float t = 0;
-    cudaEventElapsedTime(&t, h->ev[4], h->ev[5]);
-    h->stats.ms_sort += t;
-    h->stats.ms_total += t;
   }
   return PQT_OK;
 }

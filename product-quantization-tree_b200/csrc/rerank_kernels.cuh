@@ -211,28 +211,42 @@ struct Bins3Args {
   uint32_t* n_vec;
   uint32_t* dbg_bins;
   uint32_t* dbg_nbins;
+  // optional (all three or none): the candidates without the repeats.  The same bin can be
+  // listed several times (the uint32 Horner hash keeps only idx_0 mod 4 of the first part), so
+  // on a dense index about a third of the candidates repeat a code row that is already in the
+  // list.  root_pos[q][i], i < n_root[q]: positions of the first occurrences, dense, in list
+  // order (what the scan kernel evaluates); ridx[q][a]: index into that array for candidate
+  // slot a (what the ranking kernel reads the distance through).
+  uint32_t* root_pos;  // [QN][max_vec]
+  uint16_t* ridx;      // [QN][max_vec]
+  uint32_t* n_root;    // [QN]
 };
 
 constexpr int kBins3Batch = kBins2Threads * kProbesPerThread;  // 4096
+constexpr uint32_t kDedupSlots = 2048;  // hash slots (key = first position of the bin's run)
 constexpr int kBins3FineProbes = 4;                            // probes per thread of the dense-index variant
 constexpr int kBins3FineBatch = kBins2Threads * kBins3FineProbes;  // 1024
 
-inline size_t bins3_smem_bytes(uint32_t max_bins, int ppt) {
+inline size_t bins3_smem_bytes(uint32_t max_bins, int ppt, bool dedupe) {
   const size_t batch = (size_t)kBins2Threads * ppt;
-  return (max_bins + std::max<size_t>(batch, 2 * kBins2Threads) + 2 * 256 + batch / 32 + 32) * 4;
+  return (max_bins + std::max<size_t>(batch, 4 * kBins2Threads) + 2 * 256 + batch / 32 + 32 +
+          (dedupe ? (size_t)kDedupSlots + kDedupSlots / 2 : 0)) * 4;
 }
 
 // dynamic smem: list[max_bins] | binbuf[max(batch, 512)] | pairs[2][256] | bits[batch/32] | warp_sums[32]
 template <int NPAIRS, int PPT>
 __global__ void __launch_bounds__(kBins2Threads, 6) bins3_kernel(Bins3Args a) {
   constexpr uint32_t kBatch = kBins2Threads * PPT;
-  constexpr uint32_t kBuf = kBatch > 2u * kBins2Threads ? kBatch : 2u * kBins2Threads;
+  constexpr uint32_t kBuf = kBatch > 4u * kBins2Threads ? kBatch : 4u * kBins2Threads;
   extern __shared__ uint32_t smem_u[];
   uint32_t* list = smem_u;
   uint32_t* binbuf = list + a.max_bins;
   uint32_t* pairs = binbuf + kBuf;
   uint32_t* bits = pairs + 2 * 256;
   uint32_t* warp_sums = bits + kBatch / 32;
+  uint32_t* tkey = warp_sums + 32;    // [kDedupSlots] dedupe table (only when a.root_pos)
+  uint16_t* tval = reinterpret_cast<uint16_t*>(tkey + kDedupSlots);  // root-array base of the key's bin
+  const bool dedupe = a.root_pos != nullptr;
   const uint32_t K = a.c1c2;
   const uint32_t p = a.p;
   // multiplier that moves the first pair past the second pair (or single last part)
@@ -260,10 +274,18 @@ __global__ void __launch_bounds__(kBins2Threads, 6) bins3_kernel(Bins3Args a) {
     uint32_t* cand = a.cand_pos + (size_t)qi * a.max_vec;
     uint32_t* s_pos = binbuf;  // E1 staging: the probe buffer is free between batches
     uint32_t* s_start = binbuf + kBins2Threads;
+    uint32_t* s_rb = binbuf + 2 * kBins2Threads;
+    uint32_t n_root = 0;  // first-occurrence candidates listed so far
+    uint32_t* rootp = dedupe ? a.root_pos + (size_t)qi * a.max_vec : nullptr;
+    uint16_t* ridx = dedupe ? a.ridx + (size_t)qi * a.max_vec : nullptr;
+    if (dedupe) {
+      for (uint32_t e = threadIdx.x; e < kDedupSlots; e += blockDim.x) tkey[e] = 0xFFFFFFFFu;
+    }
     // ---- Step E1 (:4339-4417) over list entries [done_bins, upto).  The candidate slots of a
     // chunk of bins are written by the whole CTA (slot -> bin by binary search over the chunk's
     // exclusive scan): coalesced stores, and a bin with hundreds of vectors does not serialise
-    // one thread.
+    // one thread.  Repeated bins are recognised by the first position of their run (unique per
+    // non-empty bin) in a small hash table; tval holds the root-array base of the key's bin.
     auto step_e1 = [&](uint32_t upto) {
       for (uint32_t c0 = done_bins; c0 < upto && offset < a.max_vec; c0 += blockDim.x) {
         uint32_t b = c0 + threadIdx.x;
@@ -277,6 +299,40 @@ __global__ void __launch_bounds__(kBins2Threads, 6) bins3_kernel(Bins3Args a) {
         const uint32_t pos = offset + block_exscan(nv, warp_sums, total);
         s_pos[threadIdx.x] = pos;
         s_start[threadIdx.x] = start;
+        if (dedupe) {
+          const uint32_t nvc = pos >= a.max_vec ? 0u : (pos + nv > a.max_vec ? a.max_vec - pos : nv);
+          // find-or-insert: the thread whose compare-and-swap installs the key owns the first
+          // occurrence (which of several repeats inside one chunk wins is immaterial: they hold
+          // the same code rows).  A bin cut short by the max_vec budget never registers -- a
+          // repeat could need more rows than it lists -- and a key without a free slot is
+          // treated as a first occurrence.
+          uint32_t ts = 0xFFFFFFFFu;
+          bool first = true;
+          if (nvc) {
+            uint32_t hh = (start * 2654435761u) >> 21;  // 11 bits
+#pragma unroll 1
+            for (uint32_t probe = 0; probe < 4u; probe++, hh = (hh + 1u) & (kDedupSlots - 1u)) {
+              uint32_t kx = tkey[hh];
+              if (kx == 0xFFFFFFFFu && nvc == nv) kx = atomicCAS(&tkey[hh], 0xFFFFFFFFu, start);
+              if (kx == 0xFFFFFFFFu) {  // installed (or, for a clipped bin, not present)
+                if (nvc == nv) ts = hh;
+                break;
+              }
+              if (kx == start) {
+                ts = hh;
+                first = false;
+                break;
+              }
+            }
+          }
+          uint32_t rtotal;
+          uint32_t rb = n_root + block_exscan((nvc && first) ? nvc : 0u, warp_sums, rtotal);
+          if (nvc && first && ts != 0xFFFFFFFFu) tval[ts] = (uint16_t)rb;
+          __syncthreads();
+          if (nvc && !first) rb = tval[ts];
+          s_rb[threadIdx.x] = rb | (first ? 0x80000000u : 0u);
+          n_root += rtotal;
+        }
         __syncthreads();
         const uint32_t hi = offset + total < a.max_vec ? offset + total : a.max_vec;
         for (uint32_t slot = offset + threadIdx.x; slot < hi; slot += blockDim.x) {
@@ -285,7 +341,15 @@ __global__ void __launch_bounds__(kBins2Threads, 6) bins3_kernel(Bins3Args a) {
 #pragma unroll
           for (uint32_t step = kBins2Threads >> 1; step > 0; step >>= 1)
             if (s_pos[j + step] <= slot) j += step;
-          cand[slot] = s_start[j] + (slot - s_pos[j]);
+          const uint32_t off = slot - s_pos[j];
+          const uint32_t cpos = s_start[j] + off;
+          cand[slot] = cpos;
+          if (dedupe) {
+            const uint32_t r = s_rb[j];
+            const uint32_t ri = (r & 0x7FFFFFFFu) + off;
+            ridx[slot] = (uint16_t)ri;
+            if (r >> 31) rootp[ri] = cpos;
+          }
         }
         offset += total;
         __syncthreads();
@@ -351,7 +415,10 @@ __global__ void __launch_bounds__(kBins2Threads, 6) bins3_kernel(Bins3Args a) {
       if (threadIdx.x == 0) a.dbg_nbins[qi] = nb;
     }
     step_e1(nb);
-    if (threadIdx.x == 0) a.n_vec[qi] = offset < a.max_vec ? offset : a.max_vec;
+    if (threadIdx.x == 0) {
+      a.n_vec[qi] = offset < a.max_vec ? offset : a.max_vec;
+      if (dedupe) a.n_root[qi] = n_root;
+    }
   }
 }
 
@@ -734,12 +801,6 @@ struct RerankArgs {
   uint32_t* next_query;               // work counter (zeroed before the launch): the thread groups
                                       // draw queries from it, so a slow query does not hold up a
                                       // statically assigned tail
-  // PULL mode (multi-GPU, index sharded by bin range): candidate positions are global; the code
-  // rows of shard r live at codes_adj[r] + pos * LP (codes_adj[r] = mapped slice - shard_lo[r]*LP),
-  // local or peer memory read over NVLink.  ids (s.ids) are indexed by global position.
-  uint32_t n_shards;
-  uint32_t shard_lo[9];
-  const uint32_t* codes_adj[8];
 };
 
 constexpr int kRerankGroups = 2;  // rank2_kernel / default configuration
@@ -759,7 +820,7 @@ inline size_t rerank_smem_bytes(uint32_t c1, uint32_t LP, uint32_t max_vec, int 
 // thread; the lineparts = 32 configuration runs 512 (two groups of 256 = the 256 sorter threads
 // of a 4096-wide ranking) so that a warp can hold the code rows of TWO warp steps: the loads of
 // the next step are in flight while the current one is evaluated.
-template <int LP, int NG, bool CREP, bool PULL = false, int TPB = kScanThreads>
+template <int LP, int NG, bool CREP, int TPB = kScanThreads>
 __global__ void __launch_bounds__(TPB, 1) rerank_kernel(RerankArgs g) {
   const ScanArgs& a = g.s;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -884,13 +945,7 @@ __global__ void __launch_bounds__(TPB, 1) rerank_kernel(RerankArgs g) {
       auto load = [&](uint32_t (&w)[LP], uint32_t pos) {
         // the id is read when the result is emitted: pull its sector into L2 now
         asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ids + pos));
-        if (PULL) {
-          uint32_t r = 0;
-          for (uint32_t i = 1; i < g.n_shards; i++) r += (pos >= g.shard_lo[i]) ? 1u : 0u;
-          adc_load_rows<LP, true>(w, 0u, nullptr, lp, g.codes_adj[r] + (size_t)pos * LP);
-        } else {
-          adc_load_rows<LP, false>(w, pos, codes_lp, lp, nullptr);
-        }
+        adc_load_rows<LP, false>(w, pos, codes_lp, lp, nullptr);
       };
       uint32_t e0 = warp * 32 + lane;
       if (warp * 32 >= M) return;  // warp-uniform
@@ -1062,30 +1117,36 @@ __global__ void __launch_bounds__(TPB, 1) rerank_kernel(RerankArgs g) {
 // shared memory, so every warp of the SM streams code rows all the time.  One persistent CTA
 // per SM; all warps work on the same query (its LUT is double-buffered with TMA bulk copies)
 // and every warp keeps the rows of its NEXT 32 candidates in flight while it evaluates the
-// current ones (two register sets).  Writes the distance of candidate slot a to
-// out_val[q][a] (a < nVec); ids are not touched (the ranking kernel reads them when it emits).
+// current ones (two register sets).  Writes the distance of list entry i of query q to
+// out_val[q][i] (i < n_vec[q]); ids are not touched (the ranking kernel reads them when it
+// emits).
+//
+// INBOX (multi-GPU, index sharded by bin range): the lists are this shard's inbox -- for every
+// query of the batch the candidates that live in THIS shard's slice, as (local position, entry
+// number) pairs written by the query's owner (dispatch_kernel) -- and the distance of an entry
+// is stored straight into the distance array of the rank that owns the query: peer memory over
+// NVLink, 4 bytes per candidate.  The scan and the all-to-all of the results are one kernel.
 // ============================================================================
 struct StreamScanArgs {
-  const uint32_t* codes;     // [N][LP] line codes in bin order
-  const uint32_t* cand_pos;  // [QN][max_vec]
-  const uint32_t* n_vec;     // [QN]
+  const uint32_t* codes;     // [n_local][LP] line codes in bin order (this shard's slice)
+  const uint32_t* cand_pos;  // [QN][max_vec] positions to evaluate: the candidate list, or its
+                             // first occurrences only (root_pos of the bin walk)
+  const uint32_t* n_vec;     // [QN] how many of them
   const float* lut_dup;      // [QN][c1][32]
   const float* cbd;          // [c1*c1][CROW] (replicated rows when CREP)
   uint32_t QN, c1, max_vec;
   float* out_val;            // [QN][max_vec]
-  // PULL (multi-GPU, index sharded by bin range): candidate positions are global; the code rows
-  // of shard r live at codes_adj[r] + pos * LP (mapped slice - shard_lo[r] * LP), local or peer
-  // memory read over NVLink
-  uint32_t n_shards;
-  uint32_t shard_lo[9];
-  const uint32_t* codes_adj[8];
+  // INBOX
+  const uint2* inbox;        // [QN][max_vec] (local position, entry number)
+  uint32_t q_per_rank;       // queries [r*q_per_rank, (r+1)*q_per_rank) belong to rank r
+  float* peer_val[8];        // [world] each [q_per_rank][max_vec], mapped peer (or local) memory
 };
 
 inline size_t stream_scan_smem_bytes(uint32_t c1, uint32_t LP, bool crep) {
   return ((size_t)c1 * c1 * (crep ? 32 : LP) + 2 * (size_t)c1 * 32) * 4 + 64;
 }
 
-template <int LP, bool CREP, int TPB, bool PULL = false>
+template <int LP, bool CREP, int TPB, bool INBOX = false>
 __global__ void __launch_bounds__(TPB, 1) adc_stream_kernel(StreamScanArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr uint32_t CROW = CREP ? 32u : (uint32_t)LP;
@@ -1131,43 +1192,60 @@ __global__ void __launch_bounds__(TPB, 1) adc_stream_kernel(StreamScanArgs a) {
     }
     const uint32_t nv = min(__ldg(a.n_vec + qi), a.max_vec);
     const uint32_t* cand = a.cand_pos + (size_t)qi * a.max_vec;
-    float* out = a.out_val + (size_t)qi * a.max_vec;
-    // the first two positions of this warp are requested before the LUT wait
-    uint32_t e0 = warp * 32 + lane;
-    uint32_t pos0 = e0 < nv ? __ldg(cand + e0) : 0u;
-    uint32_t pos1 = e0 + stride < nv ? __ldg(cand + e0 + stride) : 0u;
-    const float* s_lut = buf ? s_lut1 : s_lut0;
-    const uint32_t lut_b = smem_u32(s_lut) + lane * 4u;
-    auto load = [&](uint32_t (&w)[LP], uint32_t pos) {
-      if (PULL) {
-        uint32_t r = 0;
-        for (uint32_t i = 1; i < a.n_shards; i++) r += (pos >= a.shard_lo[i]) ? 1u : 0u;
-        adc_load_rows<LP, true>(w, 0u, nullptr, lp, a.codes_adj[r] + (size_t)pos * LP);
-      } else {
-        adc_load_rows<LP, false>(w, pos, codes_lp, lp, nullptr);
+    const uint2* inbox = INBOX ? a.inbox + (size_t)qi * a.max_vec : nullptr;
+    float* out;
+    if (INBOX) {
+      const uint32_t owner = qi / a.q_per_rank;
+      out = a.peer_val[owner] + (size_t)(qi - owner * a.q_per_rank) * a.max_vec;
+    } else {
+      out = a.out_val + (size_t)qi * a.max_vec;
+    }
+    // list entry e: (position of the code row, slot of the result)
+    auto fetch = [&](uint32_t e, uint32_t& pos, uint32_t& slot) {
+      pos = 0u;
+      slot = e;
+      if (e < nv) {
+        if (INBOX) {
+          const uint2 en = __ldg(inbox + e);
+          pos = en.x;
+          slot = en.y;
+        } else {
+          pos = __ldg(cand + e);
+        }
       }
     };
+    // the first two entries of this warp are requested before the LUT wait
+    uint32_t e0 = warp * 32 + lane;
+    uint32_t pos0, pos1, slot0, slot1;
+    fetch(e0, pos0, slot0);
+    fetch(e0 + stride, pos1, slot1);
+    const float* s_lut = buf ? s_lut1 : s_lut0;
+    const uint32_t lut_b = smem_u32(s_lut) + lane * 4u;
     if (warp * 32 < nv) {  // warp-uniform
       uint32_t wA[LP], wB[LP];
-      load(wA, pos0);
+      adc_load_rows<LP, false>(wA, pos0, codes_lp, lp, nullptr);
       mbar_wait(&bars[buf], buf ? phase1 : phase0);
       for (uint32_t base = warp * 32; base < nv; base += 2 * stride) {
         const bool has1 = base + stride < nv, has2 = base + 2 * stride < nv;
-        if (has1) load(wB, pos1);
-        const uint32_t pos2 = e0 + 2 * stride < nv ? __ldg(cand + e0 + 2 * stride) : 0u;
+        if (has1) adc_load_rows<LP, false>(wB, pos1, codes_lp, lp, nullptr);
+        uint32_t pos2, slot2;
+        fetch(e0 + 2 * stride, pos2, slot2);
         {
           const float v = adc_eval_rows<LP, CROW>(wA, lut_b, cbd_b, a.c1, lp);
-          if (e0 < nv) out[e0] = v;
+          if (e0 < nv) out[slot0] = v;
         }
         if (!has1) break;
-        if (has2) load(wA, pos2);
-        const uint32_t pos3 = e0 + 3 * stride < nv ? __ldg(cand + e0 + 3 * stride) : 0u;
+        if (has2) adc_load_rows<LP, false>(wA, pos2, codes_lp, lp, nullptr);
+        uint32_t pos3, slot3;
+        fetch(e0 + 3 * stride, pos3, slot3);
         {
           const float v = adc_eval_rows<LP, CROW>(wB, lut_b, cbd_b, a.c1, lp);
-          if (e0 + stride < nv) out[e0 + stride] = v;
+          if (e0 + stride < nv) out[slot1] = v;
         }
         e0 += 2 * stride;
+        slot0 = slot2;
         pos1 = pos3;
+        slot1 = slot3;
       }
     } else {
       mbar_wait(&bars[buf], buf ? phase1 : phase0);
@@ -1178,6 +1256,55 @@ __global__ void __launch_bounds__(TPB, 1) adc_stream_kernel(StreamScanArgs a) {
       phase0 ^= 1;
     __syncthreads();  // everyone is done with s_lut[buf] before it is refilled
     buf ^= 1;
+  }
+}
+
+// ============================================================================
+// Multi-GPU dispatch: the owner of a query sends every shard the candidates that live in that
+// shard's slice of the bin-ordered list -- (position inside the slice, entry number) pairs
+// appended to the query's row of the shard's inbox (peer memory over NVLink, 8 bytes per
+// candidate), plus the row's length.  One CTA per own query.
+// ============================================================================
+struct DispatchArgs {
+  const uint32_t* list_pos;  // [q_own][max_vec] global positions (candidates or first occurrences)
+  const uint32_t* n_list;    // [q_own]
+  uint32_t q_own, q_first;   // own queries are q_first .. q_first + q_own - 1 of the batch
+  uint32_t max_vec, world;
+  uint32_t shard_lo[9];
+  uint2* peer_inbox[8];      // [world] each [QN][max_vec]
+  uint32_t* peer_cnt[8];     // [world] each [QN]
+};
+
+__global__ void __launch_bounds__(256) dispatch_kernel(DispatchArgs a) {
+  __shared__ uint32_t s_cnt[8];
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t ql = blockIdx.x; ql < a.q_own; ql += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t n = min(__ldg(a.n_list + ql), a.max_vec);
+    const uint32_t* lp = a.list_pos + (size_t)ql * a.max_vec;
+    const size_t row = (size_t)(a.q_first + ql) * a.max_vec;
+    for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {
+      const uint32_t i = i0 + threadIdx.x;
+      uint32_t pos = 0, d = 0xFFu;
+      if (i < n) {
+        pos = __ldg(lp + i);
+        d = 0;
+        for (uint32_t r = 1; r < a.world; r++) d += (pos >= a.shard_lo[r]) ? 1u : 0u;
+      }
+      for (uint32_t r = 0; r < a.world; r++) {
+        const uint32_t mask = __ballot_sync(0xffffffffu, d == r);
+        if (mask) {
+          uint32_t off = 0;
+          if (lane == 0) off = atomicAdd(&s_cnt[r], __popc(mask));
+          off = __shfl_sync(0xffffffffu, off, 0) + __popc(mask & ((1u << lane) - 1u));
+          if (d == r) a.peer_inbox[r][row + off] = make_uint2(pos - a.shard_lo[r], i);
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < a.world) a.peer_cnt[threadIdx.x][a.q_first + ql] = s_cnt[threadIdx.x];
   }
 }
 
@@ -1195,6 +1322,8 @@ struct Rank2Args {
   unsigned long long* tie_counter;
   const uint32_t* n_vec;  // optional [QN]: number of real candidates; slots beyond are padding
                           // and are NOT read (peer-store mode leaves them unwritten)
+  const uint16_t* ridx;   // optional [QN][max_vec]: the distance of candidate slot a is
+                          // val[q][ridx[q][a]] (the scan evaluated repeated candidates once)
   uint32_t fast_rank;     // 1: composite-key sort first; 0: the network only
 };
 
@@ -1232,8 +1361,9 @@ __global__ void __launch_bounds__(kRank2Threads, 4) rank2_kernel(Rank2Args a) {
     // real candidates form a prefix: given (n_vec) or found (slots >= nVec hold (1e7, PAD))
     const uint32_t limit = a.n_vec ? min(a.n_vec[qi], a.max_vec) : a.max_vec;
     uint32_t local = 0, umin = 0xFFFFFFFFu, umax = 0u, bad = 0u;
+    const uint16_t* ridx_row = a.ridx ? a.ridx + (size_t)qi * a.max_vec : nullptr;
     for (uint32_t e = threadIdx.x; e < limit; e += blockDim.x) {
-      const float v = val_row[e];
+      const float v = val_row[ridx_row ? (uint32_t)ridx_row[e] : e];
       s_val[e] = v;
       const bool real = a.n_vec ? true : !(idx_row[e] == kPadIdx && v == kPadDist);
       if (real) {

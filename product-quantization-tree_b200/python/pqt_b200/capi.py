@@ -20,11 +20,10 @@ EXPORTS = [
     "pqt_set_params", "pqt_get_params", "pqt_set_stream", "pqt_read_tree", "pqt_write_tree",
     "pqt_set_tree", "pqt_get_tree_shape", "pqt_get_tree", "pqt_set_db", "pqt_set_lines",
     "pqt_query_knn", "pqt_query_big_knn_rerank2", "pqt_build_kbest_db", "pqt_line_dist", "pqt_get_db", "pqt_get_lines",
-    "pqt_get_db_size", "pqt_set_shard", "pqt_query_scan_shard", "pqt_rank_candidates",
+    "pqt_get_db_size", "pqt_set_shard",
     "pqt_candidate_width", "pqt_shard_exchange_alloc", "pqt_shard_exchange_handle",
     "pqt_shard_exchange_open", "pqt_shard_exchange_set_peers", "pqt_shard_exchange_ptrs",
-    "pqt_shard_codes_handle", "pqt_shard_codes_open", "pqt_shard_codes_set_peers", "pqt_shard_codes_ptr",
-    "pqt_shard_candidates", "pqt_shard_scan_p2p", "pqt_shard_rank", "pqt_profile_enable", "pqt_get_stats", "pqt_reset_stats",
+    "pqt_shard_dispatch", "pqt_shard_scan_p2p", "pqt_shard_rank", "pqt_profile_enable", "pqt_get_stats", "pqt_reset_stats",
     "pqt_debug_enable", "pqt_debug_stage",
     "pqt_assign_bins", "pqt_set_db_from_bins", "pqt_line_dist_begin", "pqt_line_dist_chunk",
     "pqt_line_dist_end", "pqt_get_codes_binorder",
@@ -113,24 +112,16 @@ def lib():
         L.pqt_get_lines.argtypes = [C.c_void_p, C.c_void_p]
         L.pqt_get_db_size.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.pqt_set_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
-        L.pqt_query_scan_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32,
-                                           C.c_uint32, C.c_void_p, C.c_void_p]
-        L.pqt_rank_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
-                                          C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
         L.pqt_shard_exchange_alloc.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         L.pqt_shard_exchange_handle.argtypes = [C.c_void_p, C.c_void_p]
         L.pqt_shard_exchange_open.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
-        L.pqt_shard_exchange_set_peers.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
-        L.pqt_shard_exchange_ptrs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
-        L.pqt_shard_codes_handle.argtypes = [C.c_void_p, C.c_void_p]
-        L.pqt_shard_codes_open.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
-        L.pqt_shard_codes_set_peers.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
-        L.pqt_shard_codes_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
-        L.pqt_shard_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32,
-                                           C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
-        L.pqt_shard_scan_p2p.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
-        L.pqt_shard_rank.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
-                                     C.c_void_p, C.c_int]
+        L.pqt_shard_exchange_set_peers.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pqt_shard_exchange_ptrs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                              C.POINTER(C.c_void_p)]
+        L.pqt_shard_dispatch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32,
+                                         C.c_uint32, C.c_uint32]
+        L.pqt_shard_scan_p2p.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        L.pqt_shard_rank.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
         L.pqt_candidate_width.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
         L.pqt_profile_enable.argtypes = [C.c_void_p, C.c_int]
         L.pqt_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
@@ -346,75 +337,43 @@ class PerturbationProTree:
         self._chk(self._L.pqt_query_big_knn_rerank2(self._h, qp, qdev, QN, k, ip, dp, idev))
         return out_idx, out_dist
 
-    def queryScanShard(self, Q, QN, k, val, idx):
-        qp, qdev = _ptr(Q)
-        self._chk(self._L.pqt_query_scan_shard(self._h, qp, qdev, QN, k, _ptr(val)[0],
-                                               _ptr(idx)[0]))
-
-    def rankCandidates(self, val, idx, QN, max_vec, k, out_idx, out_dist):
-        ip, idev = _ptr(out_idx)
-        dp, _ = _ptr(out_dist)
-        self._chk(self._L.pqt_rank_candidates(self._h, _ptr(val)[0], _ptr(idx)[0], QN, max_vec,
-                                              k, ip, dp, idev))
-
-    # ---- multi-GPU: fused scan + exchange over peer memory (include/pqt_b200.h)
+    # ---- multi-GPU: dispatch + scan fused with the exchange over peer memory (include/pqt_b200.h)
     def shardExchangeAlloc(self, q_per_rank, max_vec):
         self._chk(self._L.pqt_shard_exchange_alloc(self._h, q_per_rank, max_vec))
 
     def shardExchangeHandle(self):
-        buf = C.create_string_buffer(128)
+        buf = C.create_string_buffer(192)
         self._chk(self._L.pqt_shard_exchange_handle(self._h, buf))
         return buf.raw
 
     def shardExchangeOpen(self, handles):
-        """handles: list of 128-byte IPC handles, entry r from rank r"""
+        """handles: list of 192-byte IPC handle blobs, entry r from rank r"""
         blob = b"".join(handles)
         self._chk(self._L.pqt_shard_exchange_open(self._h, len(handles), blob))
 
     def shardExchangePtrs(self):
-        v, i = C.c_void_p(), C.c_void_p()
-        self._chk(self._L.pqt_shard_exchange_ptrs(self._h, C.byref(v), C.byref(i)))
-        return v.value, i.value
+        v, i, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._chk(self._L.pqt_shard_exchange_ptrs(self._h, C.byref(v), C.byref(i), C.byref(c)))
+        return v.value, i.value, c.value
 
-    def shardExchangeSetPeers(self, val_ptrs, idx_ptrs):
+    def shardExchangeSetPeers(self, val_ptrs, inbox_ptrs, cnt_ptrs):
         n = len(val_ptrs)
         va = (C.c_void_p * n)(*val_ptrs)
-        ia = (C.c_void_p * n)(*idx_ptrs)
-        self._chk(self._L.pqt_shard_exchange_set_peers(self._h, n, va, ia))
+        ia = (C.c_void_p * n)(*inbox_ptrs)
+        ca = (C.c_void_p * n)(*cnt_ptrs)
+        self._chk(self._L.pqt_shard_exchange_set_peers(self._h, n, va, ia, ca))
 
-    # ---- pull mode: code slices of the other shards mapped into this handle
-    def shardCodesHandle(self):
-        buf = C.create_string_buffer(64)
-        self._chk(self._L.pqt_shard_codes_handle(self._h, buf))
-        return buf.raw
-
-    def shardCodesOpen(self, handles):
-        """handles: list of 64-byte IPC handles, entry r from rank r"""
-        blob = b"".join(handles)
-        self._chk(self._L.pqt_shard_codes_open(self._h, len(handles), blob))
-
-    def shardCodesPtr(self):
-        p = C.c_void_p()
-        self._chk(self._L.pqt_shard_codes_ptr(self._h, C.byref(p)))
-        return p.value
-
-    def shardCodesSetPeers(self, ptrs):
-        n = len(ptrs)
-        pa = (C.c_void_p * n)(*ptrs)
-        self._chk(self._L.pqt_shard_codes_set_peers(self._h, n, pa))
-
-    def shardCandidates(self, Q, QN, k, q_lo, q_hi, cand_pos, n_vec):
+    def shardDispatch(self, Q, QN, k, q_lo, q_hi):
         qp, qdev = _ptr(Q)
-        self._chk(self._L.pqt_shard_candidates(self._h, qp, qdev, QN, k, q_lo, q_hi,
-                                               _ptr(cand_pos)[0], _ptr(n_vec)[0]))
+        self._chk(self._L.pqt_shard_dispatch(self._h, qp, qdev, QN, k, q_lo, q_hi))
 
-    def shardScanP2P(self, QN, k, cand_pos, n_vec):
-        self._chk(self._L.pqt_shard_scan_p2p(self._h, QN, k, _ptr(cand_pos)[0], _ptr(n_vec)[0]))
+    def shardScanP2P(self, QN, k):
+        self._chk(self._L.pqt_shard_scan_p2p(self._h, QN, k))
 
-    def shardRank(self, n_vec_own, q_own, k, out_idx, out_dist):
+    def shardRank(self, q_own, k, out_idx, out_dist):
         ip, idev = _ptr(out_idx)
         dp, _ = _ptr(out_dist)
-        self._chk(self._L.pqt_shard_rank(self._h, _ptr(n_vec_own)[0], q_own, k, ip, dp, idev))
+        self._chk(self._L.pqt_shard_rank(self._h, q_own, k, ip, dp, idev))
 
     # ---- measurement / introspection
     def profile(self, on=True):

@@ -1,15 +1,13 @@
 """Host logic of the multi-GPU path (one process per GPU, torch.distributed).
 
-The index is cut into contiguous slices of the bin-ordered vector list (pqt_set_shard);
-every rank scans only its own candidates and marks the rest with (+inf, INT32_MIN).
-Since each candidate slot has exactly one owner, an element-wise float MIN / int32 MAX
-across ranks assembles exactly the single-GPU candidate arrays; the exchange is one
-reduce-scatter per array (NCCL), each rank keeping the queries it will rank.
-"""
+The bin-ordered code array is cut into contiguous slices with equal vector counts
+(pqt_set_shard); rank r owns the queries [r*q_per_rank, (r+1)*q_per_rank) of a batch and the
+code rows of its slice.  Per batch every rank dispatches the candidates of its own queries to
+the shards that hold them (pqt_shard_dispatch), scans its own inbox and stores every distance
+into the owner's array (pqt_shard_scan_p2p), and ranks its own queries (pqt_shard_rank); two
+stream-ordered barriers separate the phases.  The helpers below restate the partition rules on
+the host (tests, sizing)."""
 import torch
-import torch.distributed as dist
-
-NOT_MINE_IDX = -(1 << 31)  # 0x80000000 as int32
 
 
 def shard_bounds(n, rank, world):
@@ -18,8 +16,8 @@ def shard_bounds(n, rank, world):
 
 
 def shard_of(pos, n, world):
-    """Shard that holds bin-order position `pos`: the rule of the pull-mode scan kernel
-    (rerank_kernel<..., PULL>: r = number of shard lower bounds 1..world-1 that are <= pos)."""
+    """Shard that holds bin-order position `pos`: the rule of dispatch_kernel
+    (r = number of shard lower bounds 1..world-1 that are <= pos)."""
     r = 0
     for i in range(1, world):
         r += 1 if pos >= (n * i) // world else 0
@@ -32,34 +30,17 @@ def query_slice(qn, rank, world):
     return rank * per, (rank + 1) * per
 
 
-def exchange(val, idx, val_out, idx_out, rank, world, group=None):
-    """val/idx: [QN][max_vec] per-shard candidate arrays (float32 / int32).  Fills
-    val_out/idx_out [QN/world][max_vec] with the assembled arrays of this rank's queries."""
-    if world == 1:
-        val_out.copy_(val)
-        idx_out.copy_(idx)
-        return
-    if dist.get_backend(group) == "nccl":
-        dist.reduce_scatter_tensor(val_out, val, op=dist.ReduceOp.MIN, group=group)
-        dist.reduce_scatter_tensor(idx_out, idx, op=dist.ReduceOp.MAX, group=group)
-    else:  # gloo (CPU tests): all-reduce then keep the own slice
-        v = val.clone()
-        i = idx.clone()
-        dist.all_reduce(v, op=dist.ReduceOp.MIN, group=group)
-        dist.all_reduce(i, op=dist.ReduceOp.MAX, group=group)
-        lo, hi = query_slice(val.shape[0], rank, world)
-        val_out.copy_(v[lo:hi])
-        idx_out.copy_(i[lo:hi])
-
-
-def mask_to_shard(val, idx, cand_pos, n_vec, lo, hi, owns_pad):
-    """Reference semantics of adc_scan_kernel's ownership rule on full candidate arrays
-    (torch, any device): used by the CPU tests to emulate a shard."""
-    qn, mv = val.shape
-    a = torch.arange(mv, device=val.device)[None, :]
-    real = a < n_vec[:, None].to(torch.int64)
-    mine = real & (cand_pos >= lo) & (cand_pos < hi)
-    keep = mine | (~real if owns_pad else torch.zeros_like(real))
-    v = torch.where(keep, val, torch.full_like(val, float("inf")))
-    i = torch.where(keep, idx, torch.full_like(idx, NOT_MINE_IDX))
-    return v, i
+def dispatch(list_pos, n_list, n, world):
+    """Reference of dispatch_kernel on torch tensors: list_pos [Q][max_vec] global positions,
+    n_list [Q].  Returns per shard r a list over queries of (local positions, entry numbers),
+    entries in list order."""
+    out = []
+    los = torch.tensor([(n * r) // world for r in range(world + 1)], dtype=torch.int64)
+    for r in range(world):
+        rows = []
+        for q in range(list_pos.shape[0]):
+            p = list_pos[q, :int(n_list[q])].to(torch.int64)
+            m = (p >= los[r]) & (p < los[r + 1])
+            rows.append((p[m] - los[r], torch.nonzero(m).flatten()))
+        out.append(rows)
+    return out

@@ -284,124 +284,59 @@ def test_loaded_db_round_trips(case_small):
     t.close()
 
 
-def test_sharded_scan_assembles_the_single_gpu_result(case_small):
-    """bin-range shards on one device: element-wise min / max over the per-shard candidate
-    arrays (what the reduce-scatter does across GPUs) reproduces queryKNN exactly."""
+def _run_sharded(c, k, world, QN, **params):
+    """Bin-range shards in one process: `world` handles on one device wired with plain device
+    pointers instead of CUDA-IPC mappings; the three phases run rank after rank (the barriers
+    of the multi-process path).  Returns (idx, dist) of all queries."""
     import torch
-    c = case_small
-    QN, k = c["Q"].shape[0], 256
-    d0, i0 = oracle_query(c, k)
-    world = 3
-    Qd = torch.from_numpy(c["Q"]).cuda()
-    vals, idxs = [], []
-    for r in range(world):
-        t = make_gpu_index(c, shard=(r, world))
-        mv = t.candidateWidth(k)
-        v = torch.empty((QN, mv), dtype=torch.float32, device="cuda")
-        i = torch.empty((QN, mv), dtype=torch.int32, device="cuda")
-        t.queryScanShard(Qd, QN, k, v, i)
-        vals.append(v)
-        idxs.append(i)
-        t.close()
-    val = torch.stack(vals).amin(0).contiguous()
-    idx = torch.stack(idxs).amax(0).contiguous()  # signed max: INT32_MIN marks "not mine"
-    # every slot has exactly one finite owner
-    assert int((torch.stack(vals) < float("inf")).sum(0).min()) == 1
-    t = make_gpu_index(c)
-    oi = torch.zeros((QN, k), dtype=torch.int32, device="cuda")
-    od = torch.zeros((QN, k), dtype=torch.float32, device="cuda")
-    t.rankCandidates(val, idx, QN, mv, k, oi, od)
-    assert np.array_equal(oi.cpu().numpy().view(np.uint32), i0)
-    assert np.array_equal(od.cpu().numpy(), d0)
-    t.close()
-
-
-@pytest.mark.parametrize("which", ["small", "lp32", "dense"])
-def test_pull_mode_shards_in_one_process(which, case_small, case_lp32, case_dense):
-    """Pull mode: the index cut into 3 bin-range shards (three handles on one device, wired
-    with plain device pointers instead of IPC handles); each handle answers a slice of the
-    queries with pqt_query_knn, reading the other shards' line codes from their memory.  The
-    result is the single-index result, ties included."""
-    import torch
-    c = {"small": case_small, "lp32": case_lp32, "dense": case_dense}[which]
-    QN = c["Q"].shape[0]
-    k = 4096 if which == "dense" else 256
-    d0, i0 = oracle_query(c, k)
-    world = 3
-    hs = [make_gpu_index(c, shard=(r, world)) for r in range(world)]
-    ptrs = [t.shardCodesPtr() for t in hs]
-    for t in hs:
-        t.shardCodesSetPeers(ptrs)
-    Qd = torch.from_numpy(c["Q"]).cuda()
-    per = (QN + world - 1) // world
-    for r, t in enumerate(hs):
-        lo, hi = r * per, min(QN, (r + 1) * per)
-        oi = torch.zeros((hi - lo, k), dtype=torch.int32, device="cuda")
-        od = torch.zeros((hi - lo, k), dtype=torch.float32, device="cuda")
-        t.queryKNN(Qd[lo:hi].contiguous(), hi - lo, k, oi, od)
-        assert np.array_equal(od.cpu().numpy(), d0[lo:hi]), "rank %d" % r
-        assert np.array_equal(oi.cpu().numpy().view(np.uint32), i0[lo:hi]), "rank %d" % r
-    for t in hs:
-        t.close()
-
-
-def test_rank_candidates_dense_lists_with_ties(case_dense):
-    """The shard ranking kernel (rank2_kernel) on assembled 4096-candidate lists: composite-key
-    sort + repair + tie resolver return the oracle's order, ties included; so does the
-    network-only mode."""
-    import torch
-    c = case_dense
-    QN, k = c["Q"].shape[0], 4096
-    d0, i0 = oracle_query(c, k)
-    Qd = torch.from_numpy(c["Q"]).cuda()
-    for mode in (0, 1):
-        t = make_gpu_index(c, rank_mode=mode)
-        mv = t.candidateWidth(k)
-        v = torch.empty((QN, mv), dtype=torch.float32, device="cuda")
-        i = torch.empty((QN, mv), dtype=torch.int32, device="cuda")
-        t.queryScanShard(Qd, QN, k, v, i)
-        oi = torch.zeros((QN, k), dtype=torch.int32, device="cuda")
-        od = torch.zeros((QN, k), dtype=torch.float32, device="cuda")
-        t.rankCandidates(v, i, QN, mv, k, oi, od)
-        assert np.array_equal(od.cpu().numpy(), d0), "rank_mode %d" % mode
-        assert np.array_equal(oi.cpu().numpy().view(np.uint32), i0), "rank_mode %d" % mode
-        t.close()
-
-
-def test_peer_store_shards_in_one_process(case_small):
-    """The fused scan + exchange path with three shard handles on one device: every shard
-    stores the distances of its own candidates straight into the owner's candidate arrays
-    (here: plain device pointers instead of IPC-mapped peer memory)."""
-    import torch
-    c = case_small
-    QN, k, world = 48, 256, 3
-    c = dict(c)
-    c["Q"] = case_small["Q"][:QN]
-    d0, i0 = oracle_query(c, k)
-    Qd = torch.from_numpy(c["Q"]).cuda()
-    ts = [make_gpu_index(c, shard=(r, world)) for r in range(world)]
+    Qd = torch.from_numpy(np.ascontiguousarray(c["Q"][:QN])).cuda()
+    ts = [make_gpu_index(c, shard=(r, world), **params) for r in range(world)]
     mv = ts[0].candidateWidth(k)
     per = QN // world
     for t in ts:
         t.shardExchangeAlloc(per, mv)
     ptrs = [t.shardExchangePtrs() for t in ts]
     for t in ts:
-        t.shardExchangeSetPeers([p[0] for p in ptrs], [p[1] for p in ptrs])
-    cand = torch.zeros((QN, mv), dtype=torch.int32, device="cuda")
-    nvec = torch.zeros((QN,), dtype=torch.int32, device="cuda")
-    for r, t in enumerate(ts):   # every rank fills the rows of its own queries (+ "all-gather")
-        t.shardCandidates(Qd, QN, k, r * per, (r + 1) * per, cand, nvec)
-    for t in ts:
-        t.shardScanP2P(QN, k, cand, nvec)
-    torch.cuda.synchronize()
+        t.shardExchangeSetPeers([p[0] for p in ptrs], [p[1] for p in ptrs], [p[2] for p in ptrs])
     for r, t in enumerate(ts):
-        oi = torch.zeros((per, k), dtype=torch.int32, device="cuda")
-        od = torch.zeros((per, k), dtype=torch.float32, device="cuda")
-        t.shardRank(nvec[r * per:(r + 1) * per].contiguous(), per, k, oi, od)
-        assert np.array_equal(oi.cpu().numpy().view(np.uint32), i0[r * per:(r + 1) * per])
-        assert np.array_equal(od.cpu().numpy(), d0[r * per:(r + 1) * per])
+        t.shardDispatch(Qd, QN, k, r * per, (r + 1) * per)
+    for t in ts:
+        t.shardScanP2P(QN, k)
+    torch.cuda.synchronize()
+    oi = torch.zeros((QN, k), dtype=torch.int32, device="cuda")
+    od = torch.zeros((QN, k), dtype=torch.float32, device="cuda")
+    for r, t in enumerate(ts):
+        t.shardRank(per, k, oi[r * per:(r + 1) * per], od[r * per:(r + 1) * per])
     for t in ts:
         t.close()
+    return oi.cpu().numpy().view(np.uint32), od.cpu().numpy()
+
+
+@pytest.mark.parametrize("which,world", [("small", 3), ("lp32", 2), ("dense", 3), ("dense", 1)])
+def test_shards_in_one_process(which, world, case_small, case_lp32, case_dense):
+    """The multi-GPU pipeline (dispatch -> inbox scan with stores into the owner's arrays ->
+    ranking) returns the single-index result, ties included; world = 1 is the degenerate case
+    where every candidate stays at home."""
+    c = {"small": case_small, "lp32": case_lp32, "dense": case_dense}[which]
+    k = 4096 if which == "dense" else 256
+    QN = (c["Q"].shape[0] // world) * world
+    c = dict(c)
+    c["Q"] = c["Q"][:QN]
+    d0, i0 = oracle_query(c, k)
+    for mode in ((0, 1) if which == "dense" else (0,)):
+        i1, d1 = _run_sharded(c, k, world, QN, rank_mode=mode)
+        assert np.array_equal(d1, d0), "rank_mode %d" % mode
+        assert np.array_equal(i1, i0), "rank_mode %d" % mode
+
+
+def test_sharded_handle_rejects_the_single_gpu_call(case_small):
+    import pqt_b200
+    t = make_gpu_index(case_small, shard=(0, 2))
+    with pytest.raises(pqt_b200.PqtError):
+        t.queryKNN(case_small["Q"], 4, 16)
+    with pytest.raises(pqt_b200.PqtError):
+        t.shardScanP2P(4, 16)  # exchange buffers not connected
+    t.close()
 
 
 # ---- a11: the 1-B variant queryBIGKNNRerank2 ---------------------------------------------

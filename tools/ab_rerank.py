@@ -25,9 +25,10 @@ def main():
     od = torch.empty((a.qn, a.k), dtype=torch.float32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     ref = None
-    for mode, tpb, dd in (("fused", "512", "1"), ("split", "512", "1"), ("fused", "1024", "1")):
+    for mode, tpb, dd, bd in (("split", "512", "1", "0"), ("split", "512", "1", "1"), ("fused", "512", "1", "1")):
         if True:
             os.environ["PQT_SCAN_MODE"] = mode
+            os.environ["PQT_BINS_DEDUPE"] = bd
             os.environ["PQT_RERANK_TPB"] = tpb
             os.environ["PQT_RERANK_DEDUPE"] = dd
             for _ in range(3):
@@ -43,6 +44,7 @@ def main():
             cur = (oi.clone(), od.clone())
             same = None if ref is None else bool(torch.equal(cur[0], ref[0]) and torch.equal(cur[1], ref[1]))
             ref = ref or cur
+            print("bins_dedupe %s " % bd, end="")
             print("%s tpb %s dedupe %s: tables %.3f bins %.3f scan %.3f rank %.3f ms/step  same_as_first=%s" % (
                 mode, tpb, dd, st.ms_tables / a.steps, st.ms_bins / a.steps, st.ms_scan / a.steps,
                 st.ms_sort / a.steps, same), flush=True)
