@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--workload", default="c3", choices=["c2", "c3"],
                     help="c3 = BASELINE configs[2]: 1B vectors, lineparts 32 (default); "
                          "c2 = configs[1]: 1M vectors, lineparts 16")
-    ap.add_argument("--n", type=int, default=0, help="database vectors (overrides the workload)")
+    ap.add_argument("--n", "--dbsize", dest="n", type=int, default=0, help="database vectors (overrides the workload)")
     ap.add_argument("--lineparts", type=int, default=0)
     ap.add_argument("--qn", type=int, default=10000, help="queries per batch")
     ap.add_argument("--k", type=int, default=4096)
@@ -436,6 +436,11 @@ def run_b200(a, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = "cuda:%d" % local_rank
+    # one explicit stream for everything: torch ops, NCCL (ordered against the current stream)
+    # and the library's launches.  The legacy default stream would not do: its handle is NULL,
+    # which pqt_set_stream reads as "the handle's own stream".
+    stream = torch.cuda.Stream(device=device)
+    torch.cuda.set_stream(stream)
     variants = [v for v in a.variants.split(",") if v]
     inp = build_inputs(a, device)
     # The CPU legs (cpu_baseline, parity sample) read the reference's index files; they are
@@ -462,13 +467,12 @@ def run_b200(a, rank, world, local_rank):
     replica = world > 1 and a.mode == "replica"
     t = pqt_b200.PerturbationProTree(a.dim, a.p, a.p, local_rank)
     t.set_params(hash_size=a.hashsize, k1_build=min(16, a.c1))
+    t.set_stream(stream.cuda_stream)
     t.setTree(inp["cb1"], inp["cb2"])
     if sharded:
         assert a.qn % world == 0, "qn must be divisible by the number of ranks"
         t.setShard(rank, world)
     build = build_index_chunked(a, t, inp, 0 if replica else rank, 1 if replica else world, device)
-    stream = torch.cuda.current_stream()
-    t.set_stream(stream.cuda_stream)
     QN, k = a.qn, a.k
     Qd = inp["Q8"].to(torch.float32).contiguous()
     Qh = Qd.cpu().pin_memory()
@@ -527,24 +531,31 @@ def run_b200(a, rank, world, local_rank):
             step_device()
         barrier()
         # device-resident timing (value): CUDA events on the launching stream, L2 flushed
-        # between steps (flush outside the event pairs)
-        t.profile(True)
-        t.reset_stats()
+        # between steps (flush outside the event pairs); nothing synchronises with the host
+        # inside a step
+        def timed_pass():
+            evs = []
+            barrier()
+            for _ in range(a.steps):
+                flush.zero_()
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                step_device()
+                e1.record(stream)
+                evs.append((e0, e1))
+            barrier()
+            return sum(e0.elapsed_time(e1) for e0, e1 in evs)
+
         sampler = ClockSampler(local_rank)
         sampler.start()
-        evs = []
-        barrier()
-        for _ in range(a.steps):
-            flush.zero_()
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            step_device()
-            e1.record(stream)
-            evs.append((e0, e1))
-        barrier()
+        dev_ms = timed_pass()
         clocks = sampler.stop()
-        dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+        # the same pass again with the library's per-stage events on (a host synchronisation
+        # after every stage): stage times and counters for the roofline, not part of `value`
+        t.profile(True)
+        t.reset_stats()
+        prof_ms = timed_pass()
         st = t.stats()
         t.profile(False)
         # end-to-end through the public call with host buffers
@@ -571,7 +582,7 @@ def run_b200(a, rank, world, local_rank):
         else:
             full_i, full_d = res_i, res_d
         return dict(dev_ms=float(tm[0]), e2e_ms=float(tm[1]), st=st, clocks=clocks, idx=full_i,
-                    dist=full_d)
+                    dist=full_d, prof_ms=prof_ms)
 
     results = {}
     for v in variants:
@@ -628,7 +639,8 @@ def run_b200(a, rank, world, local_rank):
                          "candidates_per_launch": cand_per_launch,
                          "bytes_per_candidate": bytes_per_cand,
                          "stage_ms_per_step": {"tables": st.ms_tables / a.steps, "bins": st.ms_bins / a.steps,
-                                               "scan": st.ms_scan / a.steps, "sort": st.ms_sort / a.steps}},
+                                               "scan": st.ms_scan / a.steps, "sort": st.ms_sort / a.steps},
+                         "profiled_ms_per_step": r["prof_ms"] / a.steps},
             "recall_at_1": float((r["idx"][:, 0] == gtu).mean()),
             "recall_at_100": float((r["idx"][:, :100] == gtu[:, None]).any(1).mean()),
             "gpu_launches": int(st.kernel_launches),

@@ -109,7 +109,11 @@ void pqt_default_params(pqt_params *prm);
 int pqt_set_params(pqt_index *h, const pqt_params *prm);
 int pqt_get_params(const pqt_index *h, pqt_params *prm);
 /* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the
- * handle's own stream.  The reference uses the default stream throughout. */
+ * handle's own (non-blocking) stream.  The legacy default stream's handle is NULL as
+ * well: to run on a default stream pass cudaStreamLegacy / cudaStreamPerThread.  Work the
+ * caller enqueues on other streams (NCCL barriers of the multi-GPU path included) is
+ * ordered against the library's only through this stream.  The reference uses the
+ * default stream throughout. */
 int pqt_set_stream(pqt_index *h, void *cuda_stream);
 
 /* ---- index state (load path) ----------------------------------------------- */

@@ -300,9 +300,10 @@ def _run_sharded(c, k, world, QN, **params):
         t.shardExchangeSetPeers([p[0] for p in ptrs], [p[1] for p in ptrs], [p[2] for p in ptrs])
     for r, t in enumerate(ts):
         t.shardDispatch(Qd, QN, k, r * per, (r + 1) * per)
+    torch.cuda.synchronize()  # the cross-rank barrier: every inbox is complete
     for t in ts:
         t.shardScanP2P(QN, k)
-    torch.cuda.synchronize()
+    torch.cuda.synchronize()  # the cross-rank barrier: every distance has arrived
     oi = torch.zeros((QN, k), dtype=torch.int32, device="cuda")
     od = torch.zeros((QN, k), dtype=torch.float32, device="cuda")
     for r, t in enumerate(ts):
