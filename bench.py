@@ -654,7 +654,8 @@ def run_b200(a, rank, world, local_rank):
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         key = "%d_lp%d" % (a.n, a.lineparts)
         if "knn" in summ and not sharded:
-            summ["knn"]["roofline"]["traffic"] = tj["rerank_kernel"].get(key, {}).get("bytes")
+            kern = "adc_stream_kernel" if results["knn"]["st"].stream_scan_launches > 0 else "rerank_kernel"
+            summ["knn"]["roofline"]["traffic"] = tj[kern].get(key, {}).get("bytes")
     except Exception:  # noqa: BLE001
         pass
 

@@ -503,6 +503,13 @@ int launch_bins_p4(pqt_index* h, const pqt_params& P, uint32_t max_vec, uint32_t
   return PQT_OK;
 }
 
+// ranking kernel: counting sort of the composite words (default) or their bitonic sort
+// (PQT_RANK_SORT=bitonic, for A/B runs)
+static bool rank_bucket_sort() {
+  static const bool on = !(getenv("PQT_RANK_SORT") && strcmp(getenv("PQT_RANK_SORT"), "bitonic") == 0);
+  return on;
+}
+
 // Steps A..E2 (distance part) for QN queries already on the device; fills
 // val/idx [QN][max_vec].  Records profile events ev[0..3] when enabled.
 // With fused_out_* set (single GPU) the scan, the ranking and the first-k emit run in one
@@ -735,7 +742,12 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
       ra.n_vec = h->s_nvec.as<uint32_t>();
       ra.ridx = h->have_roots ? h->s_ridx.as<uint16_t>() : nullptr;
       ra.fast_rank = (P.rank_mode == 0) ? 1u : 0u;
-      const size_t rsmem = rank2_smem_bytes(max_vec);
+      ra.bucket_sort = rank_bucket_sort() ? 1u : 0u;
+      if (h->debug) {
+        CU_TRY(h, h->g_phases.ensure((size_t)QN * 8 * 8));
+        ra.phase_dbg = h->g_phases.as<unsigned long long>();
+      }
+      const size_t rsmem = rank2_smem_bytes(max_vec, ra.bucket_sort != 0);
       if (rsmem > 48 * 1024)
         CU_TRY(h, cudaFuncSetAttribute(rank2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
       rank2_kernel<false><<<std::min<uint32_t>(QN, (uint32_t)h->num_sms * 4), kRank2Threads, rsmem, h->stream>>>(ra);
@@ -854,7 +866,8 @@ int run_rank(pqt_index* h, const float* d_val, const uint32_t* d_idx, uint32_t Q
   a.out_dist = d_out_dist; a.out_idx = d_out_idx;
   a.exact_counter = h->d_exact.as<unsigned long long>();
   a.fast_rank = (h->prm.rank_mode == 0) ? 1u : 0u;
-  size_t smem = rank2_smem_bytes(max_vec);
+  a.bucket_sort = rank_bucket_sort() ? 1u : 0u;
+  size_t smem = rank2_smem_bytes(max_vec, a.bucket_sort != 0);
   if (smem > 48 * 1024)
     CU_TRY(h, cudaFuncSetAttribute(rank2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 4);
@@ -1926,7 +1939,7 @@ int pqt_shard_rank(pqt_index* h, uint32_t q_own, uint32_t k, uint32_t* idx, floa
     d_out_idx = h->s_outi.as<uint32_t>();
   }
   if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
-  size_t smem = rank2_smem_bytes(max_vec);
+  size_t smem = rank2_smem_bytes(max_vec, rank_bucket_sort());
   if (smem > 48 * 1024)
     CU_TRY(h, cudaFuncSetAttribute(rank2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // host outputs: rank in slabs so that the device->host copy of one slab overlaps the
@@ -1961,6 +1974,7 @@ int pqt_shard_rank(pqt_index* h, uint32_t q_own, uint32_t k, uint32_t* idx, floa
     a.exact_counter = h->d_exact.as<unsigned long long>();
     a.tie_counter = h->d_exact.as<unsigned long long>() + 1;
     a.fast_rank = (h->prm.rank_mode == 0) ? 1u : 0u;
+    a.bucket_sort = rank_bucket_sort() ? 1u : 0u;
     a.n_vec = h->s_nvec.as<uint32_t>() + q0;
     a.ridx = h->have_roots ? h->s_ridx.as<uint16_t>() + (size_t)q0 * max_vec : nullptr;
     rank2_kernel<false><<<std::min<uint32_t>(n, (uint32_t)h->num_sms * 4), kRank2Threads, smem, h->stream>>>(a);

@@ -1,11 +1,12 @@
 // query_kernels.cuh -- the queryKNN chain as sm_100a kernels.
 //
-//   tables_kernel   Steps A+B+C  (getKBestAssignment, getLineAssignment,
-//                                 getKBestAssignment2)
-//   bins_kernel     Steps D+E1   (getBins / selectBinKernelFast2,
-//                                 getKVectorIDsKernelFast)
-//   adc_scan_kernel Step E2      (rerankKernelFast, distance part)
-//   rank_kernel     Step E2 tail (bitonic3 / bitonicLarge + first-k emit)
+//   tables_warp_kernel / tables_kernel   Steps A+B+C (getKBestAssignment,
+//                       getLineAssignment, getKBestAssignment2); lut_kernel = Step B alone
+//   bins2_kernel        Steps D+E1 for p > 4 (getBins / selectBinKernelFast2,
+//                       getKVectorIDsKernelFast); bins3/bins4 live in rerank_kernels.cuh
+//   adc_warp_step & co  the ADC arithmetic of Step E2 (rerankKernelFast), shared by
+//                       every scan kernel; adc_scan_kernel = stand-alone scan for
+//                       shapes whose fused/streaming variants do not fit
 //
 // Citations are file:line into /root/reference/pqt/PerturbationProTree.cu unless
 // another file is named.  Semantics follow SURVEY.md App. B and are checked
@@ -281,111 +282,7 @@ __device__ __forceinline__ uint32_t block_exscan(uint32_t v, uint32_t* warp_sums
   return wbase + inc - v;
 }
 
-// ============================================================================
-// Steps D + E1: one CTA (256 threads) per query.
-// ============================================================================
-struct BinsArgs {
-  const uint32_t* idx16;     // [QN][p][16]
-  const uint32_t* dist_seq;  // [65536] traversal codes (prepareDistSequence)
-  BinDir dir;
-  FastMod hash;
-  uint32_t QN, p, m, c1c2;
-  uint32_t max_bins, max_trials, bin_threads, max_vec_per_bin, max_vec;
-  uint32_t* cand_pos;  // [QN][max_vec] positions in the bin-ordered code array
-  uint32_t* n_vec;     // [QN]
-  uint32_t* dbg_bins;  // [QN][max_bins] or null
-  uint32_t* dbg_nbins; // [QN] or null
-};
-
 constexpr int kBinsThreads = 256;
-
-// dynamic smem: list[max_bins] | idx[p*16] | warp_sums[32]
-__global__ void __launch_bounds__(kBinsThreads) bins_kernel(BinsArgs a) {
-  extern __shared__ uint32_t smem_u[];
-  uint32_t* list = smem_u;
-  uint32_t* sidx = list + a.max_bins;
-  uint32_t* warp_sums = sidx + a.p * 16;
-
-  // probes per thread and trial, consecutive in traversal order
-  const uint32_t ppt = (a.bin_threads + kBinsThreads - 1) / kBinsThreads;
-  uint32_t denom[8];
-  denom[0] = 1;
-#pragma unroll
-  for (int j = 1; j < 8; j++) denom[j] = denom[j - 1] * a.m;
-
-  for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
-    __syncthreads();
-    for (uint32_t e = threadIdx.x; e < a.p * 16; e += blockDim.x)
-      sidx[e] = a.idx16[(size_t)qi * a.p * 16 + e];
-    if (threadIdx.x == 0) list[0] = 0;  // slot 0 keeps the memset value (:3561)
-    __syncthreads();
-
-    // ---- Step D (:3462-3537)
-    uint32_t n_out = 0;
-    for (uint32_t it = 0; it < a.max_trials && n_out < a.max_bins; it++) {
-      uint32_t keep_mask = 0;
-      uint32_t my_bins[16];
-#pragma unroll 4
-      for (uint32_t r = 0; r < ppt && r < 16; r++) {
-        uint32_t t = threadIdx.x * ppt + r;
-        uint32_t bin = 0;
-        bool keep = false;
-        if (t < a.bin_threads) {
-          uint32_t s = __ldg(a.dist_seq + it * a.bin_threads + t);
-          uint32_t o = 0;
-          for (uint32_t j = 0; j < a.p; j++) {
-            uint32_t bp = (s / denom[j]) % a.m;
-            o = o * a.c1c2 + sidx[j * 16 + bp];  // uint32 wrap (:3487)
-          }
-          bin = fastmod(o, a.hash);
-          keep = dir_occupied(a.dir, bin);
-        }
-        my_bins[r] = bin;
-        keep_mask |= (keep ? 1u : 0u) << r;
-      }
-      uint32_t total;
-      uint32_t base = block_exscan(__popc(keep_mask), warp_sums, total);
-      // inclusive-scan position + nOutBins: 1-based (:3504-3510)
-      uint32_t pos = n_out + base;
-#pragma unroll 4
-      for (uint32_t r = 0; r < ppt && r < 16; r++) {
-        if ((keep_mask >> r) & 1u) {
-          pos++;
-          if (pos < a.max_bins) list[pos] = my_bins[r];
-        }
-      }
-      n_out += total;
-    }
-    __syncthreads();
-    const uint32_t nb = n_out < a.max_bins ? n_out : a.max_bins;
-    if (a.dbg_bins) {
-      for (uint32_t e = threadIdx.x; e < a.max_bins; e += blockDim.x)
-        a.dbg_bins[(size_t)qi * a.max_bins + e] =
-            (e == 0) ? 0u : ((e <= n_out && e < a.max_bins) ? list[e] : 0u);
-      if (threadIdx.x == 0) a.dbg_nbins[qi] = nb;
-    }
-
-    // ---- Step E1 (:4339-4417): concatenate min(count, max_vec_per_bin) vectors
-    // of every listed bin, truncated at max_vec
-    uint32_t offset = 0;
-    uint32_t* cand = a.cand_pos + (size_t)qi * a.max_vec;
-    for (uint32_t b0 = 0; b0 < nb && offset < a.max_vec; b0 += blockDim.x) {
-      uint32_t b = b0 + threadIdx.x;
-      uint32_t start = 0, nv = 0;
-      if (b < nb) {
-        uint32_t cnt;
-        dir_lookup(a.dir, list[b], start, cnt);
-        nv = cnt < a.max_vec_per_bin ? cnt : a.max_vec_per_bin;
-      }
-      uint32_t total;
-      uint32_t pos = offset + block_exscan(nv, warp_sums, total);
-      if (pos + nv > a.max_vec) nv = (pos >= a.max_vec) ? 0 : (a.max_vec - pos);
-      for (uint32_t v = 0; v < nv; v++) cand[pos + v] = start + v;
-      offset += total;
-    }
-    if (threadIdx.x == 0) a.n_vec[qi] = offset < a.max_vec ? offset : a.max_vec;
-  }
-}
 
 // ============================================================================
 // Step E2, distance part: the ADC scan over line codes (:5277-5329).
@@ -646,237 +543,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) adc_scan_kernel(ScanArgs a) {
     }
     __syncthreads();  // everyone is done with s_lut[buf] before it is refilled
     buf ^= 1;
-  }
-}
-
-// ============================================================================
-// Peer-store variant of the ADC scan (multi-GPU): per query the CTA first compacts the
-// candidates that live in THIS shard's slice into a dense list in shared memory, then
-// evaluates the list 32 candidates per warp step (same lane mapping and arithmetic as
-// above) and stores each result into the candidate arrays of the rank that owns the
-// query -- peer memory mapped over NVLink (or local memory for the own queries).  The
-// work of a shard is therefore proportional to its own candidates, and the all-to-all of
-// results happens inside the scan kernel's epilogue instead of in a separate collective.
-// ============================================================================
-constexpr int kP2PGroups = 2;  // thread groups per CTA, each walking its own queries
-constexpr int kP2PGroupThreads = kScanThreads / kP2PGroups;
-
-__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-template <int LP>
-__global__ void __launch_bounds__(kScanThreads, 1) adc_scan_p2p_kernel(ScanArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const uint32_t lut_floats = a.c1 * 32;
-  const uint32_t cbd_floats = a.c1 * a.c1 * 32;
-  const uint32_t grp = threadIdx.x / kP2PGroupThreads;
-  const uint32_t gt = threadIdx.x - grp * kP2PGroupThreads;  // thread inside the group
-  const uint32_t gbar_id = 1 + grp;
-  float* s_cbd = reinterpret_cast<float*>(smem_raw);
-  float* s_luts = s_cbd + cbd_floats;                                  // [groups][2][lut_floats]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_luts + kP2PGroups * 2 * lut_floats);
-  uint32_t* s_cnts = reinterpret_cast<uint32_t*>(bars + 2 * kP2PGroups + 2);
-  uint32_t* s_lists = s_cnts + 4;                                      // [groups][2][max_vec]
-  float* s_lut0 = s_luts + grp * 2 * lut_floats;
-  float* s_lut1 = s_lut0 + lut_floats;
-  uint64_t* gbar = bars + 2 * grp;
-  uint64_t* cbar = bars + 2 * kP2PGroups;
-  uint32_t* s_cnt = s_cnts + grp;
-  uint32_t* s_lpos = s_lists + (size_t)grp * 2 * a.max_vec;  // position inside this shard's slice
-  uint32_t* s_ca = s_lpos + a.max_vec;                       // candidate slot
-
-  const uint32_t lane = gt & 31, warp = gt >> 5, nwarps = kP2PGroupThreads >> 5;
-  const uint32_t lp = lane & (LP - 1);
-  const uint32_t grp_base = lane & ~(uint32_t)(LP - 1);
-  const uint32_t worker = blockIdx.x * kP2PGroups + grp;
-  const uint32_t nworkers = gridDim.x * kP2PGroups;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 2 * kP2PGroups + 1; i++) mbar_init(&bars[i], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const uint32_t cbd_bytes = cbd_floats * 4;
-    mbar_expect_tx(cbar, cbd_bytes);
-    for (uint32_t off = 0; off < cbd_bytes; off += 32768) {
-      uint32_t n = cbd_bytes - off < 32768 ? cbd_bytes - off : 32768;
-      tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_cbd) + off,
-                   reinterpret_cast<const unsigned char*>(a.cbd_dup) + off, n, cbar);
-    }
-  }
-  if (gt == 0 && worker < a.QN) {
-    mbar_expect_tx(&gbar[0], lut_floats * 4);
-    tma_bulk_g2s(s_lut0, a.lut_dup + (size_t)worker * lut_floats, lut_floats * 4, &gbar[0]);
-  }
-  mbar_wait(cbar, 0);
-
-  uint32_t buf = 0, phase0 = 0, phase1 = 0;
-  for (uint32_t qi = worker; qi < a.QN; qi += nworkers) {
-    const uint32_t qn = qi + nworkers;
-    if (gt == 0) {
-      *s_cnt = 0;
-      if (qn < a.QN) {
-        uint64_t* nb = &gbar[buf ^ 1];
-        mbar_expect_tx(nb, lut_floats * 4);
-        tma_bulk_g2s(buf ? s_lut0 : s_lut1, a.lut_dup + (size_t)qn * lut_floats, lut_floats * 4, nb);
-      }
-    }
-    named_bar_sync(gbar_id, kP2PGroupThreads);
-    const uint32_t nv = min(__ldg(a.n_vec + qi), a.max_vec);
-    const uint32_t* cand = a.cand_pos + (size_t)qi * a.max_vec;
-    // ---- phase 1: compact the candidates of this shard's slice
-    for (uint32_t base = warp * 32; base < nv; base += nwarps * 32) {
-      const uint32_t ca = base + lane;
-      uint32_t pos = 0;
-      bool mine = false;
-      if (ca < nv) {
-        pos = __ldg(cand + ca);
-        mine = (pos >= a.pos_lo) && (pos < a.pos_hi);
-      }
-      const uint32_t mask = __ballot_sync(0xffffffffu, mine);
-      if (mask) {
-        uint32_t off = 0;
-        if (lane == 0) off = atomicAdd(s_cnt, __popc(mask));
-        off = __shfl_sync(0xffffffffu, off, 0) + __popc(mask & ((1u << lane) - 1u));
-        if (mine) {
-          s_lpos[off] = pos - a.pos_lo;
-          s_ca[off] = ca;
-        }
-      }
-    }
-    named_bar_sync(gbar_id, kP2PGroupThreads);
-    const uint32_t M = *s_cnt;
-    const float* s_lut = buf ? s_lut1 : s_lut0;
-    mbar_wait(&gbar[buf], buf ? phase1 : phase0);
-    if (buf)
-      phase1 ^= 1;
-    else
-      phase0 ^= 1;
-    const uint32_t owner = qi / a.q_per_rank, ql = qi - owner * a.q_per_rank;
-    float* oval = a.peer_val[owner] + (size_t)ql * a.max_vec;
-    uint32_t* oidx = a.peer_idx[owner] + (size_t)ql * a.max_vec;
-    // ---- phase 2: dense chunks of 32 own candidates
-    for (uint32_t base = warp * 32; base < M; base += nwarps * 32) {
-      const uint32_t e = base + lane;
-      const bool valid = e < M;
-      const uint32_t lpos = valid ? s_lpos[e] : 0u;
-      const uint32_t ca = valid ? s_ca[e] : 0u;
-      const uint32_t myid = valid ? __ldg(a.ids + lpos) : 0u;
-      const float myval = adc_warp_step<LP, 32u>(lpos, a.codes + lp, smem_u32(s_lut) + lane * 4u,
-                                                 smem_u32(s_cbd) + lane * 4u, a.c1, lp);
-      if (valid) {
-        oval[ca] = myval;  // peer store (NVLink) when the query is ranked by another GPU
-        oidx[ca] = myid;
-      }
-    }
-    named_bar_sync(gbar_id, kP2PGroupThreads);  // list and LUT buffer are reused by the next query
-    buf ^= 1;
-  }
-}
-
-// Fallback for shapes whose cbd table does not fit in shared memory (c1 > 32):
-// same arithmetic, tables read through L1/L2 in their canonical layouts.
-struct ScanGenericArgs {
-  ScanArgs s;
-  const float* lut;  // [QN][LP][c1] canonical
-  const float* cbd;  // [c1][c1][LP] canonical
-  uint32_t LP;
-};
-
-__global__ void __launch_bounds__(256) adc_scan_generic_kernel(ScanGenericArgs g) {
-  const ScanArgs& a = g.s;
-  const uint32_t LP = g.LP;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const uint32_t lp = lane & (LP - 1);
-  const uint32_t grp_base = lane & ~(LP - 1);
-  for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
-    const float* lut = g.lut + (size_t)qi * LP * a.c1;
-    const uint32_t nv = min(__ldg(a.n_vec + qi), a.max_vec);
-    const uint32_t* cand = a.cand_pos + (size_t)qi * a.max_vec;
-    for (uint32_t base = warp * 32; base < a.max_vec; base += nwarps * 32) {
-      const uint32_t ca = base + lane;
-      const bool valid = ca < nv;
-      uint32_t pos = 0;
-      bool mine = false;
-      if (valid) {
-        pos = __ldg(cand + ca);
-        mine = (pos >= a.pos_lo) && (pos < a.pos_hi);
-      }
-      const uint32_t lpos = pos - a.pos_lo;
-      float myval = 0.f;
-      uint32_t myid = 0;
-      const uint32_t any_mine = __ballot_sync(0xffffffffu, mine);
-      if (any_mine) {
-        if (mine) myid = __ldg(a.ids + lpos);
-        for (uint32_t s = 0; s < LP; s++) {
-          const uint32_t src = grp_base + s;
-          const uint32_t cpos = __shfl_sync(0xffffffffu, lpos, src);
-          const bool cm = (any_mine >> src) & 1u;
-          float d = 0.f;
-          if (cm) {
-            uint32_t w = __ldg(a.codes + (size_t)cpos * LP + lp);
-            const uint32_t p1 = w & 0xFFu, p2 = (w >> 8) & 0xFFu;
-            const float lam = lambda_of(w);
-            d = tri_dist(__ldg(lut + lp * a.c1 + p1), __ldg(lut + lp * a.c1 + p2),
-                         __ldg(g.cbd + ((size_t)p2 * a.c1 + p1) * LP + lp), lam);
-          }
-          for (uint32_t st = LP >> 1; st > 0; st >>= 1)
-            d = __fadd_rn(d, __shfl_xor_sync(0xffffffffu, d, st));
-          if (lp == s) myval = d;
-        }
-      }
-      float v;
-      uint32_t id;
-      if (mine) {
-        v = myval;
-        id = myid;
-      } else if (valid || !a.owns_pad) {
-        v = __int_as_float(0x7f800000);
-        id = kNotMineIdx;
-      } else {
-        v = kPadDist;
-        id = kPadIdx;
-      }
-      if (ca < a.max_vec) {
-        a.out_val[(size_t)qi * a.max_vec + ca] = v;
-        a.out_idx[(size_t)qi * a.max_vec + ca] = id;
-      }
-    }
-  }
-}
-
-// ============================================================================
-// Step E2 tail: exact bitonic network over max_vec (val, idx) pairs and emit of
-// the first k (:5337-5346).  One CTA per query, network in shared memory.
-// ============================================================================
-struct RankArgs {
-  const float* val;     // [QN][max_vec]
-  const uint32_t* idx;  // [QN][max_vec]
-  uint32_t QN, max_vec, k;
-  float* out_dist;    // [QN][k]
-  uint32_t* out_idx;  // [QN][k]
-};
-
-constexpr int kRankThreads = 1024;
-
-__global__ void __launch_bounds__(kRankThreads) rank_kernel(RankArgs a) {
-  extern __shared__ float smem_f[];
-  float* sval = smem_f;
-  uint32_t* sidx = reinterpret_cast<uint32_t*>(sval + a.max_vec);
-  for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
-    __syncthreads();
-    for (uint32_t e = threadIdx.x; e < a.max_vec; e += blockDim.x) {
-      sval[e] = a.val[(size_t)qi * a.max_vec + e];
-      sidx[e] = a.idx[(size_t)qi * a.max_vec + e];
-    }
-    __syncthreads();
-    bitonic_smem(sval, sidx, a.max_vec, 1);
-    for (uint32_t e = threadIdx.x; e < a.k; e += blockDim.x) {
-      a.out_dist[(size_t)qi * a.k + e] = sval[e];
-      a.out_idx[(size_t)qi * a.k + e] = sidx[e];
-    }
   }
 }
 

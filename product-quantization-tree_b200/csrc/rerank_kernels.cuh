@@ -1325,9 +1325,16 @@ struct Rank2Args {
   const uint16_t* ridx;   // optional [QN][max_vec]: the distance of candidate slot a is
                           // val[q][ridx[q][a]] (the scan evaluated repeated candidates once)
   uint32_t fast_rank;     // 1: composite-key sort first; 0: the network only
+  uint32_t bucket_sort;   // 1: counting sort of the composite words (needs the counter array of
+                          // rank2_smem_bytes(max_vec, true)); 0: bitonic sort of the words
+  unsigned long long* phase_dbg;  // optional [QN][8] clock64 stamps (layout of rerank_kernel's;
+                                  // slot 1 = end of the sort proper instead of the LUT wait)
 };
 
-inline size_t rank2_smem_bytes(uint32_t max_vec) { return (size_t)max_vec * 8 + 512 + 64; }
+// val | sort words | repair bitmap | misc | bucket counters (counting sort, lists >= 1024)
+inline size_t rank2_smem_bytes(uint32_t max_vec, bool bucket = true) {
+  return (size_t)max_vec * 8 + 512 + 64 + (bucket && max_vec >= 1024 ? (size_t)max_vec * 4 : 0);
+}
 constexpr int kRank2Threads = 256;  // one query per CTA, 4 CTAs per SM
 
 template <bool DIRECT>
@@ -1342,17 +1349,24 @@ __global__ void __launch_bounds__(kRank2Threads, 4) rank2_kernel(Rank2Args a) {
   uint32_t* s_min = s_misc + 2;
   uint32_t* s_max = s_misc + 3;
   uint32_t* s_bad = s_misc + 4;
+  uint32_t* s_tot = s_misc + 5;                                      // [10] counting-sort scratch
+  uint32_t* s_hist = (a.bucket_sort && a.max_vec >= 1024u) ? s_misc + 16 : nullptr;  // [max_vec]
   uint16_t* s_pay = reinterpret_cast<uint16_t*>(s_cmp);
   const Grp G{threadIdx.x, blockDim.x, 0};
   const uint32_t lane = threadIdx.x & 31u;
   for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
     __syncthreads();
+    unsigned long long* ph = a.phase_dbg ? a.phase_dbg + (size_t)qi * 8 : nullptr;
     if (threadIdx.x == 0) {
       *s_flag = 0;
       *s_nv = 0;
       *s_min = 0xFFFFFFFFu;
       *s_max = 0u;
       *s_bad = 0u;
+      if (ph) {
+        ph[0] = clock64();
+        ph[1] = ph[3] = ph[4] = ph[5] = 0;
+      }
     }
     if (threadIdx.x < 128u) s_fix[threadIdx.x] = 0u;
     __syncthreads();
@@ -1386,6 +1400,7 @@ __global__ void __launch_bounds__(kRank2Threads, 4) rank2_kernel(Rank2Args a) {
     }
     __syncthreads();
     const uint32_t nv = a.n_vec ? limit : *s_nv;
+    if (ph && threadIdx.x == 0) ph[2] = clock64();
     float* od = a.out_dist + (size_t)qi * a.k;
     uint32_t* oi = a.out_idx + (size_t)qi * a.k;
     const uint32_t* cand = DIRECT ? nullptr : idx_row;
@@ -1396,15 +1411,21 @@ __global__ void __launch_bounds__(kRank2Threads, 4) rank2_kernel(Rank2Args a) {
     if (a.fast_rank && n2 >= kFastMinN2 && *s_bad == 0u) {
       FastRankState st{*s_min, *s_max};
       uint32_t f = fast_rank_emit<DIRECT>(G, 1, s_val, s_cmp, s_fix, s_flag, nv, n2, a.k, st, od, oi, cand, ids,
-                                          nullptr);
+                                          ph, s_hist, s_tot);
+      if (ph && threadIdx.x == 0) ph[3] = clock64();
       if (f == 1u && a.k >= nv && tie_resolve<DIRECT>(G, s_val, s_cmp, s_flag, nv, a.max_vec, od, oi, cand, ids)) {
         f = 0u;
         if (threadIdx.x == 0 && a.tie_counter) atomicAdd(a.tie_counter, 1ull);
       }
       done = (f == 0u);
+      if (ph && threadIdx.x == 0) ph[5] = clock64();
     }
     if (!done)
       rank_and_emit(G, s_val, s_pay, id_of, s_flag, nv, a.max_vec, a.k, od, oi, a.exact_counter);
+    if (ph && threadIdx.x == 0) {
+      ph[6] = clock64();
+      ph[7] = ((unsigned long long)blockIdx.x << 32) | (nv << 1) | (done ? 1u : 0u) | (1ull << 63);
+    }
   }
 }
 

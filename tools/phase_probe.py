@@ -32,11 +32,23 @@ def main():
     torch.cuda.synchronize()
     ph = t.stage("rerank_phases", (a.qn, 8), np.uint64).astype(np.int64)
     t.debug(False)
+    split = bool((ph[:, 7] < 0).any())  # bit 63: stamps of the ranking-only kernel (split pipeline)
+    ph[:, 7] &= (1 << 63) - 1
     nv = (ph[:, 7] & 0xFFFFFFFF) >> 1
     fast = ph[:, 7] & 1
     sm = ph[:, 7] >> 32
     names = ["lut_wait", "scan", "sort+emit", "repair", "ties", "network/tail"]
-    d = np.stack([ph[:, 1] - ph[:, 0], ph[:, 2] - ph[:, 1],
+    if split:
+        # rank2_kernel: slot 1 = end of the sort proper; phases: load, sort, emit, repair, ties, tail
+        names = ["load", "sort", "emit", "repair", "ties", "network/tail"]
+        s1 = np.where(ph[:, 1] > 0, ph[:, 1], ph[:, 2])
+        d = np.stack([ph[:, 2] - ph[:, 0], s1 - ph[:, 2],
+                      np.where(ph[:, 4] > 0, ph[:, 4] - s1, 0),
+                      np.where(ph[:, 3] > 0, ph[:, 3] - ph[:, 4], 0),
+                      np.where(ph[:, 5] > 0, ph[:, 5] - ph[:, 3], 0),
+                      ph[:, 6] - np.where(ph[:, 5] > 0, ph[:, 5], ph[:, 2])], 1)
+    else:
+      d = np.stack([ph[:, 1] - ph[:, 0], ph[:, 2] - ph[:, 1],
                   np.where(ph[:, 4] > 0, ph[:, 4] - ph[:, 2], 0),
                   np.where(ph[:, 3] > 0, ph[:, 3] - ph[:, 4], 0),
                   np.where(ph[:, 5] > 0, ph[:, 5] - ph[:, 3], 0),
