@@ -112,117 +112,6 @@ __device__ __forceinline__ void block_sort_u32(uint32_t (&c)[E], uint32_t t, uin
   }
 }
 
-// ----------------------------------------------------------------------------
-// Counting sort of one query's composite words (ranking-only kernel).  The key bits of a
-// word are an affine image of the distance over [min, max] of the query, so the top
-// sb = log2(n2) bits spread the nv words over n2 buckets of a few words each: O(n) shared-
-// memory traffic instead of the O(n log^2 n) compare-exchanges of the bitonic sort, and six
-// barriers instead of one or two per cross-warp step.
-//   1. count: atomicAdd on the bucket's counter (the returned arrival number is kept)
-//   2. exclusive scan of the n2 counters (E per thread, warp shuffles, 8 warp totals)
-//   3. scatter to start[bucket] + arrival
-//   4. order inside a bucket: rank = number of smaller words of the bucket (the words are
-//      distinct, so the result does not depend on the arrival order), re-stored in place
-// Called by all g.n threads, g.n * E == n2, g.n <= 256.  Result: s_cmp[0 .. nv) ascending.
-// Returns false (to every thread; s_cmp undefined) when a bucket holds more than
-// kBucketMaxCount words -- a distribution the caller sorts with the network instead.
-// s_hist: n2 words, s_tot: 10 words of scratch.
-constexpr uint32_t kBucketMaxCount = 64;
-
-template <int E>
-__device__ __forceinline__ bool bucket_sort_u32(const Grp& g, const float* s_val, uint32_t* s_cmp,
-                                                uint32_t* s_hist, uint32_t* s_tot, uint32_t nv,
-                                                uint32_t n2, uint32_t umin, uint32_t shift, uint32_t sb) {
-  static_assert(E % 4 == 0, "counters are scanned four at a time");
-  const uint32_t t = g.t, gn = g.n;
-  const uint32_t bsh = 32u - sb;
-#pragma unroll
-  for (int r = 0; r < E; r++) s_hist[t + r * gn] = 0u;
-  if (t == 0) s_tot[8] = 0u;
-  g.sync();
-  uint32_t w[E];
-  uint32_t arr[E / 4];  // arrival numbers, one byte each
-#pragma unroll
-  for (int r = 0; r < E / 4; r++) arr[r] = 0u;
-#pragma unroll
-  for (int r = 0; r < E; r++) {
-    const uint32_t e = t + r * gn;
-    w[r] = 0xFFFFFFFFu;
-    if (e < nv) {
-      w[r] = (((sortable_key(s_val[e]) - umin) >> shift) << sb) | e;
-      const uint32_t a = atomicAdd(&s_hist[w[r] >> bsh], 1u);
-      arr[r >> 2] |= min(a, 255u) << ((r & 3) * 8);
-    }
-  }
-  g.sync();
-  // exclusive scan: thread t owns counters t*E .. t*E+E-1
-  {
-    uint32_t c[E];
-    uint4* hv = reinterpret_cast<uint4*>(s_hist + t * E);
-#pragma unroll
-    for (int q = 0; q < E / 4; q++) {
-      const uint4 v = hv[q];
-      c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
-    }
-    uint32_t sum = 0, mx = 0;
-#pragma unroll
-    for (int i = 0; i < E; i++) {
-      const uint32_t ci = c[i];
-      mx = max(mx, ci);
-      c[i] = sum;
-      sum += ci;
-    }
-    uint32_t incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-      if ((t & 31u) >= (uint32_t)o) incl += n;
-    }
-    mx = __reduce_max_sync(0xffffffffu, mx);
-    if ((t & 31u) == 31u) s_tot[t >> 5] = incl;
-    if ((t & 31u) == 0u && mx > kBucketMaxCount) atomicMax(&s_tot[8], mx);
-    g.sync();
-    uint32_t base = incl - sum;
-    for (uint32_t wq = 0; wq < (t >> 5); wq++) base += s_tot[wq];
-#pragma unroll
-    for (int q = 0; q < E / 4; q++)
-      hv[q] = make_uint4(base + c[4 * q], base + c[4 * q + 1], base + c[4 * q + 2], base + c[4 * q + 3]);
-  }
-  g.sync();
-  if (s_tot[8] != 0u) return false;
-  // scatter; meta = first slot of the bucket | members << 16
-  uint32_t meta[E];
-#pragma unroll
-  for (int r = 0; r < E; r++) {
-    meta[r] = 0u;
-    if (t + r * gn < nv) {
-      const uint32_t b = w[r] >> bsh;
-      const uint32_t s0 = s_hist[b];
-      const uint32_t s1 = (b + 1u < n2) ? s_hist[b + 1u] : nv;
-      s_cmp[s0 + ((arr[r >> 2] >> ((r & 3) * 8)) & 255u)] = w[r];
-      meta[r] = s0 | ((s1 - s0) << 16);
-    }
-  }
-  g.sync();
-  // rank inside the buckets that hold more than one word
-#pragma unroll
-  for (int r = 0; r < E; r++) {
-    const uint32_t cnt = meta[r] >> 16;
-    if (cnt > 1u) {
-      const uint32_t s0 = meta[r] & 0xFFFFu;
-      uint32_t rank = 0;
-      for (uint32_t j = 0; j < cnt; j++) rank += (s_cmp[s0 + j] < w[r]) ? 1u : 0u;
-      meta[r] = (s0 + rank) | (cnt << 16);
-    }
-  }
-  g.sync();
-#pragma unroll
-  for (int r = 0; r < E; r++)
-    if ((meta[r] >> 16) > 1u) s_cmp[meta[r] & 0xFFFFu] = w[r];
-  g.sync();
-  return true;
-}
-
 // Where a candidate slot's vector identity and id come from.  Fused single-GPU kernel:
 // slot -> bin-order position (cand) -> id (ids).  DIRECT (candidates assembled from shards):
 // ids[slot] is the id itself and doubles as the identity.
@@ -257,45 +146,25 @@ __device__ __forceinline__ uint32_t fast_sort_emit(uint32_t t, uint32_t gn, uint
                                                    uint32_t sb, float* out_dist, uint32_t* out_idx,
                                                    const uint32_t* __restrict__ cand,
                                                    const uint32_t* __restrict__ ids,
-                                                   unsigned long long* ph = nullptr,
-                                                   uint32_t* s_hist = nullptr, uint32_t* s_tot = nullptr,
-                                                   uint32_t grp_bar = 0) {
+                                                   unsigned long long* ph = nullptr) {
   constexpr int CH = E < 8 ? E : 8;  // slots handled together (loads of a level issued together)
   const uint32_t T = n2 / E;
   const uint32_t Ta = min(T, ((nv + E - 1u) / E + 31u) & ~31u);  // sorter threads
   const uint32_t smask = n2 - 1u;
   uint32_t flag = 0;
-  // ranking-only kernel (one group = n2 / E threads, counter array provided): counting sort by
-  // all threads of the group; the network below only for distributions it declines
-  bool sorted = false;
-  if (s_hist != nullptr && gn * E == n2)
-    sorted = bucket_sort_u32<E>(Grp{t, gn, grp_bar}, s_val, s_cmp, s_hist, s_tot, nv, n2, umin, shift, sb);
   if (t < Ta) {
     uint32_t c[E];
-    if (sorted) {
-      const uint4* sv = reinterpret_cast<const uint4*>(s_cmp + t * E);
 #pragma unroll
-      for (int q = 0; q < E / 4; q++) {
-        const uint4 v = sv[q];
-        c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
-      }
-#pragma unroll
-      for (int r = 0; r < E; r++)
-        if (t * E + r >= nv) c[r] = 0xFFFFFFFFu;
-      if (ph && t == 0) ph[1] = clock64();
-    } else {
-#pragma unroll
-      for (int r = 0; r < E; r++) {
-        const uint32_t e = t * E + r;
-        c[r] = e < nv ? ((((sortable_key(s_val[e]) - umin) >> shift) << sb) | e) : 0xFFFFFFFFu;
-      }
-      block_sort_u32<E>(c, t, T, Ta, s_cmp, sub_bar);
-      if (ph && t == 0) ph[1] = clock64();  // ranking-only kernels: end of the sort proper
-      // publish: neighbours' edge slots and the repair windows read s_cmp
-#pragma unroll
-      for (int r = 0; r < E; r++) s_cmp[t * E + r] = c[r];
-      asm volatile("bar.sync %0, %1;" ::"r"(sub_bar), "r"(Ta) : "memory");
+    for (int r = 0; r < E; r++) {
+      const uint32_t e = t * E + r;
+      c[r] = e < nv ? ((((sortable_key(s_val[e]) - umin) >> shift) << sb) | e) : 0xFFFFFFFFu;
     }
+    block_sort_u32<E>(c, t, T, Ta, s_cmp, sub_bar);
+    if (ph && t == 0) ph[1] = clock64();  // ranking-only kernels: end of the sort proper
+    // publish: neighbours' edge slots and the repair windows read s_cmp
+#pragma unroll
+    for (int r = 0; r < E; r++) s_cmp[t * E + r] = c[r];
+    asm volatile("bar.sync %0, %1;" ::"r"(sub_bar), "r"(Ta) : "memory");
     // left neighbour of the thread's first slot
     uint32_t c_prev = t > 0u ? s_cmp[t * E - 1u] : 0xFFFFFFFFu;
     float v_prev = 0.f;
@@ -405,8 +274,7 @@ __device__ __forceinline__ uint32_t fast_rank_emit(const Grp& g, uint32_t sub_ba
                                                    FastRankState st, float* out_dist,
                                                    uint32_t* out_idx, const uint32_t* __restrict__ cand,
                                                    const uint32_t* __restrict__ ids,
-                                                   unsigned long long* ph, uint32_t* s_hist = nullptr,
-                                                   uint32_t* s_bkt = nullptr) {
+                                                   unsigned long long* ph) {
   const uint32_t t = g.t;
   const uint32_t range = st.umax - st.umin;
   // composite word = key << sb | slot: sb = log2(n2) slot bits, the other 32 - sb bits hold
@@ -422,14 +290,13 @@ __device__ __forceinline__ uint32_t fast_rank_emit(const Grp& g, uint32_t sub_ba
   uint32_t flag;
   if (n2 >= 4096u)
     flag = fast_sort_emit<16, DIRECT>(t, g.n, sub_bar, s_val, s_cmp, s_fix, nv, n2, k, st.umin, shift, sb,
-                                      out_dist, out_idx, cand, ids, ph && ph[1] == 0 ? ph : nullptr,
-                                      s_hist, s_bkt, g.bar);
+                                      out_dist, out_idx, cand, ids, ph && ph[1] == 0 ? ph : nullptr);
   else if (n2 >= 2048u)
     flag = fast_sort_emit<8, DIRECT>(t, g.n, sub_bar, s_val, s_cmp, s_fix, nv, n2, k, st.umin, shift, sb,
-                                     out_dist, out_idx, cand, ids, nullptr, s_hist, s_bkt, g.bar);
+                                     out_dist, out_idx, cand, ids);
   else
     flag = fast_sort_emit<4, DIRECT>(t, g.n, sub_bar, s_val, s_cmp, s_fix, nv, n2, k, st.umin, shift, sb,
-                                     out_dist, out_idx, cand, ids, nullptr, s_hist, s_bkt, g.bar);
+                                     out_dist, out_idx, cand, ids);
   if (flag) atomicOr(s_flag, flag);
   g.sync();
   if (ph && t == 0) ph[4] = clock64();

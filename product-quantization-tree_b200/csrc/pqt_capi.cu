@@ -503,13 +503,6 @@ int launch_bins_p4(pqt_index* h, const pqt_params& P, uint32_t max_vec, uint32_t
   return PQT_OK;
 }
 
-// ranking kernel: counting sort of the composite words (default) or their bitonic sort
-// (PQT_RANK_SORT=bitonic, for A/B runs)
-static bool rank_bucket_sort() {
-  static const bool on = !(getenv("PQT_RANK_SORT") && strcmp(getenv("PQT_RANK_SORT"), "bitonic") == 0);
-  return on;
-}
-
 // Steps A..E2 (distance part) for QN queries already on the device; fills
 // val/idx [QN][max_vec].  Records profile events ev[0..3] when enabled.
 // With fused_out_* set (single GPU) the scan, the ranking and the first-k emit run in one
@@ -742,12 +735,11 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
       ra.n_vec = h->s_nvec.as<uint32_t>();
       ra.ridx = h->have_roots ? h->s_ridx.as<uint16_t>() : nullptr;
       ra.fast_rank = (P.rank_mode == 0) ? 1u : 0u;
-      ra.bucket_sort = rank_bucket_sort() ? 1u : 0u;
       if (h->debug) {
         CU_TRY(h, h->g_phases.ensure((size_t)QN * 8 * 8));
         ra.phase_dbg = h->g_phases.as<unsigned long long>();
       }
-      const size_t rsmem = rank2_smem_bytes(max_vec, ra.bucket_sort != 0);
+      const size_t rsmem = rank2_smem_bytes(max_vec);
       if (rsmem > 48 * 1024)
         CU_TRY(h, cudaFuncSetAttribute(rank2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
       rank2_kernel<false><<<std::min<uint32_t>(QN, (uint32_t)h->num_sms * 4), kRank2Threads, rsmem, h->stream>>>(ra);
@@ -866,8 +858,7 @@ int run_rank(pqt_index* h, const float* d_val, const uint32_t* d_idx, uint32_t Q
   a.out_dist = d_out_dist; a.out_idx = d_out_idx;
   a.exact_counter = h->d_exact.as<unsigned long long>();
   a.fast_rank = (h->prm.rank_mode == 0) ? 1u : 0u;
-  a.bucket_sort = rank_bucket_sort() ? 1u : 0u;
-  size_t smem = rank2_smem_bytes(max_vec, a.bucket_sort != 0);
+  size_t smem = rank2_smem_bytes(max_vec);
   if (smem > 48 * 1024)
     CU_TRY(h, cudaFuncSetAttribute(rank2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 4);
@@ -1900,7 +1891,20 @@ int pqt_shard_scan_p2p(pqt_index* h, uint32_t QN, uint32_t k) {
   if (ssmem > (size_t)227 * 1024) return fail(h, PQT_ERR_INVALID, "c1 = %u > 32 is not supported by the ADC scan yet", h->c1);
   const uint32_t sgrid = std::min<uint32_t>(QN, (uint32_t)h->num_sms);
   if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-  if (h->LP == 32) {
+  static const bool warp_mode = !(getenv("PQT_INBOX_MODE") && strcmp(getenv("PQT_INBOX_MODE"), "cta") == 0);  // A/B runs
+  const size_t wsmem = inbox_scan_smem_bytes(h->c1, h->LP, h->LP == 32);
+  if (warp_mode && wsmem <= (size_t)227 * 1024) {
+    CU_TRY(h, h->d_sched.ensure(64));
+    CU_TRY(h, cudaMemsetAsync(h->d_sched.p, 0, 4, h->stream));
+    const uint32_t wgrid = std::min<uint32_t>((QN + kInboxWarps - 1) / kInboxWarps, (uint32_t)h->num_sms);
+    if (h->LP == 32) {
+      CU_TRY(h, cudaFuncSetAttribute(adc_inbox_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+      adc_inbox_kernel<32, true><<<wgrid, kInboxWarps * 32, wsmem, h->stream>>>(sa, h->d_sched.as<uint32_t>());
+    } else {
+      CU_TRY(h, cudaFuncSetAttribute(adc_inbox_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+      adc_inbox_kernel<16, false><<<wgrid, kInboxWarps * 32, wsmem, h->stream>>>(sa, h->d_sched.as<uint32_t>());
+    }
+  } else if (h->LP == 32) {
     CU_TRY(h, cudaFuncSetAttribute(adc_stream_kernel<32, true, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
     adc_stream_kernel<32, true, 512, true><<<sgrid, 512, ssmem, h->stream>>>(sa);
   } else {
@@ -1939,7 +1943,7 @@ int pqt_shard_rank(pqt_index* h, uint32_t q_own, uint32_t k, uint32_t* idx, floa
     d_out_idx = h->s_outi.as<uint32_t>();
   }
   if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
-  size_t smem = rank2_smem_bytes(max_vec, rank_bucket_sort());
+  size_t smem = rank2_smem_bytes(max_vec);
   if (smem > 48 * 1024)
     CU_TRY(h, cudaFuncSetAttribute(rank2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // host outputs: rank in slabs so that the device->host copy of one slab overlaps the
@@ -1974,8 +1978,7 @@ int pqt_shard_rank(pqt_index* h, uint32_t q_own, uint32_t k, uint32_t* idx, floa
     a.exact_counter = h->d_exact.as<unsigned long long>();
     a.tie_counter = h->d_exact.as<unsigned long long>() + 1;
     a.fast_rank = (h->prm.rank_mode == 0) ? 1u : 0u;
-    a.bucket_sort = rank_bucket_sort() ? 1u : 0u;
-    a.n_vec = h->s_nvec.as<uint32_t>() + q0;
+      a.n_vec = h->s_nvec.as<uint32_t>() + q0;
     a.ridx = h->have_roots ? h->s_ridx.as<uint16_t>() + (size_t)q0 * max_vec : nullptr;
     rank2_kernel<false><<<std::min<uint32_t>(n, (uint32_t)h->num_sms * 4), kRank2Threads, smem, h->stream>>>(a);
     CU_TRY(h, cudaGetLastError());

@@ -1260,6 +1260,113 @@ __global__ void __launch_bounds__(TPB, 1) adc_stream_kernel(StreamScanArgs a) {
 }
 
 // ============================================================================
+// Inbox scan, one WARP per query (multi-GPU).  An inbox row of an N-shard index holds about
+// max_vec / N entries: one or two steps of a 512-thread CTA, so the CTA-per-query loop above
+// spends its time in the per-query chain (LUT wait -> inbox read -> code rows -> look-ups ->
+// store) instead of streaming.  Here the 16 warps of the persistent CTA walk 16 different
+// queries, each with its own 4 KB LUT buffer (own mbarrier, refilled by the warp's lane 0) and
+// its own double-buffered code rows; queries are drawn from a global counter.  Shared memory:
+// c^2 table + 16 LUTs (128 + 64 KB at c1 = 32, LP = 32).
+// ============================================================================
+constexpr int kInboxWarps = 16;
+
+inline size_t inbox_scan_smem_bytes(uint32_t c1, uint32_t LP, bool crep) {
+  return ((size_t)c1 * c1 * (crep ? 32 : LP) + (size_t)kInboxWarps * c1 * 32) * 4 + (kInboxWarps + 1) * 8 + 64;
+}
+
+template <int LP, bool CREP>
+__global__ void __launch_bounds__(kInboxWarps * 32, 1) adc_inbox_kernel(StreamScanArgs a, uint32_t* next_query) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr uint32_t CROW = CREP ? 32u : (uint32_t)LP;
+  const uint32_t lut_floats = a.c1 * 32;
+  const uint32_t cbd_floats = a.c1 * a.c1 * CROW;
+  float* s_cbd = reinterpret_cast<float*>(smem_raw);
+  float* s_luts = s_cbd + cbd_floats;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_luts + (size_t)kInboxWarps * lut_floats);  // [w]: LUT of warp w, [16]: cbd
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lp = lane & (LP - 1);
+  const uint32_t cbd_b = smem_u32(s_cbd) + (CREP ? lane : lp) * 4u;
+  const uint32_t* __restrict__ codes_lp = a.codes + lp;
+  float* s_lut = s_luts + (size_t)warp * lut_floats;
+  const uint32_t lut_b = smem_u32(s_lut) + lane * 4u;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i <= kInboxWarps; i++) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t cbd_bytes = cbd_floats * 4;
+    mbar_expect_tx(&bars[kInboxWarps], cbd_bytes);
+    for (uint32_t off = 0; off < cbd_bytes; off += 32768) {
+      uint32_t n = cbd_bytes - off < 32768 ? cbd_bytes - off : 32768;
+      tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_cbd) + off,
+                   reinterpret_cast<const unsigned char*>(a.cbd) + off, n, &bars[kInboxWarps]);
+    }
+  }
+  uint32_t phase = 0;
+  bool cbd_ready = false;
+  for (;;) {
+    uint32_t qi = 0;
+    if (lane == 0) qi = atomicAdd(next_query, 1u);
+    qi = __shfl_sync(0xffffffffu, qi, 0);
+    if (qi >= a.QN) break;
+    const uint32_t nv = min(__ldg(a.n_vec + qi), a.max_vec);
+    if (nv == 0u) continue;  // nothing of this query lives in this shard
+    if (lane == 0) {  // the warp's previous reads of its LUT ended with the __syncwarp below
+      mbar_expect_tx(&bars[warp], lut_floats * 4);
+      tma_bulk_g2s(s_lut, a.lut_dup + (size_t)qi * lut_floats, lut_floats * 4, &bars[warp]);
+    }
+    const uint2* inbox = a.inbox + (size_t)qi * a.max_vec;
+    const uint32_t owner = qi / a.q_per_rank;
+    float* out = a.peer_val[owner] + (size_t)(qi - owner * a.q_per_rank) * a.max_vec;
+    auto fetch = [&](uint32_t e, uint32_t& pos, uint32_t& slot) {
+      pos = 0u;
+      slot = 0u;
+      if (e < nv) {
+        const uint2 en = __ldg(inbox + e);
+        pos = en.x;
+        slot = en.y;
+      }
+    };
+    uint32_t e0 = lane;
+    uint32_t pos0, pos1, slot0, slot1;
+    fetch(e0, pos0, slot0);
+    fetch(e0 + 32u, pos1, slot1);
+    uint32_t wA[LP], wB[LP];
+    adc_load_rows<LP, false>(wA, pos0, codes_lp, lp, nullptr);
+    if (!cbd_ready) {
+      mbar_wait(&bars[kInboxWarps], 0);
+      cbd_ready = true;
+    }
+    mbar_wait(&bars[warp], phase);
+    phase ^= 1u;
+    for (uint32_t base = 0; base < nv; base += 64u) {
+      const bool has1 = base + 32u < nv, has2 = base + 64u < nv;
+      if (has1) adc_load_rows<LP, false>(wB, pos1, codes_lp, lp, nullptr);
+      uint32_t pos2, slot2;
+      fetch(e0 + 64u, pos2, slot2);
+      {
+        const float v = adc_eval_rows<LP, CROW>(wA, lut_b, cbd_b, a.c1, lp);
+        if (e0 < nv) out[slot0] = v;
+      }
+      if (!has1) break;
+      if (has2) adc_load_rows<LP, false>(wA, pos2, codes_lp, lp, nullptr);
+      uint32_t pos3, slot3;
+      fetch(e0 + 96u, pos3, slot3);
+      {
+        const float v = adc_eval_rows<LP, CROW>(wB, lut_b, cbd_b, a.c1, lp);
+        if (e0 + 32u < nv) out[slot1] = v;
+      }
+      e0 += 64u;
+      slot0 = slot2;
+      pos1 = pos3;
+      slot1 = slot3;
+    }
+    __syncwarp();  // every lane is done with the LUT before lane 0 refills it
+  }
+}
+
+// ============================================================================
 // Multi-GPU dispatch: the owner of a query sends every shard the candidates that live in that
 // shard's slice of the bin-ordered list -- (position inside the slice, entry number) pairs
 // appended to the query's row of the shard's inbox (peer memory over NVLink, 8 bytes per
@@ -1325,16 +1432,11 @@ struct Rank2Args {
   const uint16_t* ridx;   // optional [QN][max_vec]: the distance of candidate slot a is
                           // val[q][ridx[q][a]] (the scan evaluated repeated candidates once)
   uint32_t fast_rank;     // 1: composite-key sort first; 0: the network only
-  uint32_t bucket_sort;   // 1: counting sort of the composite words (needs the counter array of
-                          // rank2_smem_bytes(max_vec, true)); 0: bitonic sort of the words
   unsigned long long* phase_dbg;  // optional [QN][8] clock64 stamps (layout of rerank_kernel's;
                                   // slot 1 = end of the sort proper instead of the LUT wait)
 };
 
-// val | sort words | repair bitmap | misc | bucket counters (counting sort, lists >= 1024)
-inline size_t rank2_smem_bytes(uint32_t max_vec, bool bucket = true) {
-  return (size_t)max_vec * 8 + 512 + 64 + (bucket && max_vec >= 1024 ? (size_t)max_vec * 4 : 0);
-}
+inline size_t rank2_smem_bytes(uint32_t max_vec) { return (size_t)max_vec * 8 + 512 + 64; }
 constexpr int kRank2Threads = 256;  // one query per CTA, 4 CTAs per SM
 
 template <bool DIRECT>
@@ -1349,8 +1451,6 @@ __global__ void __launch_bounds__(kRank2Threads, 4) rank2_kernel(Rank2Args a) {
   uint32_t* s_min = s_misc + 2;
   uint32_t* s_max = s_misc + 3;
   uint32_t* s_bad = s_misc + 4;
-  uint32_t* s_tot = s_misc + 5;                                      // [10] counting-sort scratch
-  uint32_t* s_hist = (a.bucket_sort && a.max_vec >= 1024u) ? s_misc + 16 : nullptr;  // [max_vec]
   uint16_t* s_pay = reinterpret_cast<uint16_t*>(s_cmp);
   const Grp G{threadIdx.x, blockDim.x, 0};
   const uint32_t lane = threadIdx.x & 31u;
@@ -1376,16 +1476,45 @@ __global__ void __launch_bounds__(kRank2Threads, 4) rank2_kernel(Rank2Args a) {
     const uint32_t limit = a.n_vec ? min(a.n_vec[qi], a.max_vec) : a.max_vec;
     uint32_t local = 0, umin = 0xFFFFFFFFu, umax = 0u, bad = 0u;
     const uint16_t* ridx_row = a.ridx ? a.ridx + (size_t)qi * a.max_vec : nullptr;
-    for (uint32_t e = threadIdx.x; e < limit; e += blockDim.x) {
-      const float v = val_row[ridx_row ? (uint32_t)ridx_row[e] : e];
-      s_val[e] = v;
-      const bool real = a.n_vec ? true : !(idx_row[e] == kPadIdx && v == kPadDist);
-      if (real) {
-        local = e + 1;
-        const uint32_t u = sortable_key(v);
-        umin = min(umin, u);
-        umax = max(umax, u);
-        if (!(v < kPadDist) || !(v > -__int_as_float(0x7f800000))) bad = 1u;
+    // 8 slots of a thread at a time: their loads are all issued before the first one is used
+    // (the row comes from L2 / HBM; a rolled loop would pay that latency once per slot), and
+    // the id of every candidate is requested into L2 for the emit
+    constexpr int kSlots = 8;
+    for (uint32_t eb = threadIdx.x; eb < limit; eb += kSlots * kRank2Threads) {
+      uint32_t src[kSlots], ix[kSlots];
+      float vv[kSlots];
+#pragma unroll
+      for (int r = 0; r < kSlots; r++) {
+        const uint32_t e = eb + r * kRank2Threads;
+        src[r] = e;
+        if (ridx_row && e < limit) src[r] = ridx_row[e];
+      }
+#pragma unroll
+      for (int r = 0; r < kSlots; r++) {
+        const uint32_t e = eb + r * kRank2Threads;
+        vv[r] = 0.f;
+        ix[r] = 0u;
+        if (e < limit) {
+          vv[r] = val_row[src[r]];
+          if (!DIRECT || !a.n_vec) ix[r] = idx_row[e];
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kSlots; r++) {
+        const uint32_t e = eb + r * kRank2Threads;
+        if (e < limit) {
+          const float v = vv[r];
+          s_val[e] = v;
+          const bool real = a.n_vec ? true : !(ix[r] == kPadIdx && v == kPadDist);
+          if (real) {
+            local = e + 1;
+            const uint32_t u = sortable_key(v);
+            umin = min(umin, u);
+            umax = max(umax, u);
+            if (!(v < kPadDist) || !(v > -__int_as_float(0x7f800000))) bad = 1u;
+            if (!DIRECT) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ids + ix[r]));
+          }
+        }
       }
     }
     local = __reduce_max_sync(0xffffffffu, local);
@@ -1411,7 +1540,7 @@ __global__ void __launch_bounds__(kRank2Threads, 4) rank2_kernel(Rank2Args a) {
     if (a.fast_rank && n2 >= kFastMinN2 && *s_bad == 0u) {
       FastRankState st{*s_min, *s_max};
       uint32_t f = fast_rank_emit<DIRECT>(G, 1, s_val, s_cmp, s_fix, s_flag, nv, n2, a.k, st, od, oi, cand, ids,
-                                          ph, s_hist, s_tot);
+                                          ph);
       if (ph && threadIdx.x == 0) ph[3] = clock64();
       if (f == 1u && a.k >= nv && tie_resolve<DIRECT>(G, s_val, s_cmp, s_flag, nv, a.max_vec, od, oi, cand, ids)) {
         f = 0u;

@@ -179,9 +179,83 @@ __device__ __forceinline__ uint32_t tie_resolve(const Grp& g, const float* s_val
         }
       }
     }
+    // ---- fast-forward.  After stage kk of the network every aligned block of kk positions is
+    // sorted (ascending iff (pos & kk) == 0): Lower, Equal, Higher in a row.  While no block
+    // holds two Equal positions that arrangement follows from the block's class counts alone --
+    // the one Equal element, if any, keeps its label -- so the planes after stage kk0 = the
+    // largest such block size are written down directly and only the stages that bring two
+    // Equal elements into one block are simulated (for a two-element group at random positions
+    // 12 of the 78 sub-stages half of the time, 23 a quarter of the time, ...).
+    uint32_t kk_first = 2u;
+    {
+      uint32_t cLH[4], cEB[4];  // popcounts: Lower | Higher << 16, Equal | label-B << 16
+#pragma unroll
+      for (uint32_t i = 0; i < 4u; i++) {
+        const uint32_t E = ~(L[i] | H[i]);
+        cLH[i] = __popc(L[i]) | (__popc(H[i]) << 16);
+        cEB[i] = __popc(E) | (__popc(B[i] & E) << 16);
+      }
+      // block totals for growing block sizes bw (in words); stop at the first size with two
+      // Equal positions in some block
+      uint32_t bw0 = 0u;
+      uint32_t tLH[4], tEB[4];
+      if (!__any_sync(0xffffffffu, ((cEB[0] | cEB[1] | cEB[2] | cEB[3]) & 0xFFFEu) != 0u)) {
+        bw0 = 1u;
+#pragma unroll
+        for (uint32_t i = 0; i < 4u; i++) {
+          tLH[i] = cLH[i];
+          tEB[i] = cEB[i];
+        }
+        const uint32_t p0 = cEB[0] + cEB[1], p1 = cEB[2] + cEB[3];
+        if (nW >= 2u && !__any_sync(0xffffffffu, ((p0 | p1) & 0xFFFEu) != 0u)) {
+          bw0 = 2u;
+          tLH[0] = tLH[1] = cLH[0] + cLH[1];
+          tLH[2] = tLH[3] = cLH[2] + cLH[3];
+          tEB[0] = tEB[1] = p0;
+          tEB[2] = tEB[3] = p1;
+          uint32_t sLH = tLH[0] + tLH[2], sEB = p0 + p1;
+          if (nW >= 4u && !__any_sync(0xffffffffu, (sEB & 0xFFFEu) != 0u)) {
+            bw0 = 4u;
+            for (uint32_t ld = 1u; ld < 32u; ld <<= 1) {
+              const uint32_t oLH = __shfl_xor_sync(0xffffffffu, sLH, ld);
+              const uint32_t oEB = __shfl_xor_sync(0xffffffffu, sEB, ld);
+              if ((ld << 3) > nW || __any_sync(0xffffffffu, ((sEB + oEB) & 0xFFFEu) != 0u)) break;
+              sLH += oLH;
+              sEB += oEB;
+              bw0 = ld << 3;
+            }
+#pragma unroll
+            for (uint32_t i = 0; i < 4u; i++) {
+              tLH[i] = sLH;
+              tEB[i] = sEB;
+            }
+          }
+        }
+      }
+      if (bw0 != 0u) {
+        auto low = [](int n) { return n <= 0 ? 0u : n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u); };
+#pragma unroll
+        for (uint32_t i = 0; i < 4u; i++) {
+          const uint32_t x = (lane << 2) + i;
+          const int o = (int)((x & (bw0 - 1u)) << 5);  // first position of the word inside its block
+          const int nL = (int)(tLH[i] & 0xFFFFu), nH = (int)(tLH[i] >> 16);
+          const int nE = (int)(tEB[i] & 0xFFFFu);
+          const bool lab = (tEB[i] >> 16) != 0u;
+          if ((x & bw0) == 0u) {  // ascending block: Lower, Equal, Higher
+            L[i] = low(nL - o);
+            H[i] = ~low(nL + nE - o);
+          } else {                // descending block: Higher, Equal, Lower
+            H[i] = low(nH - o);
+            L[i] = ~low(nH + nE - o);
+          }
+          B[i] = lab ? ~(L[i] | H[i]) : 0u;
+        }
+        kk_first = bw0 << 6;  // the first stage that still has to run: 2 * 32 * bw0
+      }
+    }
     // the network of pqt/bitonicSort.cuh:16-44 / :47-78: for k = 2..n, for j = k/2..1:
     // pairs (i, i^j), ascending iff (i & k) == 0.  x = 4*lane + i is the word index.
-    for (uint32_t kk = 2u; kk <= max_vec; kk <<= 1) {
+    for (uint32_t kk = kk_first; kk <= max_vec; kk <<= 1) {
       for (uint32_t j = kk >> 1; j > 0u; j >>= 1) {
         if (j < 32u) {
           const uint32_t M = j == 1u ? 0x55555555u : j == 2u ? 0x33333333u : j == 4u ? 0x0F0F0F0Fu
