@@ -1094,7 +1094,8 @@ __global__ void __launch_bounds__(TPB, 1) rerank_kernel(RerankArgs g) {
                                                 od, oi, cand, a.ids, ph);
       if (ph && G.t == 0) ph[3] = clock64();
       // bit-equal distances of different vectors: re-order them the way the network does
-      if (f == 1u && g.k >= nv && tie_resolve<false>(G, s_val, s_cmp, s_flag, nv, a.max_vec, od, oi, cand, a.ids)) {
+      if (f == 1u && g.k >= nv && tie_resolve<false>(G, s_val, s_cmp, s_flag, nv, a.max_vec, od, oi, cand, a.ids,
+                                                                  1u + 2u * kRerankGroups + grp, 1u)) {
         f = 0u;
         if (G.t == 0 && g.tie_counter) atomicAdd(g.tie_counter, 1ull);
       }
@@ -1542,7 +1543,10 @@ __global__ void __launch_bounds__(kRank2Threads, 4) rank2_kernel(Rank2Args a) {
       uint32_t f = fast_rank_emit<DIRECT>(G, 1, s_val, s_cmp, s_fix, s_flag, nv, n2, a.k, st, od, oi, cand, ids,
                                           ph);
       if (ph && threadIdx.x == 0) ph[3] = clock64();
-      if (f == 1u && a.k >= nv && tie_resolve<DIRECT>(G, s_val, s_cmp, s_flag, nv, a.max_vec, od, oi, cand, ids)) {
+      if (ph && threadIdx.x == 0) s_misc[8] = s_misc[9] = 0u;
+      if (f == 1u && a.k >= nv &&
+          tie_resolve<DIRECT>(G, s_val, s_cmp, s_flag, nv, a.max_vec, od, oi, cand, ids, 2u, 2u,
+                              ph ? s_misc + 8 : nullptr)) {
         f = 0u;
         if (threadIdx.x == 0 && a.tie_counter) atomicAdd(a.tie_counter, 1ull);
       }
@@ -1553,7 +1557,9 @@ __global__ void __launch_bounds__(kRank2Threads, 4) rank2_kernel(Rank2Args a) {
       rank_and_emit(G, s_val, s_pay, id_of, s_flag, nv, a.max_vec, a.k, od, oi, a.exact_counter);
     if (ph && threadIdx.x == 0) {
       ph[6] = clock64();
-      ph[7] = ((unsigned long long)blockIdx.x << 32) | (nv << 1) | (done ? 1u : 0u) | (1ull << 63);
+      // meta: block | tie groups << 48 | (cycles of the tie search >> 4) << 14 | nv << 1 | fast
+      ph[7] = ((unsigned long long)blockIdx.x << 32) | ((unsigned long long)(s_misc[9] & 15u) << 48) |
+              ((unsigned long long)min(s_misc[8] >> 4, 0x3FFFFu) << 14) | (nv << 1) | (done ? 1u : 0u) | (1ull << 63);
     }
   }
 }

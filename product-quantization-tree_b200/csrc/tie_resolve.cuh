@@ -63,15 +63,21 @@ __device__ __forceinline__ void tie_substage_xword(uint32_t& L, uint32_t& H, uin
 //               candidate is in the output); ids inside equal-distance groups in any order
 //   cand / ids: candidate slot -> bin-order position -> vector id
 // Every thread of the group must call.  Returns 1 when all groups were resolved, 0 when the
-// caller has to rank the query with the network itself.  g.n is a multiple of 128.
+// caller has to rank the query with the network itself.  g.n is a multiple of 128; the first
+// nteams * 128 threads of the group (nteams * 128 <= g.n) simulate, one group of ties per team,
+// and use the hardware barriers team_bar0 .. team_bar0 + nteams - 1.
 // DIRECT: ids[slot] is the id (see fast_rank.cuh).
 template <bool DIRECT>
 __device__ __forceinline__ uint32_t tie_resolve(const Grp& g, const float* s_val, uint32_t* s_scr,
                                                 uint32_t* s_flag, uint32_t nv, uint32_t max_vec,
                                                 const float* out_dist, uint32_t* out_idx,
                                                 const uint32_t* __restrict__ cand,
-                                                const uint32_t* __restrict__ ids) {
+                                                const uint32_t* __restrict__ ids,
+                                                uint32_t team_bar0, uint32_t nteams,
+                                                uint32_t* dbg = nullptr) {
+  // dbg (optional, 2 shared words): cycles spent finding the groups, number of groups
   const uint32_t t = g.t;
+  const long long tdbg0 = dbg ? clock64() : 0ll;
   uint32_t* s_cnt = s_scr;           // [1]
   uint32_t* s_gr = s_scr + 8;        // [kTieMaxGroups] first slot
   uint32_t* s_gm = s_gr + 8;         // length
@@ -143,25 +149,35 @@ __device__ __forceinline__ uint32_t tie_resolve(const Grp& g, const float* s_val
   if (fail) atomicOr(s_flag, 8u);
   g.sync();
   const uint32_t cnt = *s_cnt;
+  if (dbg && t == 0) {
+    dbg[0] = (uint32_t)(clock64() - tdbg0);
+    dbg[1] = cnt;
+  }
   if (*s_flag & 8u) return 0u;
   if (cnt == 0u) return 1u;  // only duplicates of one vector shared a distance: nothing to do
 
-  // ---- B. one WARP per group: lane l owns words 4l .. 4l+3 of the three planes (max_vec <=
-  // 4096 positions = 128 words), so the whole network runs in registers and shuffles -- no
-  // shared memory, no barrier, and the warps without a group stay out of the issue slots.
-  const uint32_t lane = t & 31u, warp = t >> 5, nwarps = g.n >> 5;
-  for (uint32_t g0 = 0; g0 < cnt; g0 += nwarps) {
-    const uint32_t gi = g0 + warp;
-    if (gi >= cnt) break;  // warp-uniform
-    const uint32_t r = s_gr[gi], m = s_gm[gi];
-    const uint32_t idA = s_ga[gi], idB = s_gb[gi];
-    const float v = out_dist[r];
-    uint32_t L[4] = {0u, 0u, 0u, 0u}, H[4] = {~0u, ~0u, ~0u, ~0u}, B[4] = {0u, 0u, 0u, 0u};
-    // classes of the input positions (candidate order, pads = Higher); word w goes to lane w / 4
-    for (uint32_t w0 = 0; w0 < nW; w0 += 4u) {
-#pragma unroll
-      for (uint32_t i = 0; i < 4u; i++) {
-        const uint32_t w = w0 + i;
+  // ---- B. one TEAM of 128 threads per group: thread x of the team owns word x of the three
+  // planes (max_vec <= 4096 positions = 128 words).  Sub-stages at bit distance < 32 are
+  // bitwise inside the word, distances 32 .. 512 are shuffles inside the team's warps, the
+  // three sub-stages at distance 1024 / 2048 go through shared memory.  Teams synchronise on
+  // their own named barrier (team_bar0 + team); threads beyond the teams wait at the end.
+  const uint32_t lane = t & 31u;
+  const uint32_t team = t >> 7, x = t & 127u, tw = x >> 5;
+  if (team < nteams) {
+    uint32_t* s_tm = s_scr + 64u + team * 384u;  // planes in transit (only lists > 1024 get there)
+    uint32_t* s_lvl = s_scr + 48u + team;        // level mask of the fast-forward
+    const uint32_t tbar = team_bar0 + team;
+    auto team_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(tbar), "r"(128) : "memory"); };
+    for (uint32_t gi = team; gi < cnt; gi += nteams) {  // team-uniform
+      const uint32_t r = s_gr[gi], m = s_gm[gi];
+      const uint32_t idA = s_ga[gi], idB = s_gb[gi];
+      const float v = out_dist[r];
+      if (x == 0u) *s_lvl = 0u;
+      // classes of the input positions (candidate order, pads = Higher): warp tw of the team
+      // builds words 32*tw .. 32*tw+31 with ballots, lane i keeps word 32*tw + i
+      uint32_t L = 0u, H = ~0u, B = 0u;
+      for (uint32_t i = 0; i < 32u; i++) {
+        const uint32_t w = (tw << 5) + i;
         if (w < nW) {  // warp-uniform
           const uint32_t a = (w << 5) + lane;
           const float val = a < nv ? s_val[a] : kPadDist;
@@ -171,157 +187,97 @@ __device__ __forceinline__ uint32_t tie_resolve(const Grp& g, const float* s_val
           const uint32_t bl = __ballot_sync(0xffffffffu, isL);
           const uint32_t bh = __ballot_sync(0xffffffffu, isH);
           const uint32_t bb = __ballot_sync(0xffffffffu, isB);
-          if (lane == (w0 >> 2)) {
-            L[i] = bl;
-            H[i] = bh;
-            B[i] = bb;
+          if (lane == i) {
+            L = bl;
+            H = bh;
+            B = bb;
           }
         }
       }
-    }
-    // ---- fast-forward.  After stage kk of the network every aligned block of kk positions is
-    // sorted (ascending iff (pos & kk) == 0): Lower, Equal, Higher in a row.  While no block
-    // holds two Equal positions that arrangement follows from the block's class counts alone --
-    // the one Equal element, if any, keeps its label -- so the planes after stage kk0 = the
-    // largest such block size are written down directly and only the stages that bring two
-    // Equal elements into one block are simulated (for a two-element group at random positions
-    // 12 of the 78 sub-stages half of the time, 23 a quarter of the time, ...).
-    uint32_t kk_first = 2u;
-    {
-      uint32_t cLH[4], cEB[4];  // popcounts: Lower | Higher << 16, Equal | label-B << 16
-#pragma unroll
-      for (uint32_t i = 0; i < 4u; i++) {
-        const uint32_t E = ~(L[i] | H[i]);
-        cLH[i] = __popc(L[i]) | (__popc(H[i]) << 16);
-        cEB[i] = __popc(E) | (__popc(B[i] & E) << 16);
-      }
-      // block totals for growing block sizes bw (in words); stop at the first size with two
-      // Equal positions in some block
-      uint32_t bw0 = 0u;
-      uint32_t tLH[4], tEB[4];
-      if (!__any_sync(0xffffffffu, ((cEB[0] | cEB[1] | cEB[2] | cEB[3]) & 0xFFFEu) != 0u)) {
-        bw0 = 1u;
-#pragma unroll
-        for (uint32_t i = 0; i < 4u; i++) {
-          tLH[i] = cLH[i];
-          tEB[i] = cEB[i];
+      // ---- fast-forward.  After stage kk of the network every aligned block of kk positions
+      // is sorted (ascending iff (pos & kk) == 0): Lower, Equal, Higher in a row.  While no
+      // block holds two Equal positions that arrangement follows from the block's class counts
+      // alone -- the one Equal element, if any, keeps its label -- so the planes after stage
+      // kk0 = the largest such block size (up to the 1024 positions of one warp) are written
+      // down directly and only the later stages are simulated.
+      const uint32_t cLH = __popc(L) | (__popc(H) << 16);          // Lower | Higher << 16
+      const uint32_t cEB = __popc(~(L | H)) | (__popc(B) << 16);   // Equal | label-B << 16 (B is a subset of Equal)
+      {
+        uint32_t viol = __any_sync(0xffffffffu, (cEB & 0xFFFEu) != 0u) ? 1u : 0u;  // bit l: blocks of 2^l words
+        uint32_t sEB = cEB;
+        for (uint32_t ld = 1u, bit = 2u; ld < 32u; ld <<= 1, bit <<= 1) {
+          sEB += __shfl_xor_sync(0xffffffffu, sEB, ld);
+          if (__any_sync(0xffffffffu, (sEB & 0xFFFEu) != 0u)) viol |= bit;
         }
-        const uint32_t p0 = cEB[0] + cEB[1], p1 = cEB[2] + cEB[3];
-        if (nW >= 2u && !__any_sync(0xffffffffu, ((p0 | p1) & 0xFFFEu) != 0u)) {
-          bw0 = 2u;
-          tLH[0] = tLH[1] = cLH[0] + cLH[1];
-          tLH[2] = tLH[3] = cLH[2] + cLH[3];
-          tEB[0] = tEB[1] = p0;
-          tEB[2] = tEB[3] = p1;
-          uint32_t sLH = tLH[0] + tLH[2], sEB = p0 + p1;
-          if (nW >= 4u && !__any_sync(0xffffffffu, (sEB & 0xFFFEu) != 0u)) {
-            bw0 = 4u;
-            for (uint32_t ld = 1u; ld < 32u; ld <<= 1) {
-              const uint32_t oLH = __shfl_xor_sync(0xffffffffu, sLH, ld);
-              const uint32_t oEB = __shfl_xor_sync(0xffffffffu, sEB, ld);
-              if ((ld << 3) > nW || __any_sync(0xffffffffu, ((sEB + oEB) & 0xFFFEu) != 0u)) break;
-              sLH += oLH;
-              sEB += oEB;
-              bw0 = ld << 3;
-            }
-#pragma unroll
-            for (uint32_t i = 0; i < 4u; i++) {
-              tLH[i] = sLH;
-              tEB[i] = sEB;
-            }
+        team_sync();  // the level mask was cleared
+        if (lane == 0u && viol) atomicOr(s_lvl, viol);
+        team_sync();
+      }
+      uint32_t kk_first = 2u;
+      {
+        const uint32_t viol = *s_lvl;
+        uint32_t bw0 = 0u;  // words per block of the last stage that needs no simulation
+        for (uint32_t bw = 1u, bit = 1u; bw <= 32u && bw <= nW && !(viol & bit); bw <<= 1, bit <<= 1) bw0 = bw;
+        if (bw0 != 0u) {
+          uint32_t sLH = cLH, sEB = cEB;
+          for (uint32_t ld = 1u; ld < bw0; ld <<= 1) {
+            sLH += __shfl_xor_sync(0xffffffffu, sLH, ld);
+            sEB += __shfl_xor_sync(0xffffffffu, sEB, ld);
           }
-        }
-      }
-      if (bw0 != 0u) {
-        auto low = [](int n) { return n <= 0 ? 0u : n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u); };
-#pragma unroll
-        for (uint32_t i = 0; i < 4u; i++) {
-          const uint32_t x = (lane << 2) + i;
+          auto low = [](int n) { return n <= 0 ? 0u : n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u); };
           const int o = (int)((x & (bw0 - 1u)) << 5);  // first position of the word inside its block
-          const int nL = (int)(tLH[i] & 0xFFFFu), nH = (int)(tLH[i] >> 16);
-          const int nE = (int)(tEB[i] & 0xFFFFu);
-          const bool lab = (tEB[i] >> 16) != 0u;
+          const int nL = (int)(sLH & 0xFFFFu), nH = (int)(sLH >> 16);
+          const int nE = (int)(sEB & 0xFFFFu);
           if ((x & bw0) == 0u) {  // ascending block: Lower, Equal, Higher
-            L[i] = low(nL - o);
-            H[i] = ~low(nL + nE - o);
+            L = low(nL - o);
+            H = ~low(nL + nE - o);
           } else {                // descending block: Higher, Equal, Lower
-            H[i] = low(nH - o);
-            L[i] = ~low(nH + nE - o);
+            H = low(nH - o);
+            L = ~low(nH + nE - o);
           }
-          B[i] = lab ? ~(L[i] | H[i]) : 0u;
+          B = (sEB >> 16) != 0u ? ~(L | H) : 0u;
+          kk_first = bw0 << 6;  // the first stage that still has to run: 2 * 32 * bw0
         }
-        kk_first = bw0 << 6;  // the first stage that still has to run: 2 * 32 * bw0
       }
-    }
-    // the network of pqt/bitonicSort.cuh:16-44 / :47-78: for k = 2..n, for j = k/2..1:
-    // pairs (i, i^j), ascending iff (i & k) == 0.  x = 4*lane + i is the word index.
-    for (uint32_t kk = kk_first; kk <= max_vec; kk <<= 1) {
-      for (uint32_t j = kk >> 1; j > 0u; j >>= 1) {
-        if (j < 32u) {
-          const uint32_t M = j == 1u ? 0x55555555u : j == 2u ? 0x33333333u : j == 4u ? 0x0F0F0F0Fu
-                             : j == 8u ? 0x00FF00FFu : 0x0000FFFFu;
-          if (kk < 32u) {
-            const uint32_t Mk = kk == 2u ? 0x33333333u : kk == 4u ? 0x0F0F0F0Fu
-                                : kk == 8u ? 0x00FF00FFu : 0x0000FFFFu;
-            const uint32_t D = ~Mk & M;  // positions with (pos & kk) != 0
-#pragma unroll
-            for (uint32_t i = 0; i < 4u; i++) tie_substage_inword(L[i], H[i], B[i], j, M, D);
-          } else {
-            const uint32_t kw = kk >> 5;
-#pragma unroll
-            for (uint32_t i = 0; i < 4u; i++)
-              tie_substage_inword(L[i], H[i], B[i], j, M, (((lane << 2) + i) & kw) ? M : 0u);
-          }
-        } else {
-          const uint32_t wd = j >> 5, kw = kk >> 5;
-          if (wd < 4u) {
-            // partner word in the same lane: i ^ wd
-#pragma unroll
-            for (uint32_t i = 0; i < 4u; i++) {
-              if ((i & wd) == 0u) {
-                const uint32_t q = i ^ wd;  // wd is 1 or 2: compile-time after unrolling on both
-                const bool desc = (((lane << 2) + i) & kw) != 0u;
-                uint32_t L0 = L[i], H0 = H[i], B0 = B[i];
-                uint32_t L1 = wd == 1u ? L[i ^ 1u] : L[i ^ 2u];
-                uint32_t H1 = wd == 1u ? H[i ^ 1u] : H[i ^ 2u];
-                uint32_t B1 = wd == 1u ? B[i ^ 1u] : B[i ^ 2u];
-                const uint32_t gt = (H0 & ~H1) | (~L0 & L1);
-                const uint32_t lt = (H1 & ~H0) | (~L1 & L0);
-                const uint32_t sw = desc ? lt : gt;
-                const uint32_t dL = (L0 ^ L1) & sw, dH = (H0 ^ H1) & sw, dB = (B0 ^ B1) & sw;
-                L[i] = L0 ^ dL;
-                H[i] = H0 ^ dH;
-                B[i] = B0 ^ dB;
-                if (wd == 1u) {
-                  L[i ^ 1u] = L1 ^ dL;
-                  H[i ^ 1u] = H1 ^ dH;
-                  B[i ^ 1u] = B1 ^ dB;
-                } else {
-                  L[i ^ 2u] = L1 ^ dL;
-                  H[i ^ 2u] = H1 ^ dH;
-                  B[i ^ 2u] = B1 ^ dB;
-                }
-                (void)q;
-              }
+      // the network of pqt/bitonicSort.cuh:16-44 / :47-78: for k = 2..n, for j = k/2..1:
+      // pairs (i, i^j), ascending iff (i & k) == 0
+      for (uint32_t kk = kk_first; kk <= max_vec; kk <<= 1) {
+        const uint32_t kw = kk >> 5;
+        for (uint32_t j = kk >> 1; j > 0u; j >>= 1) {
+          if (j < 32u) {
+            const uint32_t M = j == 1u ? 0x55555555u : j == 2u ? 0x33333333u : j == 4u ? 0x0F0F0F0Fu
+                               : j == 8u ? 0x00FF00FFu : 0x0000FFFFu;
+            uint32_t D;
+            if (kk < 32u) {
+              const uint32_t Mk = kk == 2u ? 0x33333333u : kk == 4u ? 0x0F0F0F0Fu
+                                  : kk == 8u ? 0x00FF00FFu : 0x0000FFFFu;
+              D = ~Mk & M;  // positions with (pos & kk) != 0
+            } else {
+              D = (x & kw) ? M : 0u;
             }
+            tie_substage_inword(L, H, B, j, M, D);
           } else {
-            const uint32_t ld = wd >> 2;  // lane distance
-            const bool lo = (lane & ld) == 0u;
-#pragma unroll
-            for (uint32_t i = 0; i < 4u; i++) {
-              const uint32_t oL = __shfl_xor_sync(0xffffffffu, L[i], ld);
-              const uint32_t oH = __shfl_xor_sync(0xffffffffu, H[i], ld);
-              const uint32_t oB = __shfl_xor_sync(0xffffffffu, B[i], ld);
-              tie_substage_xword(L[i], H[i], B[i], oL, oH, oB, lo, (((lane << 2) + i) & kw) != 0u);
+            const uint32_t wd = j >> 5;
+            uint32_t oL, oH, oB;
+            if (wd < 32u) {
+              oL = __shfl_xor_sync(0xffffffffu, L, wd);
+              oH = __shfl_xor_sync(0xffffffffu, H, wd);
+              oB = __shfl_xor_sync(0xffffffffu, B, wd);
+            } else {
+              s_tm[x] = L;
+              s_tm[128u + x] = H;
+              s_tm[256u + x] = B;
+              team_sync();
+              oL = s_tm[x ^ wd];
+              oH = s_tm[128u + (x ^ wd)];
+              oB = s_tm[256u + (x ^ wd)];
+              team_sync();
             }
+            tie_substage_xword(L, H, B, oL, oH, oB, (x & wd) == 0u, (x & kw) != 0u);
           }
         }
       }
-    }
-    // ---- the Equal positions are now the group's output slots r .. r+m-1
-#pragma unroll
-    for (uint32_t i = 0; i < 4u; i++) {
-      const uint32_t x = (lane << 2) + i;
+      // ---- the Equal positions are now the group's output slots r .. r+m-1
       if (x < nW) {
         const uint32_t base = x << 5;
         uint32_t want = 0;
@@ -330,15 +286,16 @@ __device__ __forceinline__ uint32_t tie_resolve(const Grp& g, const float* s_val
           const uint32_t hi = min(32u, r + m - base);
           want = (hi >= 32u ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
         }
-        const uint32_t eq = ~(L[i] | H[i]);
+        const uint32_t eq = ~(L | H);
         if (eq != want) atomicOr(s_flag, 8u);  // cannot happen for a sorted result; be safe
         uint32_t todo = want;
         while (todo) {
           const uint32_t b = __ffs(todo) - 1u;
           todo &= todo - 1u;
-          out_idx[base + b] = ((B[i] >> b) & 1u) ? idB : idA;
+          out_idx[base + b] = ((B >> b) & 1u) ? idB : idA;
         }
       }
+      team_sync();  // everyone has read the level mask before the next group clears it
     }
   }
   g.sync();

@@ -34,9 +34,11 @@ def main():
     t.debug(False)
     split = bool((ph[:, 7] < 0).any())  # bit 63: stamps of the ranking-only kernel (split pipeline)
     ph[:, 7] &= (1 << 63) - 1
-    nv = (ph[:, 7] & 0xFFFFFFFF) >> 1
+    nv = (ph[:, 7] & 0x3FFF) >> 1
+    tie_search = ((ph[:, 7] >> 14) & 0x3FFFF) << 4
+    tie_groups = (ph[:, 7] >> 48) & 15
     fast = ph[:, 7] & 1
-    sm = ph[:, 7] >> 32
+    sm = (ph[:, 7] >> 32) & 0xFFFF
     names = ["lut_wait", "scan", "sort+emit", "repair", "ties", "network/tail"]
     if split:
         # rank2_kernel: slot 1 = end of the sort proper; phases: load, sort, emit, repair, ties, tail
@@ -58,6 +60,14 @@ def main():
     print("mean cycles per query: total %.0f" % tot.mean())
     for i, n in enumerate(names):
         print("  %-22s mean %8.0f  p99 %8.0f  max %9d" % (n, d[:, i].mean(), np.percentile(d[:, i], 99), d[:, i].max()))
+    if split:
+        ties = d[:, 4]
+        print("  tie resolver: search for groups mean %.0f cycles; groups per query: %s" %
+              (tie_search.mean(), " ".join("%d:%d" % (g, int((tie_groups == g).sum())) for g in range(9))))
+        for g in range(0, 9):
+            m = tie_groups == g
+            if m.any():
+                print("    %d groups: %5d queries, ties phase mean %.0f (search %.0f)" % (g, m.sum(), ties[m].mean(), tie_search[m].mean()))
     for lo, hi in [(0, 512), (512, 1024), (1024, 2048), (2048, 4097)]:
         m = (nv >= lo) & (nv < hi)
         if m.any():
