@@ -91,8 +91,16 @@ __device__ __forceinline__ void xthread_step_u32(uint32_t (&c)[E], uint32_t t, u
     }
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(Ta) : "memory");
   }
+  // min or max by a predicate: one predicated pair per element instead of min + max + select
+  // (the hardware's VIMNMX takes the choice as a predicate operand; nvcc does not emit that
+  // form for the ternary)
+  const uint32_t km = keep_min ? 1u : 0u;
 #pragma unroll
-  for (int r = 0; r < E; r++) c[r] = keep_min ? min(c[r], o[r]) : max(c[r], o[r]);
+  for (int r = 0; r < E; r++) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p min.u32 %0, %0, %1;\n\t@!p max.u32 %0, %0, %1;\n\t}"
+        : "+r"(c[r])
+        : "r"(o[r]), "r"(km));
+  }
 }
 
 // Ascending sort of n2 = E*T distinct words of which only the first E*Ta (Ta a multiple of
