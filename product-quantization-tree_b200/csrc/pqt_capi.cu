@@ -710,9 +710,9 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
       const uint32_t sgrid = std::min<uint32_t>(QN, (uint32_t)h->num_sms);
 #define LAUNCH_STREAM(LPV, CREPV)                                                                   \
   do {                                                                                              \
-    CU_TRY(h, cudaFuncSetAttribute(adc_stream_kernel<LPV, CREPV, 512, false>,                       \
+    CU_TRY(h, cudaFuncSetAttribute(adc_stream_kernel<LPV, CREPV, 512>,                       \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));        \
-    adc_stream_kernel<LPV, CREPV, 512, false><<<sgrid, 512, ssmem, h->stream>>>(sa);                 \
+    adc_stream_kernel<LPV, CREPV, 512><<<sgrid, 512, ssmem, h->stream>>>(sa);                 \
   } while (0)
       if (h->LP == 32) LAUNCH_STREAM(32, true); else LAUNCH_STREAM(16, false);
 #undef LAUNCH_STREAM
@@ -1887,29 +1887,18 @@ int pqt_shard_scan_p2p(pqt_index* h, uint32_t QN, uint32_t k) {
   sa.inbox = h->x_inbox.as<uint2>();
   sa.q_per_rank = h->x_q_per_rank;
   for (uint32_t r = 0; r < h->world; r++) sa.peer_val[r] = h->x_peer_val[r];
-  const size_t ssmem = stream_scan_smem_bytes(h->c1, h->LP, h->LP == 32);
-  if (ssmem > (size_t)227 * 1024) return fail(h, PQT_ERR_INVALID, "c1 = %u > 32 is not supported by the ADC scan yet", h->c1);
-  const uint32_t sgrid = std::min<uint32_t>(QN, (uint32_t)h->num_sms);
-  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
-  static const bool warp_mode = !(getenv("PQT_INBOX_MODE") && strcmp(getenv("PQT_INBOX_MODE"), "cta") == 0);  // A/B runs
   const size_t wsmem = inbox_scan_smem_bytes(h->c1, h->LP, h->LP == 32);
-  if (warp_mode && wsmem <= (size_t)227 * 1024) {
-    CU_TRY(h, h->d_sched.ensure(64));
-    CU_TRY(h, cudaMemsetAsync(h->d_sched.p, 0, 4, h->stream));
-    const uint32_t wgrid = std::min<uint32_t>((QN + kInboxWarps - 1) / kInboxWarps, (uint32_t)h->num_sms);
-    if (h->LP == 32) {
-      CU_TRY(h, cudaFuncSetAttribute(adc_inbox_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-      adc_inbox_kernel<32, true><<<wgrid, kInboxWarps * 32, wsmem, h->stream>>>(sa, h->d_sched.as<uint32_t>());
-    } else {
-      CU_TRY(h, cudaFuncSetAttribute(adc_inbox_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-      adc_inbox_kernel<16, false><<<wgrid, kInboxWarps * 32, wsmem, h->stream>>>(sa, h->d_sched.as<uint32_t>());
-    }
-  } else if (h->LP == 32) {
-    CU_TRY(h, cudaFuncSetAttribute(adc_stream_kernel<32, true, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
-    adc_stream_kernel<32, true, 512, true><<<sgrid, 512, ssmem, h->stream>>>(sa);
+  if (wsmem > (size_t)227 * 1024) return fail(h, PQT_ERR_INVALID, "c1 = %u > 32 is not supported by the ADC scan yet", h->c1);
+  if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+  CU_TRY(h, h->d_sched.ensure(64));
+  CU_TRY(h, cudaMemsetAsync(h->d_sched.p, 0, 4, h->stream));
+  const uint32_t wgrid = std::min<uint32_t>((QN + kInboxWarps - 1) / kInboxWarps, (uint32_t)h->num_sms);
+  if (h->LP == 32) {
+    CU_TRY(h, cudaFuncSetAttribute(adc_inbox_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+    adc_inbox_kernel<32, true><<<wgrid, kInboxWarps * 32, wsmem, h->stream>>>(sa, h->d_sched.as<uint32_t>());
   } else {
-    CU_TRY(h, cudaFuncSetAttribute(adc_stream_kernel<16, false, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
-    adc_stream_kernel<16, false, 512, true><<<sgrid, 512, ssmem, h->stream>>>(sa);
+    CU_TRY(h, cudaFuncSetAttribute(adc_inbox_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+    adc_inbox_kernel<16, false><<<wgrid, kInboxWarps * 32, wsmem, h->stream>>>(sa, h->d_sched.as<uint32_t>());
   }
   CU_TRY(h, cudaGetLastError());
   h->stats.kernel_launches++;
