@@ -723,6 +723,23 @@ def run_b200(a, rank, world, local_rank):
                   "bins_s": build["bins_s"], "lines_s": build["lines_s"],
                   "chunk": min(a.chunk, a.n)},
     }
+    if sharded:
+        # what bounds the step at this N (per-rank stage times of rank 0, profiled pass)
+        st_ms = head["roofline"]["stage_ms_per_step"]
+        stage, ms = max(st_ms.items(), key=lambda kv: kv[1])
+        per = QN // world
+        why = {"tables": "Steps A-C of the own queries plus Step B of every query of the batch",
+               "bins": "bin walk + dispatch of the own queries: one CTA per query, %d queries = %.1f waves of "
+                       "latency-bound CTAs" % (per, per / (148 * 5.0)),
+               "scan": "inbox scan: every shard touches all %d queries (LUT load + pipeline ramp per query for "
+                       "about max_vec/%d entries each)" % (QN, world),
+               "sort": "ranking of the own queries: one CTA per query, %d queries = %.1f waves" % (per, per / (148 * 4.0))}
+        out["limiter"] = {
+            "largest_stage": stage, "ms": ms, "why": why.get(stage, ""),
+            "outside_the_stages_ms": max(0.0, head["ms_per_step"] - sum(st_ms.values())),
+            "outside_the_stages": "two stream-ordered NCCL all-reduce barriers and launch gaps",
+            "e2e": "every rank returns %d MB per step over PCIe; with all ranks copying at once the host side "
+                   "delivers far less than the 55 GB/s a single rank sees (tools/d2h_probe.py)" % (per * k * 8 >> 20)}
     if "big" in summ:
         b = summ["big"]
         out["big_variant"] = {

@@ -171,6 +171,11 @@ struct Grp {
   }
 };
 
+// request the line of a global address into L2 (no register result, no stall)
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // ---- mbarrier / TMA bulk copy (cp.async.bulk, SASS: UBLKCP) ----------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
