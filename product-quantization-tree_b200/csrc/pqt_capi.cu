@@ -706,8 +706,6 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
       sa.cbd = h->LP == 32 ? h->d_cbd_dup.as<float>() : h->d_cbd.as<float>();
       sa.QN = QN; sa.c1 = h->c1; sa.max_vec = max_vec;
       sa.out_val = h->s_val.as<float>();
-      static const int pf_steps = getenv("PQT_SCAN_PREFETCH") ? atoi(getenv("PQT_SCAN_PREFETCH")) : 0;  // A/B runs
-      sa.pf_steps = (uint32_t)pf_steps;
       const size_t ssmem = stream_scan_smem_bytes(h->c1, h->LP, h->LP == 32);
       const uint32_t sgrid = std::min<uint32_t>(QN, (uint32_t)h->num_sms);
 #define LAUNCH_STREAM(LPV, CREPV)                                                                   \
@@ -742,15 +740,9 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
         ra.phase_dbg = h->g_phases.as<unsigned long long>();
       }
       const size_t rsmem = rank2_smem_bytes(max_vec);
-      static const int minb = getenv("PQT_RANK_CTAS") ? atoi(getenv("PQT_RANK_CTAS")) : 4;  // A/B runs
-      if (minb == 5) {
-        CU_TRY(h, cudaFuncSetAttribute(rank2_kernel<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-        rank2_kernel<false, 5><<<std::min<uint32_t>(QN, (uint32_t)h->num_sms * 5), kRank2Threads, rsmem, h->stream>>>(ra);
-      } else {
-        if (rsmem > 48 * 1024)
-          CU_TRY(h, cudaFuncSetAttribute(rank2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-        rank2_kernel<false><<<std::min<uint32_t>(QN, (uint32_t)h->num_sms * 4), kRank2Threads, rsmem, h->stream>>>(ra);
-      }
+      if (rsmem > 48 * 1024)
+        CU_TRY(h, cudaFuncSetAttribute(rank2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+      rank2_kernel<false><<<std::min<uint32_t>(QN, (uint32_t)h->num_sms * 4), kRank2Threads, rsmem, h->stream>>>(ra);
       CU_TRY(h, cudaGetLastError());
       h->stats.kernel_launches++;
       if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));

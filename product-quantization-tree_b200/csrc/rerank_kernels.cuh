@@ -1135,8 +1135,6 @@ struct StreamScanArgs {
   const uint2* inbox;        // [QN][max_vec] (local position, entry number)
   uint32_t q_per_rank;       // queries [r*q_per_rank, (r+1)*q_per_rank) belong to rank r
   float* peer_val[8];        // [world] each [q_per_rank][max_vec], mapped peer (or local) memory
-  uint32_t pf_steps;         // adc_stream_kernel: code rows are requested into L2 this many warp
-                             // steps ahead of their loads (0 = off)
 };
 
 inline size_t stream_scan_smem_bytes(uint32_t c1, uint32_t LP, bool crep) {
@@ -1207,29 +1205,9 @@ __global__ void __launch_bounds__(TPB, 1) adc_stream_kernel(StreamScanArgs a) {
       uint32_t wA[LP], wB[LP];
       adc_load_rows<LP, false>(wA, pos0, codes_lp, lp, nullptr);
       mbar_wait(&bars[buf], buf ? phase1 : phase0);
-      // L2 prefetch pipeline: the positions read in one iteration are prefetched in the next
-      const uint32_t pfd = a.pf_steps * stride;
-      uint32_t pfA = 0xFFFFFFFFu, pfB = 0xFFFFFFFFu;
-      if (pfd) {
-        // the rows of the first pf_steps steps of this query are requested right away
-        for (uint32_t s = 2; s < a.pf_steps + 2u; s++) {
-          const uint32_t e = e0 + s * stride;
-          if (e < nv) prefetch_l2(a.codes + (size_t)__ldg(cand + e) * LP);
-        }
-        const uint32_t ea = e0 + pfd + 2 * stride, eb = ea + stride;
-        if (ea < nv) pfA = __ldg(cand + ea);
-        if (eb < nv) pfB = __ldg(cand + eb);
-      }
       for (uint32_t base = warp * 32; base < nv; base += 2 * stride) {
         const bool has1 = base + stride < nv, has2 = base + 2 * stride < nv;
         if (has1) adc_load_rows<LP, false>(wB, pos1, codes_lp, lp, nullptr);
-        if (pfd) {
-          if (pfA != 0xFFFFFFFFu) prefetch_l2(a.codes + (size_t)pfA * LP);
-          if (pfB != 0xFFFFFFFFu) prefetch_l2(a.codes + (size_t)pfB * LP);
-          const uint32_t ea = e0 + pfd + 4 * stride, eb = ea + stride;
-          pfA = ea < nv ? __ldg(cand + ea) : 0xFFFFFFFFu;
-          pfB = eb < nv ? __ldg(cand + eb) : 0xFFFFFFFFu;
-        }
         uint32_t pos2, slot2;
         fetch(e0 + 2 * stride, pos2, slot2);
         {
@@ -1447,8 +1425,11 @@ struct Rank2Args {
 inline size_t rank2_smem_bytes(uint32_t max_vec) { return (size_t)max_vec * 8 + 512 + 64; }
 constexpr int kRank2Threads = 256;  // one query per CTA, 4 CTAs per SM
 
-template <bool DIRECT, int MINB = 4>
-__global__ void __launch_bounds__(kRank2Threads, MINB) rank2_kernel(Rank2Args a) {
+// (5 CTAs per SM at 48 registers were measured: the spills cost more than the occupancy gives,
+// 1.28 vs 1.03 ms per 10 k queries at 100 M vectors; an L2 prefetch pipeline in the scan kernel
+// likewise: 1.40-1.44 vs 1.34 ms -- profiles/r02k_ab_rank_ctas_scan_prefetch_100m.log)
+template <bool DIRECT>
+__global__ void __launch_bounds__(kRank2Threads, 4) rank2_kernel(Rank2Args a) {
   extern __shared__ float smem_f[];
   float* s_val = smem_f;
   uint32_t* s_cmp = reinterpret_cast<uint32_t*>(s_val + a.max_vec);  // sort words / network payloads
