@@ -141,6 +141,7 @@ struct pqt_index {
   uint32_t* x_peer_cnt[8] = {nullptr};
   bool x_ipc_opened[8] = {false};
   DevBuf d_sched;  // one uint32: work counter of the fused scan+rank kernel
+  DevBuf s_ids;    // [QN][max_vec] ids of the candidates when the scan kernel gathers them (PQT_SCAN_IDS=1)
   DevBuf d_exact;  // two uint64: queries ranked by the exact-network fallback, queries with re-ordered ties
 
   // profiling
@@ -706,6 +707,17 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
       sa.cbd = h->LP == 32 ? h->d_cbd_dup.as<float>() : h->d_cbd.as<float>();
       sa.QN = QN; sa.c1 = h->c1; sa.max_vec = max_vec;
       sa.out_val = h->s_val.as<float>();
+      // PQT_SCAN_IDS=1: the scan also gathers the id of every candidate (one more load in its row
+      // pipeline) and the ranking kernel reads id rows instead of chasing position -> id per
+      // result.  Measured at 1 B vectors: ranking 1.11 -> 1.04 ms, scan +0.09 ms: off by default
+      // (profiles/r02l_ab_ids_by_scan.log).
+      static const bool scan_ids = getenv("PQT_SCAN_IDS") && atoi(getenv("PQT_SCAN_IDS")) == 1;
+      const bool ids_by_scan = scan_ids && !h->have_roots;
+      if (ids_by_scan) {
+        CU_TRY(h, h->s_ids.ensure((size_t)QN * max_vec * 4));
+        sa.ids = h->d_dbidx.as<uint32_t>() + h->pos_lo;
+        sa.out_id = h->s_ids.as<uint32_t>();
+      }
       const size_t ssmem = stream_scan_smem_bytes(h->c1, h->LP, h->LP == 32);
       const uint32_t sgrid = std::min<uint32_t>(QN, (uint32_t)h->num_sms);
 #define LAUNCH_STREAM(LPV, CREPV)                                                                   \
@@ -742,7 +754,15 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
       const size_t rsmem = rank2_smem_bytes(max_vec);
       if (rsmem > 48 * 1024)
         CU_TRY(h, cudaFuncSetAttribute(rank2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-      rank2_kernel<false><<<std::min<uint32_t>(QN, (uint32_t)h->num_sms * 4), kRank2Threads, rsmem, h->stream>>>(ra);
+      if (ids_by_scan) {
+        ra.idx = h->s_ids.as<uint32_t>();
+        ra.ids = nullptr;
+        if (rsmem > 48 * 1024)
+          CU_TRY(h, cudaFuncSetAttribute(rank2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+        rank2_kernel<true><<<std::min<uint32_t>(QN, (uint32_t)h->num_sms * 4), kRank2Threads, rsmem, h->stream>>>(ra);
+      } else {
+        rank2_kernel<false><<<std::min<uint32_t>(QN, (uint32_t)h->num_sms * 4), kRank2Threads, rsmem, h->stream>>>(ra);
+      }
       CU_TRY(h, cudaGetLastError());
       h->stats.kernel_launches++;
       if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));

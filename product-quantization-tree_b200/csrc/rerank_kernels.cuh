@@ -1131,6 +1131,9 @@ struct StreamScanArgs {
   const float* cbd;          // [c1*c1][CROW] (replicated rows when CREP)
   uint32_t QN, c1, max_vec;
   float* out_val;            // [QN][max_vec]
+  const uint32_t* ids;       // optional: id of every bin-order position; with out_id the kernel also
+  uint32_t* out_id;          // stores ids[pos] of every list entry ([QN][max_vec]): the gather rides
+                             // in the scan's load pipeline and the ranking kernel reads id rows
   // adc_inbox_kernel (multi-GPU)
   const uint2* inbox;        // [QN][max_vec] (local position, entry number)
   uint32_t q_per_rank;       // queries [r*q_per_rank, (r+1)*q_per_rank) belong to rank r
@@ -1204,23 +1207,38 @@ __global__ void __launch_bounds__(TPB, 1) adc_stream_kernel(StreamScanArgs a) {
     if (warp * 32 < nv) {  // warp-uniform
       uint32_t wA[LP], wB[LP];
       adc_load_rows<LP, false>(wA, pos0, codes_lp, lp, nullptr);
+      uint32_t* oid = a.out_id ? a.out_id + (size_t)qi * a.max_vec : nullptr;
+      uint32_t idA = 0u, idB = 0u;  // ids of the candidates whose rows are in wA / wB
+      if (oid) idA = __ldg(a.ids + pos0);
       mbar_wait(&bars[buf], buf ? phase1 : phase0);
       for (uint32_t base = warp * 32; base < nv; base += 2 * stride) {
         const bool has1 = base + stride < nv, has2 = base + 2 * stride < nv;
-        if (has1) adc_load_rows<LP, false>(wB, pos1, codes_lp, lp, nullptr);
+        if (has1) {
+          adc_load_rows<LP, false>(wB, pos1, codes_lp, lp, nullptr);
+          if (oid) idB = __ldg(a.ids + pos1);
+        }
         uint32_t pos2, slot2;
         fetch(e0 + 2 * stride, pos2, slot2);
         {
           const float v = adc_eval_rows<LP, CROW>(wA, lut_b, cbd_b, a.c1, lp);
-          if (e0 < nv) out[slot0] = v;
+          if (e0 < nv) {
+            out[slot0] = v;
+            if (oid) oid[slot0] = idA;
+          }
         }
         if (!has1) break;
-        if (has2) adc_load_rows<LP, false>(wA, pos2, codes_lp, lp, nullptr);
+        if (has2) {
+          adc_load_rows<LP, false>(wA, pos2, codes_lp, lp, nullptr);
+          if (oid) idA = __ldg(a.ids + pos2);
+        }
         uint32_t pos3, slot3;
         fetch(e0 + 3 * stride, pos3, slot3);
         {
           const float v = adc_eval_rows<LP, CROW>(wB, lut_b, cbd_b, a.c1, lp);
-          if (e0 + stride < nv) out[slot1] = v;
+          if (e0 + stride < nv) {
+            out[slot1] = v;
+            if (oid) oid[slot1] = idB;
+          }
         }
         e0 += 2 * stride;
         slot0 = slot2;
