@@ -1,14 +1,10 @@
 mkdir -p gpurun_out
-run() {
-  tag=$1; shift
-  env "$@" timeout 900 python bench.py --no-cpu-baseline --variants knn --steps 20 > gpurun_out/s13_bench_1b_$tag.log 2>&1
-  python - <<P
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 4 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/s14_bench_n4_1b.log 2>&1
+python - <<P
 import json
 try:
-    j=json.loads([l for l in open('gpurun_out/s13_bench_1b_$tag.log').read().strip().splitlines() if l.startswith('{')][-1])
-    print('1B $tag', round(j['value']), round(j['ms_per_step'],3), {k:round(v,3) for k,v in j['roofline']['stage_ms_per_step'].items()}, 'frac', round(j['roofline']['frac'],3), 'recall', j['recall_at_1'], j['recall_at_100'], 'e2e', round(j['e2e']['value']), 'k100', round(j['e2e_k100']['value']))
+    j=json.loads([l for l in open('gpurun_out/s14_bench_n4_1b.log').read().strip().splitlines() if l.startswith('{')][-1])
+    print('N4 1B', round(j['value']), round(j['ms_per_step'],3), {k:round(v,3) for k,v in j['roofline']['stage_ms_per_step'].items()}, 'recall', j['recall_at_1'], j['recall_at_100'], 'e2e', round(j['e2e']['value']), j['clocks'], j['limiter'], j['setup'])
 except Exception as e:
-    print('parse failed', e); print(open('gpurun_out/s13_bench_1b_$tag.log').read()[-1500:])
+    print('parse failed', e); print(open('gpurun_out/s14_bench_n4_1b.log').read()[-1500:])
 P
-}
-run default PQT_SCAN_IDS=0
