@@ -140,6 +140,7 @@ struct pqt_index {
   uint2* x_peer_inbox[8] = {nullptr};
   uint32_t* x_peer_cnt[8] = {nullptr};
   bool x_ipc_opened[8] = {false};
+  uint32_t scratch_queries = 0;  // largest slab of the batch in flight (query_common)
   DevBuf d_sched;  // one uint32: work counter of the fused scan+rank kernel
   DevBuf s_ids;    // [QN][max_vec] ids of the candidates when the scan kernel gathers them (PQT_SCAN_IDS=1)
   DevBuf d_exact;  // two uint64: queries ranked by the exact-network fallback, queries with re-ordered ties
@@ -519,10 +520,13 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
   const uint32_t n = P.k1 * h->c2;
   if (m > n) return fail(h, PQT_ERR_INVALID, "k1*c2 < traversal width");
 
-  CU_TRY(h, h->s_lut.ensure((size_t)QN * h->c1 * 32 * sizeof(float)));
-  CU_TRY(h, h->s_idx16.ensure((size_t)QN * h->p * 16 * sizeof(uint32_t)));
-  CU_TRY(h, h->s_cand.ensure((size_t)QN * max_vec * sizeof(uint32_t)));
-  CU_TRY(h, h->s_nvec.ensure((size_t)QN * sizeof(uint32_t)));
+  // scratch is sized for the largest slab of the call, so that it never grows (= device-wide
+  // synchronisation in cudaFree) between the slabs of a pipelined batch
+  const uint32_t QNa = std::max(QN, h->scratch_queries);
+  CU_TRY(h, h->s_lut.ensure((size_t)QNa * h->c1 * 32 * sizeof(float)));
+  CU_TRY(h, h->s_idx16.ensure((size_t)QNa * h->p * 16 * sizeof(uint32_t)));
+  CU_TRY(h, h->s_cand.ensure((size_t)QNa * max_vec * sizeof(uint32_t)));
+  CU_TRY(h, h->s_nvec.ensure((size_t)QNa * sizeof(uint32_t)));
   if (h->debug) {
     CU_TRY(h, h->g_assign.ensure((size_t)QN * P.k1 * h->p * 4));
     CU_TRY(h, h->g_lut.ensure((size_t)QN * h->LP * h->c1 * 4));
@@ -551,8 +555,8 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
     a.lut_dup = h->s_lut.as<float>();
     a.idx16 = h->s_idx16.as<uint32_t>();
     if (big) {
-      CU_TRY(h, h->s_topv.ensure((size_t)QN * h->p * kBigKMax * 4));
-      CU_TRY(h, h->s_topi.ensure((size_t)QN * h->p * kBigKMax * 4));
+      CU_TRY(h, h->s_topv.ensure((size_t)QNa * h->p * kBigKMax * 4));
+      CU_TRY(h, h->s_topi.ensure((size_t)QNa * h->p * kBigKMax * 4));
       a.top_val = h->s_topv.as<float>();
       a.top_idx = h->s_topi.as<uint32_t>();
       a.top_n = kBigKMax;
@@ -697,7 +701,7 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
                                    : rerank_smem_bytes(h->c1, h->LP, max_vec, 2, true);
     h->split_ranked = false;
     if (will_split) {
-      CU_TRY(h, h->s_val.ensure((size_t)QN * max_vec * 4));
+      CU_TRY(h, h->s_val.ensure((size_t)QNa * max_vec * 4));
       StreamScanArgs sa{};
       sa.codes = h->d_codes.as<uint32_t>();
       // repeated candidates are evaluated once: the bin walk left the first occurrences
@@ -714,7 +718,7 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
       static const bool scan_ids = getenv("PQT_SCAN_IDS") && atoi(getenv("PQT_SCAN_IDS")) == 1;
       const bool ids_by_scan = scan_ids && !h->have_roots;
       if (ids_by_scan) {
-        CU_TRY(h, h->s_ids.ensure((size_t)QN * max_vec * 4));
+        CU_TRY(h, h->s_ids.ensure((size_t)QNa * max_vec * 4));
         sa.ids = h->d_dbidx.as<uint32_t>() + h->pos_lo;
         sa.out_id = h->s_ids.as<uint32_t>();
       }
@@ -1624,8 +1628,21 @@ static int query_common(pqt_index* h, const float* Q, int q_on_device, uint32_t 
   // Host outputs: queries go through in slabs so that the device->host copy of one slab
   // (on the copy stream) overlaps the kernels of the next.  Device outputs / debug
   // recording: one pass.
-  const uint32_t slab = (out_on_device || h->debug) ? QN : std::min<uint32_t>(QN, kSlabQueries);
-  const uint32_t nslabs = (QN + slab - 1) / slab;
+  // The copies are the bottleneck at large k (PCIe), so what counts is how soon the first one can
+  // start: the slabs grow from kSlabQueries / 4 to kSlabQueries.
+  std::vector<uint32_t> slab_lo{0u};
+  if (out_on_device || h->debug) {
+    slab_lo.push_back(QN);
+  } else {
+    uint32_t sz = QN > kSlabQueries ? kSlabQueries / 4 : kSlabQueries;
+    while (slab_lo.back() < QN) {
+      slab_lo.push_back(std::min<uint64_t>(QN, (uint64_t)slab_lo.back() + sz));
+      sz = std::min<uint32_t>(kSlabQueries, sz * 2);
+    }
+  }
+  const uint32_t nslabs = (uint32_t)slab_lo.size() - 1;
+  h->scratch_queries = 0;
+  for (uint32_t s = 0; s < nslabs; s++) h->scratch_queries = std::max(h->scratch_queries, slab_lo[s + 1] - slab_lo[s]);
   if (!out_on_device) {
     while (h->slab_ev.size() < nslabs) {
       cudaEvent_t e;
@@ -1634,7 +1651,7 @@ static int query_common(pqt_index* h, const float* Q, int q_on_device, uint32_t 
     }
   }
   auto issue_copy = [&](uint32_t s) -> int {
-    const uint32_t q0 = s * slab, n = std::min(slab, QN - q0);
+    const uint32_t q0 = slab_lo[s], n = slab_lo[s + 1] - q0;
     CU_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->slab_ev[s], 0));
     CU_TRY(h, cudaMemcpyAsync(idx + (size_t)q0 * k, d_out_idx + (size_t)q0 * k, (size_t)n * k * 4,
                               cudaMemcpyDeviceToHost, h->copy_stream));
@@ -1643,7 +1660,7 @@ static int query_common(pqt_index* h, const float* Q, int q_on_device, uint32_t 
     return PQT_OK;
   };
   for (uint32_t s = 0; s < nslabs; s++) {
-    const uint32_t q0 = s * slab, n = std::min(slab, QN - q0);
+    const uint32_t q0 = slab_lo[s], n = slab_lo[s + 1] - q0;
     const float* q = dQ + (size_t)q0 * h->dim;
     float* od = d_out_dist + (size_t)q0 * k;
     uint32_t* oi = d_out_idx + (size_t)q0 * k;
@@ -1654,8 +1671,8 @@ static int query_common(pqt_index* h, const float* Q, int q_on_device, uint32_t 
         CU_TRY(h, cudaEventRecord(h->ev[5], h->stream));
       }
     } else {
-      CU_TRY(h, h->s_val.ensure((size_t)n * max_vec * 4));
-      CU_TRY(h, h->s_idx.ensure((size_t)n * max_vec * 4));
+      CU_TRY(h, h->s_val.ensure((size_t)h->scratch_queries * max_vec * 4));
+      CU_TRY(h, h->s_idx.ensure((size_t)h->scratch_queries * max_vec * 4));
       PQ_TRY(run_scan_chain(h, q, n, k, h->s_val.as<float>(), h->s_idx.as<uint32_t>(), nullptr, nullptr, big));
       if (h->profile) CU_TRY(h, cudaEventRecord(h->ev[4], h->stream));
       PQ_TRY(run_rank(h, h->s_val.as<float>(), h->s_idx.as<uint32_t>(), n, max_vec, k, od, oi));
