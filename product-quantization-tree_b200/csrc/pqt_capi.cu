@@ -755,6 +755,9 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
         CU_TRY(h, h->g_phases.ensure((size_t)QN * 8 * 8));
         ra.phase_dbg = h->g_phases.as<unsigned long long>();
       }
+      CU_TRY(h, h->d_sched.ensure(64));
+      CU_TRY(h, cudaMemsetAsync(h->d_sched.as<uint32_t>() + 1, 0, 4, h->stream));
+      ra.next_query = h->d_sched.as<uint32_t>() + 1;
       const size_t rsmem = rank2_smem_bytes(max_vec);
       if (rsmem > 48 * 1024)
         CU_TRY(h, cudaFuncSetAttribute(rank2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
@@ -792,7 +795,7 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
       const int env_dedupe = getenv("PQT_RERANK_DEDUPE") ? atoi(getenv("PQT_RERANK_DEDUPE")) : 1;  // A/B runs
       const int env_tpb = getenv("PQT_RERANK_TPB") ? atoi(getenv("PQT_RERANK_TPB")) : 512;
       g.dedupe = env_dedupe ? 1u : 0u;
-      CU_TRY(h, h->d_sched.ensure(4));
+      CU_TRY(h, h->d_sched.ensure(64));
       CU_TRY(h, cudaMemsetAsync(h->d_sched.p, 0, 4, h->stream));
       g.next_query = h->d_sched.as<uint32_t>();
       if (h->debug) {
@@ -2006,6 +2009,9 @@ int pqt_shard_rank(pqt_index* h, uint32_t q_own, uint32_t k, uint32_t* idx, floa
     a.fast_rank = (h->prm.rank_mode == 0) ? 1u : 0u;
       a.n_vec = h->s_nvec.as<uint32_t>() + q0;
     a.ridx = h->have_roots ? h->s_ridx.as<uint16_t>() + (size_t)q0 * max_vec : nullptr;
+    CU_TRY(h, h->d_sched.ensure(64));
+    CU_TRY(h, cudaMemsetAsync(h->d_sched.as<uint32_t>() + 1, 0, 4, h->stream));
+    a.next_query = h->d_sched.as<uint32_t>() + 1;
     rank2_kernel<false><<<std::min<uint32_t>(n, (uint32_t)h->num_sms * 4), kRank2Threads, smem, h->stream>>>(a);
     CU_TRY(h, cudaGetLastError());
     h->stats.kernel_launches++;

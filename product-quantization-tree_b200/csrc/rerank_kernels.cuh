@@ -1438,6 +1438,10 @@ struct Rank2Args {
   uint32_t fast_rank;     // 1: composite-key sort first; 0: the network only
   unsigned long long* phase_dbg;  // optional [QN][8] clock64 stamps (layout of rerank_kernel's;
                                   // slot 1 = end of the sort proper instead of the LUT wait)
+  uint32_t* next_query;           // optional work counter (zeroed before the launch): CTAs draw their
+                                  // queries from it.  Queries with tie groups take twice as long as
+                                  // the others, so a static stride leaves the kernel waiting for its
+                                  // unluckiest CTA (measured: slowest CTA 1.28 x the mean)
 };
 
 inline size_t rank2_smem_bytes(uint32_t max_vec) { return (size_t)max_vec * 8 + 512 + 64; }
@@ -1461,8 +1465,17 @@ __global__ void __launch_bounds__(kRank2Threads, 4) rank2_kernel(Rank2Args a) {
   uint16_t* s_pay = reinterpret_cast<uint16_t*>(s_cmp);
   const Grp G{threadIdx.x, blockDim.x, 0};
   const uint32_t lane = threadIdx.x & 31u;
-  for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
+  __shared__ uint32_t s_next;
+  uint32_t qi = blockIdx.x;
+  if (a.next_query) {
+    if (threadIdx.x == 0) s_next = atomicAdd(a.next_query, 1u);
     __syncthreads();
+    qi = s_next;
+  }
+  for (; qi < a.QN;) {
+    __syncthreads();
+    if (a.next_query && threadIdx.x == 0) s_next = atomicAdd(a.next_query, 1u);  // read after the next barrier
+    const uint32_t q_after = qi + gridDim.x;
     unsigned long long* ph = a.phase_dbg ? a.phase_dbg + (size_t)qi * 8 : nullptr;
     if (threadIdx.x == 0) {
       *s_flag = 0;
@@ -1567,6 +1580,7 @@ __global__ void __launch_bounds__(kRank2Threads, 4) rank2_kernel(Rank2Args a) {
       ph[7] = ((unsigned long long)blockIdx.x << 32) | ((unsigned long long)(s_misc[9] & 15u) << 48) |
               ((unsigned long long)min(s_misc[8] >> 4, 0x3FFFFu) << 14) | (nv << 1) | (done ? 1u : 0u) | (1ull << 63);
     }
+    qi = a.next_query ? s_next : q_after;  // s_next: written before at least one barrier of this iteration
   }
 }
 
