@@ -49,6 +49,8 @@ struct BinsBigArgs {
   uint32_t* n_vec;      // [QN]
   uint32_t* dbg_bins;   // [QN][list_cap] or null
   uint32_t* dbg_nbins;  // [QN] or null
+  uint32_t* next_query;  // optional work counter (zeroed before the launch): the number of rounds
+                         // differs from query to query, so CTAs draw their queries
 };
 
 // dynamic smem: l_val[512] | l_idx[512] | r_dist[1024] | r_bin[1024] | in_val[128] | in_idx[128]
@@ -74,8 +76,17 @@ __global__ void __launch_bounds__(kBigThreads) bins_big_kernel(BinsBigArgs a) {
   const uint32_t factor = K * K;  // uint32 wrap (:3101)
   const size_t seq_total = (size_t)kNumAnisoDir * kNumDistSeq;
 
-  for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
+  __shared__ uint32_t s_next;
+  uint32_t qi = blockIdx.x;
+  if (a.next_query) {
+    if (tid == 0) s_next = atomicAdd(a.next_query, 1u);
     __syncthreads();
+    qi = s_next;
+  }
+  for (; qi < a.QN;) {
+    __syncthreads();
+    if (a.next_query && tid == 0) s_next = atomicAdd(a.next_query, 1u);  // read at the end of the iteration
+    const uint32_t q_this = qi;
     for (uint32_t e = tid; e < a.list_cap; e += blockDim.x) list[e] = 0;  // memset of _bins (:3716)
     // ---- selectBinKernel2D2Parts: parts (0,1) and (2,3)
     for (uint32_t pi = 0; pi < 2; pi++) {
@@ -176,6 +187,7 @@ __global__ void __launch_bounds__(kBigThreads) bins_big_kernel(BinsBigArgs a) {
       offset += total;
     }
     if (tid == 0) a.n_vec[qi] = offset < a.max_vec ? offset : a.max_vec;
+    qi = a.next_query ? s_next : q_this + gridDim.x;
   }
 }
 

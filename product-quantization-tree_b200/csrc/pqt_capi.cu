@@ -485,8 +485,11 @@ int launch_bins_p4(pqt_index* h, const pqt_params& P, uint32_t max_vec, uint32_t
       h->have_roots = true;
     }
     const size_t smem = bins3_smem_bytes(P.max_bins, fine ? kBins3FineProbes : kProbesPerThread, h->have_roots);
-    // static query assignment: never launch more CTAs than are resident at once
+    // never launch more CTAs than are resident at once; they draw their queries from a counter
     grid = std::min<uint32_t>(grid, (uint32_t)h->num_sms * std::max<uint32_t>(1u, std::min<uint32_t>(6u, (uint32_t)((227 * 1024) / (smem + 1024)))));
+    CU_TRY(h, h->d_sched.ensure(64));
+    CU_TRY(h, cudaMemsetAsync(h->d_sched.as<uint32_t>() + 2, 0, 4, h->stream));
+    a.next_query = h->d_sched.as<uint32_t>() + 2;
 #define LAUNCH_BINS3(NP, PPTV)                                                                       \
   do {                                                                                               \
     if (smem > 48 * 1024)                                                                            \
@@ -641,6 +644,9 @@ int run_scan_chain(pqt_index* h, const float* dQ, uint32_t QN, uint32_t k, float
     if (smem > 48 * 1024)
       CU_TRY(h, cudaFuncSetAttribute(bins_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint32_t grid = std::min<uint32_t>(QN, (uint32_t)h->num_sms * 2);
+    CU_TRY(h, h->d_sched.ensure(64));
+    CU_TRY(h, cudaMemsetAsync(h->d_sched.as<uint32_t>() + 2, 0, 4, h->stream));
+    a.next_query = h->d_sched.as<uint32_t>() + 2;
     bins_big_kernel<<<grid, kBigThreads, smem, h->stream>>>(a);
     CU_TRY(h, cudaGetLastError());
     h->stats.kernel_launches++;

@@ -220,6 +220,8 @@ struct Bins3Args {
   uint32_t* root_pos;  // [QN][max_vec]
   uint16_t* ridx;      // [QN][max_vec]
   uint32_t* n_root;    // [QN]
+  uint32_t* next_query;  // optional work counter (zeroed before the launch): the walk of a query
+                         // stops after one to several probe batches, so CTAs draw their queries
 };
 
 constexpr int kBins3Batch = kBins2Threads * kProbesPerThread;  // 4096
@@ -255,7 +257,14 @@ __global__ void __launch_bounds__(kBins2Threads, 6) bins3_kernel(Bins3Args a) {
   const MagicMod hash = a.hash;
   const uint32_t* __restrict__ bitmap = a.dir.bitmap;
 
-  for (uint32_t qi = blockIdx.x; qi < a.QN; qi += gridDim.x) {
+  __shared__ uint32_t s_next;
+  uint32_t qi = blockIdx.x;
+  if (a.next_query) {
+    if (threadIdx.x == 0) s_next = atomicAdd(a.next_query, 1u);
+    __syncthreads();
+    qi = s_next;
+  }
+  for (; qi < a.QN;) {
     __syncthreads();
     const uint32_t* gi = a.idx16 + (size_t)qi * p * 16;
     for (uint32_t e = threadIdx.x; e < NPAIRS * 256; e += blockDim.x) {
@@ -265,7 +274,11 @@ __global__ void __launch_bounds__(kBins2Threads, 6) bins3_kernel(Bins3Args a) {
       if (j1 < p) v = v * K + __ldg(gi + j1 * 16 + r1);
       pairs[e] = v;
     }
-    if (threadIdx.x == 0) list[0] = 0;  // slot 0 keeps the memset value (:3561)
+    if (threadIdx.x == 0) {
+      list[0] = 0;  // slot 0 keeps the memset value (:3561)
+      if (a.next_query) s_next = atomicAdd(a.next_query, 1u);  // read at the end of the iteration
+    }
+    const uint32_t q_this = qi;
     __syncthreads();
 
     uint32_t n_out = 0;
@@ -419,6 +432,7 @@ __global__ void __launch_bounds__(kBins2Threads, 6) bins3_kernel(Bins3Args a) {
       a.n_vec[qi] = offset < a.max_vec ? offset : a.max_vec;
       if (dedupe) a.n_root[qi] = n_root;
     }
+    qi = a.next_query ? s_next : q_this + gridDim.x;
   }
 }
 
