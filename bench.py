@@ -632,7 +632,7 @@ def run_b200(a, rank, world, local_rank):
                     "d2h_bytes_per_step": int(QN * k * 8), "ms_per_step": r["e2e_ms"] / a.steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None,
-                         "kernel": "adc_stream_kernel<INBOX> (ADC scan of the own shard, results stored to the owners over NVLink)" if sharded else
+                         "kernel": "adc_inbox_kernel (ADC scan of the own shard, one warp per query, results stored to the owners over NVLink)" if sharded else
                          ("adc_stream_kernel (ADC scan; ranking = rank2_kernel, stage 'sort')" if split
                           else "rerank_kernel (ADC scan + ranking fused)"),
                          "peak_source": peak_src, "ms_per_launch": scan_ms,

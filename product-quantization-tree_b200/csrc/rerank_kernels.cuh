@@ -1,12 +1,18 @@
-// rerank_kernels.cuh -- second-generation per-query kernels:
+// rerank_kernels.cuh -- the per-query kernels of Steps D, E1 and E2:
 //
-//   bins2_kernel    Steps D+E1 with nibble-packed traversal codes, per-query pair
-//                   tables for the Horner hash, multiply-shift modulo, and all probes
-//                   of a query issued in a few large batches (no per-trial barriers)
-//   rerank_kernel   Step E2 fused: ADC scan -> shared memory -> ranking -> first k,
-//                   one persistent CTA per SM; the (val, idx) candidate arrays never
-//                   touch HBM
-//   rank2_kernel    ranking only (multi-GPU path: after the shards are assembled)
+//   bins3_kernel / bins4_kernel   Steps D+E1: nibble-packed traversal codes in static visiting
+//                   orders, per-query pair tables for the Horner hash, multiply-shift modulo,
+//                   bitmap + rank directory; bins3 stops as soon as the candidate list is full
+//                   (dense indexes), bins4 walks 16 384 codes at a time (sparse indexes);
+//                   bins2_kernel (query_kernels.cuh) serves p > 4
+//   adc_stream_kernel   Step E2, distance part: the streaming ADC scan of the split pipeline
+//                   (persistent CTA per SM, TMA-staged tables, double-buffered code rows)
+//   rank2_kernel    Step E2, ranking + emit: composite-key sort, repair, tie resolver; one CTA
+//                   per query, queries drawn from a work counter
+//   rerank_kernel   Step E2 fused (scan -> shared memory -> ranking -> first k in one persistent
+//                   kernel): short candidate lists and PQT_SCAN_MODE=fused
+//   dispatch_kernel / adc_inbox_kernel   multi-GPU: candidates routed to the shard that holds
+//                   them; inbox scan, one warp per query, distances stored to the owners
 //
 // Ranking.  The reference ranks with a bitonic network over max_vec slots
 // (pqt/bitonicSort.cuh:16-78).  grp_sort_pairs executes the same compare-exchanges (same
