@@ -340,6 +340,33 @@ def test_sharded_handle_rejects_the_single_gpu_call(case_small):
     t.close()
 
 
+def test_eight_parts_take_the_generic_bin_walk():
+    """p = 8 (the GIST-style tree shape) with a traversal width of 8 (k1 * c2 = 8, 8^8 codes):
+    bins2_kernel instead of the p <= 4 kernels, generic table kernel, LP = 16"""
+    import conftest
+    c = conftest.make_case(N=6000, QN=16, p=8, c1=8, c2=4, LP=16, hash_size=65537, seed=13, k1=2)
+    QN = c["Q"].shape[0]
+    t = make_gpu_index(c)
+    for k in (16, 256):
+        d0, i0 = oracle_query(c, k)
+        i1, d1 = t.queryKNN(c["Q"], QN, k)
+        assert np.array_equal(d1, d0)
+        assert np.array_equal(i1, i0)
+    t.close()
+
+
+def test_traversal_tables_beyond_the_supported_size_are_rejected():
+    """p = 8 with the default traversal width 16 would need 16^8 codes (the reference's uint
+    nVec wraps to 0 there, pqt/ProTree.cu:139): refused with an error, not answered wrongly"""
+    import conftest
+    import pqt_b200
+    c = conftest.make_case(N=3000, QN=4, p=8, c1=8, c2=4, LP=16, hash_size=65537, seed=13, k1=2)
+    t = make_gpu_index(c, k1=8)  # k1 * c2 = 32 -> traversal width 16
+    with pytest.raises(pqt_b200.PqtError):
+        t.queryKNN(c["Q"], 4, 16)
+    t.close()
+
+
 # ---- a11: the 1-B variant queryBIGKNNRerank2 ---------------------------------------------
 
 def _big_check(c, hash_size, ks):
