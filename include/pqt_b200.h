@@ -209,6 +209,18 @@ int pqt_get_lines(const pqt_index *h, uint32_t *lines);
 int pqt_get_codes_binorder(const pqt_index *h, uint64_t pos0, uint64_t n, uint32_t *codes);
 int pqt_get_db_size(const pqt_index *h, uint32_t *N, uint32_t *line_parts);
 
+/* ---- compact index file (no reference counterpart) ---------------------------------
+ * The reference's index files are two dense HASH_SIZE arrays (.prefix / .count, 3.2 GB at
+ * 4e8 bins), .dbIdx and the line codes by vector id (tool_createdb.cpp:105-114,
+ * test/test1B.cpp:1181-1233); loading them rebuilds the directory and re-orders the codes.
+ * pqt_save_index writes what the handle holds -- bitmap, rank directory, compact prefix,
+ * dbIdx and the line codes in bin order (of a sharded handle: its own slice) -- and
+ * pqt_load_index restores it: header checks against the handle's tree, hash_size and shard,
+ * then plain uploads (ids, centroid numbers and bin lists are range-checked on the device).
+ * pqt_get_db / pqt_get_lines still expand the reference's arrays from a loaded index. */
+int pqt_save_index(const pqt_index *h, const char *path);
+int pqt_load_index(pqt_index *h, const char *path);
+
 /* ---- multi-GPU: bin-range shards ----------------------------------------------
  * The reference is single-GPU; its 1-B mode keeps the line codes in pinned host memory
  * (test/test1B.cpp:1121-1192).  Here the bin-ordered code array is cut into `world` contiguous

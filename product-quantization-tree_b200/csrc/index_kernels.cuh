@@ -164,6 +164,13 @@ __global__ void check_below_kernel(const uint32_t* v, size_t n, uint32_t bound, 
     bad |= v[i] >= bound;
   if (bad) atomicOr(flag, 1u);
 }
+// flag = 1 unless v[0] <= v[1] <= ... <= v[n-1]
+__global__ void check_monotone_kernel(const uint32_t* v, size_t n, uint32_t* flag) {
+  bool bad = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n; i += (size_t)gridDim.x * blockDim.x)
+    bad |= v[i] > v[i + 1];
+  if (bad) atomicOr(flag, 1u);
+}
 // flag = 1 if a non-empty bin's list [prefix, prefix + count) leaves the N ids
 __global__ void check_lists_kernel(const uint32_t* counts, const uint32_t* prefix, size_t hs, uint32_t N,
                                    uint32_t* flag) {

@@ -1237,6 +1237,149 @@ int pqt_set_lines(pqt_index* h, const uint32_t* lines, uint32_t N, uint32_t line
   return PQT_OK;
 }
 
+// ---- compact index file: the resident layout as it is ----------------------------------
+//   The reference's files keep two dense hash_size arrays (.prefix / .count,
+// 3.2 GB at HASH_SIZE 4e8) and the line codes by vector id; loading them means rebuilding the
+// directory and re-ordering 128 GB of codes.  This file holds what the handle holds: header,
+// then bitmap | rank_base | cprefix | dbIdx (bin order) | codes (bin order, this handle's
+// slice), each as u64 byte count + bytes.
+namespace {
+struct IndexFileHeader {
+  char magic[8];  // "PQTB2IDX"
+  uint32_t version, dim, p, c1, c2, N, hash_size, n_nonempty, LP, rank, world, pos_lo, pos_hi, reserved;
+};
+static_assert(sizeof(IndexFileHeader) == 64, "header layout");
+constexpr size_t kFileChunk = (size_t)64 << 20;
+
+struct HostStage {
+  void* p = nullptr;
+  ~HostStage() {
+    if (p) cudaFreeHost(p);
+  }
+};
+struct FileCloser {
+  FILE* f = nullptr;
+  ~FileCloser() {
+    if (f) fclose(f);
+  }
+};
+
+int write_section(const pqt_index* h, FILE* f, const void* dev, size_t bytes, void* stage) {
+  const uint64_t n64 = bytes;
+  if (fwrite(&n64, 8, 1, f) != 1) return fail(h, PQT_ERR_IO, "short write");
+  for (size_t off = 0; off < bytes; off += kFileChunk) {
+    const size_t n = std::min(kFileChunk, bytes - off);
+    CU_TRY(h, cudaMemcpy(stage, static_cast<const char*>(dev) + off, n, cudaMemcpyDeviceToHost));
+    if (fwrite(stage, 1, n, f) != n) return fail(h, PQT_ERR_IO, "short write");
+  }
+  return PQT_OK;
+}
+
+int read_section(pqt_index* h, FILE* f, DevBuf& dst, size_t want_bytes, size_t alloc_bytes, void* stage,
+                 const char* what) {
+  uint64_t n64 = 0;
+  if (fread(&n64, 8, 1, f) != 1 || n64 != want_bytes)
+    return fail(h, PQT_ERR_IO, "index file: section '%s' holds %llu bytes, expected %llu", what,
+                (unsigned long long)n64, (unsigned long long)want_bytes);
+  CU_TRY(h, dst.ensure(std::max<size_t>(alloc_bytes, 16)));
+  for (size_t off = 0; off < want_bytes; off += kFileChunk) {
+    const size_t n = std::min(kFileChunk, want_bytes - off);
+    if (fread(stage, 1, n, f) != n) return fail(h, PQT_ERR_IO, "index file: section '%s' is truncated", what);
+    CU_TRY(h, cudaMemcpy(static_cast<char*>(dst.p) + off, stage, n, cudaMemcpyHostToDevice));
+  }
+  return PQT_OK;
+}
+}  // namespace
+
+int pqt_save_index(const pqt_index* h, const char* path) {
+  if (!h || !path) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (!h->has_db || !h->has_lines) return fail(h, PQT_ERR_STATE, "pqt_save_index needs the DB and the line codes");
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  FileCloser fc;
+  fc.f = fopen(path, "wb");
+  if (!fc.f) return fail(h, PQT_ERR_IO, "cannot open %s for writing", path);
+  HostStage st;
+  CU_TRY(h, cudaMallocHost(&st.p, kFileChunk));
+  IndexFileHeader hd{};
+  memcpy(hd.magic, "PQTB2IDX", 8);
+  hd.version = 1;
+  hd.dim = h->dim; hd.p = h->p; hd.c1 = h->c1; hd.c2 = h->c2;
+  hd.N = h->N; hd.hash_size = h->db_hash_size; hd.n_nonempty = h->n_nonempty; hd.LP = h->LP;
+  hd.rank = h->rank; hd.world = h->world; hd.pos_lo = h->pos_lo; hd.pos_hi = h->pos_hi;
+  if (fwrite(&hd, sizeof(hd), 1, fc.f) != 1) return fail(h, PQT_ERR_IO, "short write");
+  const size_t nwords = ((size_t)h->db_hash_size + 31) >> 5, ngroups = (nwords + 7) >> 3;
+  PQ_TRY(write_section(h, fc.f, h->d_bitmap.p, ngroups * 8 * 4, st.p));
+  PQ_TRY(write_section(h, fc.f, h->d_rank_base.p, (ngroups + 1) * 4, st.p));
+  PQ_TRY(write_section(h, fc.f, h->d_cprefix.p, ((size_t)h->n_nonempty + 1) * 4, st.p));
+  PQ_TRY(write_section(h, fc.f, h->d_dbidx.p, (size_t)h->N * 4, st.p));
+  PQ_TRY(write_section(h, fc.f, h->d_codes.p, (size_t)(h->pos_hi - h->pos_lo) * h->LP * 4, st.p));
+  if (fflush(fc.f) != 0) return fail(h, PQT_ERR_IO, "short write");
+  return PQT_OK;
+}
+
+int pqt_load_index(pqt_index* h, const char* path) {
+  if (!h || !path) return PQT_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (!h->c1) return fail(h, PQT_ERR_STATE, "pqt_load_index needs the tree (pqt_read_tree / pqt_set_tree)");
+  FileCloser fc;
+  fc.f = fopen(path, "rb");
+  if (!fc.f) return fail(h, PQT_ERR_IO, "cannot open %s", path);
+  IndexFileHeader hd{};
+  if (fread(&hd, sizeof(hd), 1, fc.f) != 1 || memcmp(hd.magic, "PQTB2IDX", 8) != 0 || hd.version != 1)
+    return fail(h, PQT_ERR_IO, "%s is not a pqt_b200 index file (version 1)", path);
+  if (hd.dim != h->dim || hd.p != h->p || hd.c1 != h->c1 || hd.c2 != h->c2)
+    return fail(h, PQT_ERR_INVALID, "index file was built for a %u-d tree with p=%u c1=%u c2=%u", hd.dim, hd.p, hd.c1, hd.c2);
+  if (hd.hash_size != h->prm.hash_size)
+    return fail(h, PQT_ERR_INVALID, "index file uses hash_size %u, the handle %u (pqt_set_params)", hd.hash_size, h->prm.hash_size);
+  if (hd.rank != h->rank || hd.world != h->world)
+    return fail(h, PQT_ERR_INVALID, "index file holds shard %u of %u, the handle is shard %u of %u (pqt_set_shard)",
+                hd.rank, hd.world, h->rank, h->world);
+  const uint32_t lo = (uint32_t)((uint64_t)hd.N * hd.rank / hd.world), hi = (uint32_t)((uint64_t)hd.N * (hd.rank + 1) / hd.world);
+  if (!hd.hash_size || hd.pos_lo != lo || hd.pos_hi != hi || hd.n_nonempty > hd.hash_size || hd.n_nonempty > hd.N)
+    return fail(h, PQT_ERR_IO, "index file header is inconsistent");
+  PQ_TRY(check_lp(h, hd.LP));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  h->has_db = false;
+  h->has_lines = false;
+  HostStage st;
+  CU_TRY(h, cudaMallocHost(&st.p, kFileChunk));
+  const size_t nwords = ((size_t)hd.hash_size + 31) >> 5, ngroups = (nwords + 7) >> 3;
+  PQ_TRY(read_section(h, fc.f, h->d_bitmap, ngroups * 8 * 4, ngroups * 8 * 4, st.p, "bitmap"));
+  PQ_TRY(read_section(h, fc.f, h->d_rank_base, (ngroups + 1) * 4, (ngroups + 1) * 4, st.p, "rank_base"));
+  PQ_TRY(read_section(h, fc.f, h->d_cprefix, ((size_t)hd.n_nonempty + 1) * 4, ((size_t)hd.n_nonempty + 2) * 4, st.p, "cprefix"));
+  PQ_TRY(read_section(h, fc.f, h->d_dbidx, (size_t)hd.N * 4, (size_t)hd.N * 4, st.p, "dbIdx"));
+  const size_t code_words = (size_t)(hi - lo) * hd.LP;
+  PQ_TRY(read_section(h, fc.f, h->d_codes, code_words * 4, code_words * 4, st.p, "codes"));
+  // what a file can get wrong and a kernel would trip over: ids, centroid numbers, the list end
+  DevBuf flag;
+  CU_TRY(h, flag.ensure(8));
+  CU_TRY(h, cudaMemsetAsync(flag.p, 0, 8, h->stream));
+  if (hd.N) check_below_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->d_dbidx.as<uint32_t>(), hd.N, hd.N, flag.as<uint32_t>());
+  if (code_words) check_codes_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->d_codes.as<uint32_t>(), code_words, h->c1, flag.as<uint32_t>() + 1);
+  check_below_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->d_cprefix.as<uint32_t>(), (size_t)hd.n_nonempty + 1, hd.N + 1, flag.as<uint32_t>());
+  check_monotone_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->d_cprefix.as<uint32_t>(), (size_t)hd.n_nonempty + 1, flag.as<uint32_t>());
+  CU_TRY(h, cudaGetLastError());
+  uint32_t bad[2] = {0, 0}, last = 0;
+  CU_TRY(h, cudaMemcpyAsync(bad, flag.p, 8, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaMemcpyAsync(&last, h->d_cprefix.as<uint32_t>() + hd.n_nonempty, 4, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  if (bad[0] || bad[1] || last != hd.N)
+    return fail(h, PQT_ERR_INVALID, "index file holds ids >= N, centroid numbers >= c1 or bin lists that leave the N ids");
+  h->N = hd.N;
+  h->db_hash_size = hd.hash_size;
+  h->n_nonempty = hd.n_nonempty;
+  h->pos_lo = lo;
+  h->pos_hi = hi;
+  h->has_db = true;
+  h->LP = hd.LP;
+  h->sl = h->dim / hd.LP;
+  PQ_TRY(compute_cbd(h, hd.LP));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  h->has_lines = true;
+  return PQT_OK;
+}
+
 int pqt_get_db_size(const pqt_index* h, uint32_t* N, uint32_t* line_parts) {
   if (!h) return PQT_ERR_INVALID;
   if (N) *N = h->has_db ? h->N : 0;

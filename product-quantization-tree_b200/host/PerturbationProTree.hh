@@ -143,6 +143,12 @@ class PerturbationProTree {
     return v;
   }
 
+  // ---- compact index file (no counterpart in the reference): the resident directory, dbIdx and
+  // bin-ordered line codes as they are; loading skips the dense .prefix/.count arrays and the
+  // re-ordering of the codes
+  void saveIndex(const std::string& _name) { chk(pqt_save_index(h_, _name.c_str())); }
+  void loadIndex(const std::string& _name) { chk(pqt_load_index(h_, _name.c_str())); }
+
   pqt_index* handle() { return h_; }
 
  private:

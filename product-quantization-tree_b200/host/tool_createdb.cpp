@@ -44,6 +44,7 @@ int main(int argc, char** argv) {
   fl.add("basename", "tmp", "prefix for generated data");
   fl.add("dataset", "base.umem", "path to vector dataset");
   fl.add("train", "20000", "vectors used for codebook training (reference literal)");
+  fl.add("compact", "0", "1: also write <pre>_<lineparts>.pqtx, the resident index as one file (tool_query --compact 1 loads it)");
   try {
     if (!fl.parse(argc, argv,
                   "This tool builds a database for a given dataset of vectors\n"
@@ -111,6 +112,11 @@ int main(int argc, char** argv) {
     dump(pre + ".prefix", ppt.getBinPrefix());
     dump(pre + ".count", ppt.getBinCounts());
     dump(pre + ".dbIdx", ppt.getDBIdx());
+    if (fl.num("compact") != 0) {
+      const std::string cname = pre + "_" + std::to_string(LP) + ".pqtx";
+      ppt.saveIndex(cname);
+      std::cout << "written " << cname << std::endl;
+    }
   } catch (const std::exception& e) {
     std::cerr << "tool_createdb: " << e.what() << std::endl;
     return 1;

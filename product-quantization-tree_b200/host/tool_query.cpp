@@ -44,6 +44,7 @@ int main(int argc, char** argv) {
   fl.add("queries", "0", "number of queries (0 = all in the query set)");
   fl.add("groundtruth", "", "optional .imem with exact neighbours: prints recall@1");
   fl.add("out", "", "optional output prefix: writes <out>.idx.imem and <out>.dist.fmem");
+  fl.add("compact", "0", "1: load <pre>_<lineparts>.pqtx (tool_createdb --compact 1) instead of .prefix/.count/.dbIdx/.lines");
   try {
     if (!fl.parse(argc, argv,
                   "This tool queries a database built by tool_createdb\n"
@@ -76,31 +77,36 @@ int main(int argc, char** argv) {
     std::cout << "codebook exists, reading from " << codebook_file << std::endl;
     ppt.readTreeFromFile(codebook_file);
 
-    // The database size is what tool_createdb wrote, i.e. the length of .dbIdx (the reference
-    // takes DataReader.num(); --chunksize is not the DB size).  Every file must agree with it.
-    const std::string idx_file = pre + ".dbIdx", lines_file = pre + "_" + std::to_string(LP) + ".lines";
-    if (stat(idx_file.c_str(), &sb) != 0) throw std::runtime_error("cannot stat " + idx_file);
-    if (sb.st_size == 0 || sb.st_size % 4) throw std::runtime_error(idx_file + ": size is not a multiple of 4");
-    if ((uint64_t)sb.st_size / 4 > 0xFFFFFFFFull) throw std::runtime_error(idx_file + ": too many vectors");
-    const uint32_t base_num = (uint32_t)(sb.st_size / 4);
-    if (base_num > DataReader.num())
-      throw std::runtime_error("the database holds " + std::to_string(base_num) + " vectors, the dataset only " +
-                               std::to_string(DataReader.num()));
-    if (stat(lines_file.c_str(), &sb) != 0) throw std::runtime_error("cannot stat " + lines_file);
-    if ((uint64_t)sb.st_size != (uint64_t)base_num * LP * 4)
-      throw std::runtime_error(lines_file + ": size does not match " + std::to_string(base_num) + " vectors x " +
-                               std::to_string(LP) + " line parts");
-    std::vector<pqt::uint> binPrefix = slurp<pqt::uint>(pre + ".prefix", hashsize);
-    std::vector<pqt::uint> binCounts = slurp<pqt::uint>(pre + ".count", hashsize);
-    std::vector<pqt::uint> dbIdx = slurp<pqt::uint>(pre + ".dbIdx", base_num);
-    std::vector<float> hLines = slurp<float>(lines_file, (size_t)base_num * LP);
+    if (fl.num("compact") != 0) {
+      // the resident index as one file: no dense .prefix/.count arrays, no re-ordering of the codes
+      ppt.loadIndex(pre + "_" + std::to_string(LP) + ".pqtx");
+    } else {
+      // The database size is what tool_createdb wrote, i.e. the length of .dbIdx (the reference
+      // takes DataReader.num(); --chunksize is not the DB size).  Every file must agree with it.
+      const std::string idx_file = pre + ".dbIdx", lines_file = pre + "_" + std::to_string(LP) + ".lines";
+      if (stat(idx_file.c_str(), &sb) != 0) throw std::runtime_error("cannot stat " + idx_file);
+      if (sb.st_size == 0 || sb.st_size % 4) throw std::runtime_error(idx_file + ": size is not a multiple of 4");
+      if ((uint64_t)sb.st_size / 4 > 0xFFFFFFFFull) throw std::runtime_error(idx_file + ": too many vectors");
+      const uint32_t base_num = (uint32_t)(sb.st_size / 4);
+      if (base_num > DataReader.num())
+        throw std::runtime_error("the database holds " + std::to_string(base_num) + " vectors, the dataset only " +
+                                 std::to_string(DataReader.num()));
+      if (stat(lines_file.c_str(), &sb) != 0) throw std::runtime_error("cannot stat " + lines_file);
+      if ((uint64_t)sb.st_size != (uint64_t)base_num * LP * 4)
+        throw std::runtime_error(lines_file + ": size does not match " + std::to_string(base_num) + " vectors x " +
+                                 std::to_string(LP) + " line parts");
+      std::vector<pqt::uint> binPrefix = slurp<pqt::uint>(pre + ".prefix", hashsize);
+      std::vector<pqt::uint> binCounts = slurp<pqt::uint>(pre + ".count", hashsize);
+      std::vector<pqt::uint> dbIdx = slurp<pqt::uint>(pre + ".dbIdx", base_num);
+      std::vector<float> hLines = slurp<float>(lines_file, (size_t)base_num * LP);
 
-    ppt.setDB(base_num, binPrefix.data(), binCounts.data(), dbIdx.data());
-    ppt.setLines(hLines.data(), base_num, LP);
-    binPrefix.clear();
-    binPrefix.shrink_to_fit();
-    binCounts.clear();
-    binCounts.shrink_to_fit();
+      ppt.setDB(base_num, binPrefix.data(), binCounts.data(), dbIdx.data());
+      ppt.setLines(hLines.data(), base_num, LP);
+      binPrefix.clear();
+      binPrefix.shrink_to_fit();
+      binCounts.clear();
+      binCounts.shrink_to_fit();
+    }
 
     std::vector<pqt::uint> allIdx((size_t)QN * k);
     std::vector<float> allDist((size_t)QN * k);

@@ -26,7 +26,7 @@ EXPORTS = [
     "pqt_shard_dispatch", "pqt_shard_scan_p2p", "pqt_shard_rank", "pqt_profile_enable", "pqt_get_stats", "pqt_reset_stats",
     "pqt_debug_enable", "pqt_debug_stage",
     "pqt_assign_bins", "pqt_set_db_from_bins", "pqt_line_dist_begin", "pqt_line_dist_chunk",
-    "pqt_line_dist_end", "pqt_get_codes_binorder",
+    "pqt_line_dist_end", "pqt_get_codes_binorder", "pqt_save_index", "pqt_load_index",
 ]
 
 X_F32, X_U8 = 0, 1
@@ -108,6 +108,8 @@ def lib():
                                           C.c_uint32, C.c_void_p]
         L.pqt_line_dist_end.argtypes = [C.c_void_p]
         L.pqt_get_codes_binorder.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.pqt_save_index.argtypes = [C.c_void_p, C.c_char_p]
+        L.pqt_load_index.argtypes = [C.c_void_p, C.c_char_p]
         L.pqt_get_db.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pqt_get_lines.argtypes = [C.c_void_p, C.c_void_p]
         L.pqt_get_db_size.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
@@ -278,6 +280,14 @@ class PerturbationProTree:
             out = np.zeros((n, lp), np.uint32)
         self._chk(self._L.pqt_get_codes_binorder(self._h, pos0, n, out.ctypes.data))
         return out
+
+    def saveIndex(self, path):
+        """the resident index (directory, dbIdx, bin-ordered codes of this handle's slice) as one file"""
+        self._chk(self._L.pqt_save_index(self._h, os.fsencode(path)))
+
+    def loadIndex(self, path):
+        """restores a saveIndex file; the tree, hash_size and shard of the handle must match"""
+        self._chk(self._L.pqt_load_index(self._h, os.fsencode(path)))
 
     def dbSize(self):
         n, lp = C.c_uint32(), C.c_uint32()

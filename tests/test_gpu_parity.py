@@ -2,6 +2,8 @@
 inputs -- bit-exact for ids, bins and every float (the kernels pin the reference's
 rounding order, so distances are compared for equality, well inside the 1e-4 relative
 tolerance north_star states)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -311,6 +313,75 @@ def _run_sharded(c, k, world, QN, **params):
     for t in ts:
         t.close()
     return oi.cpu().numpy().view(np.uint32), od.cpu().numpy()
+
+
+def test_compact_index_file_round_trip(case_small, case_lp32, tmp_path):
+    """pqt_save_index / pqt_load_index: a fresh handle with the same tree answers from the file
+    exactly like the handle that wrote it and still expands the reference's arrays; sharded
+    handles write and read their own slice; mismatching trees / shards / files are refused"""
+    import pqt_b200
+    for name, c in (("small", case_small), ("lp32", case_lp32)):
+        prm = c["prm"]
+        QN = c["Q"].shape[0]
+        d0, i0 = oracle_query(c, 256)
+        path = str(tmp_path / (name + ".pqtx"))
+        t = make_gpu_index(c)
+        t.saveIndex(path)
+        t.close()
+        t2 = pqt_b200.PerturbationProTree(prm.dim, prm.p)
+        t2.set_params(hash_size=prm.hash_size, k1=prm.k1, max_bins=prm.max_bins, max_trials=prm.max_trials,
+                      bin_threads=prm.bin_threads, max_vec_per_bin=prm.max_vec_per_bin)
+        t2.setTree(c["cb1"], c["cb2"].reshape(prm.p, prm.c1, prm.c2, prm.dim // prm.p))
+        t2.loadIndex(path)
+        i1, d1 = t2.queryKNN(c["Q"], QN, 256)
+        assert np.array_equal(i1, i0) and np.array_equal(d1, d0)
+        prefix, counts, db_idx = t2.getDB()
+        assert np.array_equal(prefix, c["prefix"]) and np.array_equal(counts, c["counts"])
+        assert np.array_equal(db_idx, c["db_idx"]) and np.array_equal(t2.getLine(), c["lines"])
+        t2.close()
+    # a shard's file holds its slice of the codes and refuses another shard's handle
+    c = case_small
+    prm = c["prm"]
+    N = c["db_idx"].size
+    path = str(tmp_path / "shard1.pqtx")
+    t = make_gpu_index(c, shard=(1, 3))
+    t.saveIndex(path)
+    t.close()
+    lo, hi = N // 3, (2 * N) // 3
+    assert os.path.getsize(path) < os.path.getsize(str(tmp_path / "small.pqtx"))
+    for shard, ok in (((1, 3), True), ((0, 3), False), (None, False)):
+        t3 = pqt_b200.PerturbationProTree(prm.dim, prm.p)
+        t3.set_params(hash_size=prm.hash_size)
+        t3.setTree(c["cb1"], c["cb2"].reshape(prm.p, prm.c1, prm.c2, prm.dim // prm.p))
+        if shard:
+            t3.setShard(*shard)
+        if ok:
+            t3.loadIndex(path)
+            assert np.array_equal(t3.getCodesBinOrder(0, hi - lo), c["lines"][c["db_idx"]][lo:hi])
+        else:
+            with pytest.raises(pqt_b200.PqtError):
+                t3.loadIndex(path)
+        t3.close()
+    # wrong tree shape, wrong hash size, truncated file, not an index file
+    t4 = pqt_b200.PerturbationProTree(prm.dim, prm.p)
+    t4.set_params(hash_size=prm.hash_size + 2)
+    t4.setTree(c["cb1"], c["cb2"].reshape(prm.p, prm.c1, prm.c2, prm.dim // prm.p))
+    with pytest.raises(pqt_b200.PqtError):
+        t4.loadIndex(str(tmp_path / "small.pqtx"))
+    t4.set_params(hash_size=prm.hash_size)
+    blob = open(str(tmp_path / "small.pqtx"), "rb").read()
+    open(str(tmp_path / "cut.pqtx"), "wb").write(blob[:len(blob) // 2])
+    open(str(tmp_path / "junk.pqtx"), "wb").write(b"x" * 4096)
+    for bad in ("cut.pqtx", "junk.pqtx", "missing.pqtx"):
+        with pytest.raises(pqt_b200.PqtError):
+            t4.loadIndex(str(tmp_path / bad))
+    with pytest.raises(pqt_b200.PqtError):
+        t4.queryKNN(c["Q"], 4, 16)  # a refused file leaves no half-loaded index behind
+    t4.loadIndex(str(tmp_path / "small.pqtx"))
+    i1, d1 = t4.queryKNN(c["Q"], c["Q"].shape[0], 256)
+    d0, i0 = oracle_query(c, 256)
+    assert np.array_equal(i1, i0) and np.array_equal(d1, d0)
+    t4.close()
 
 
 @pytest.mark.parametrize("which,world", [("small", 3), ("lp32", 2), ("dense", 3), ("dense", 1)])

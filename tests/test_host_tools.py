@@ -59,7 +59,7 @@ def test_createdb_then_query_end_to_end(tmp_path):
     common = ["--c1", str(c1), "--c2", str(c2), "--p", str(p), "--dim", str(dim), "--lineparts",
               str(LP), "--hashsize", str(hs), "--chunksize", "3000", "--basename", base,
               "--dataset", str(tmp_path / "base.umem")]
-    r = subprocess.run([TOOL_CREATEDB] + common, capture_output=True, text=True)
+    r = subprocess.run([TOOL_CREATEDB] + common + ["--compact", "1"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     pre = formats.base_name(base, dim, p, c1, c2)
     paths = formats.index_paths(pre, LP)
@@ -86,3 +86,12 @@ def test_createdb_then_query_end_to_end(tmp_path):
     d0, i0 = po.query_knn(prm, tree["cb1"], tree["cb2"], prefix, counts, db_idx, lines,
                           Q.astype(np.float32), k)
     assert np.array_equal(idx, i0) and np.array_equal(dist, d0)
+
+    # the same query from the compact index file (one file, the resident layout as it is)
+    assert os.path.getsize("%s_%d.pqtx" % (pre, LP)) < 4 * (2 * hs + N + N * LP)  # smaller than the four files
+    out2 = str(tmp_path / "res2")
+    r = subprocess.run([TOOL_QUERY] + common + ["--queryset", str(tmp_path / "query.umem"), "--k", str(k),
+                                                "--out", out2, "--compact", "1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert np.array_equal(formats.read_mem(out2 + ".idx.imem", np.uint32), i0)
+    assert np.array_equal(formats.read_mem(out2 + ".dist.fmem", np.float32), d0)
