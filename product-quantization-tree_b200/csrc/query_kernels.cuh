@@ -779,6 +779,49 @@ __global__ void __launch_bounds__(kTablesWarps * 32) tables_warp_kernel(TablesWa
           top16_done = true;
         }
       }
+      // The 1-B variant (k1 = 16 cells: 512 entries) consumes the 64 best entries per part:
+      // same selection with 23-bit keys | 9-bit entry numbers, slots 0..64 pairwise different.
+      if (a.npC == 512 && a.top_val && a.top_n == 64 && !a.dbg_aval) {
+        uint32_t c[16];
+        uint32_t umin = 0xFFFFFFFFu, umax = 0u;
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+          const uint32_t e = lane * 16 + r;
+          c[r] = __float_as_uint(sv[e]);
+          if (e < n) {
+            umin = min(umin, c[r]);
+            umax = max(umax, c[r]);
+          }
+        }
+        umin = __reduce_min_sync(0xffffffffu, umin);
+        umax = __reduce_max_sync(0xffffffffu, umax);
+        const uint32_t bits = 32u - (uint32_t)__clz((int)(umax - umin));
+        const uint32_t shift = bits > 23u ? bits - 23u : 0u;
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+          const uint32_t e = lane * 16 + r;
+          c[r] = e < n ? ((((c[r] - umin) >> shift) << 9) | e) : 0xFFFFFFFFu;
+        }
+        block_sort_u32<16>(c, lane, 32u, 32u, nullptr, 0u);  // lane t: sorted slots 16t .. 16t+15
+        uint32_t clash = 0;
+#pragma unroll
+        for (int r = 0; r < 15; r++) clash |= (((c[r] ^ c[r + 1]) >> 9) == 0u) ? 1u : 0u;
+        const uint32_t nxt = __shfl_down_sync(0xffffffffu, c[0], 1);
+        clash |= (((c[15] ^ nxt) >> 9) == 0u) ? 1u : 0u;
+        if (!(__ballot_sync(0xffffffffu, clash != 0u) & 15u)) {  // lanes 0..3: boundaries of slots 0..64
+          if (lane < 4) {
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+              const uint32_t slot = lane * 16 + r, e = c[r] & 0x1FFu;
+              const bool real = c[r] != 0xFFFFFFFFu;
+              a.top_val[((size_t)qi * a.p + part) * a.top_n + slot] = real ? sv[e] : kPadSortC;
+              a.top_idx[((size_t)qi * a.p + part) * a.top_n + slot] = real ? si[e] : kPadIdx;
+              if (slot < 16) a.idx16[((size_t)qi * a.p + part) * 16 + slot] = (slot < a.m && real) ? si[e] : 0u;
+            }
+          }
+          top16_done = true;
+        }
+      }
       if (!top16_done) {
         switch (a.npC) {  // :1639 bitonic3(shm, shmIdx, _NP2)
           case 32: warp_sort_regs<1>(sv, si, lane); break;
@@ -790,7 +833,7 @@ __global__ void __launch_bounds__(kTablesWarps * 32) tables_warp_kernel(TablesWa
         }
         if (lane < 16) a.idx16[((size_t)qi * a.p + part) * 16 + lane] = (lane < a.m) ? si[lane] : 0u;
       }
-      if (a.top_val) {
+      if (a.top_val && !top16_done) {
         for (uint32_t e = lane; e < a.top_n; e += 32) {
           a.top_val[((size_t)qi * a.p + part) * a.top_n + e] = sv[e];
           a.top_idx[((size_t)qi * a.p + part) * a.top_n + e] = si[e];
