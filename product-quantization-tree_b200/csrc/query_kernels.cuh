@@ -442,7 +442,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) adc_scan_kernel(ScanArgs a) {
 
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const uint32_t lp = lane & (LP - 1);
-  const uint32_t grp_base = lane & ~(uint32_t)(LP - 1);
 
   if (blockIdx.x >= a.QN) return;
 

@@ -880,7 +880,6 @@ __global__ void __launch_bounds__(TPB, 1) rerank_kernel(RerankArgs g) {
 
   const uint32_t lane = G.t & 31, warp = G.t >> 5, nwarps = G.n >> 5;
   const uint32_t lp = lane & (LP - 1);
-  const uint32_t grp_base = lane & ~(uint32_t)(LP - 1);
   const uint32_t cbd_b = smem_u32(s_cbd) + (CREP ? lane : lp) * 4u;
   const uint32_t* __restrict__ codes_lp = a.codes + lp;
 
