@@ -1342,6 +1342,8 @@ int pqt_load_index(pqt_index* h, const char* path) {
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   h->has_db = false;
   h->has_lines = false;
+  h->line_build = false;  // a chunked build in progress is abandoned
+  h->b_inv.release();
   HostStage st;
   CU_TRY(h, cudaMallocHost(&st.p, kFileChunk));
   const size_t nwords = ((size_t)hd.hash_size + 31) >> 5, ngroups = (nwords + 7) >> 3;
