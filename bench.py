@@ -198,13 +198,34 @@ def build_inputs(a, device):
 
 
 def cache_paths(a):
+    """Where the index files of this workload live: the first candidate directory that already
+    holds a complete set, else the first one with room for it (tmpfs first: the CPU arms
+    memory-map the files; a disk directory is the fallback on boxes with a small /dev/shm)."""
     import synthdb
     key = "n%d_d%d_p%d_c%d_%d_h%d_g%d" % (a.n, a.dim, a.p, a.c1, a.c2, a.hashsize, a.clusters)
-    d = os.path.join(a.cache_dir, key)
-    paths = synthdb.index_files(os.path.join(d, "synth"), a.dim, a.p, a.c1, a.c2, a.lineparts)
-    paths["dir"] = d
-    paths["mu"] = os.path.join(d, "mu.u8")
-    return paths
+    need = a.n * (a.lineparts * 4 + 4) + 2 * a.hashsize * 4
+
+    def paths_in(base):
+        d = os.path.join(base, key)
+        p = synthdb.index_files(os.path.join(d, "synth"), a.dim, a.p, a.c1, a.c2, a.lineparts)
+        p["dir"] = d
+        p["mu"] = os.path.join(d, "mu.u8")
+        return p
+
+    bases = [a.cache_dir, "/tmp/pqt_b200_bench", os.path.join(ROOT, "gpurun_out", "pqt_b200_bench")]
+    cands = [paths_in(b) for b in dict.fromkeys(bases)]
+    for p in cands:
+        if synthdb.files_complete(p, a.n, a.hashsize, a.lineparts) and os.path.exists(p["ppqt"]):
+            return p
+    for p in cands:
+        try:
+            os.makedirs(p["dir"], exist_ok=True)
+            st = os.statvfs(p["dir"])
+            if st.f_bavail * st.f_frsize >= need * 1.02:
+                return p
+        except OSError:
+            pass
+    return cands[0]
 
 
 def ensure_index_files(a, inp, device_index):
